@@ -1,0 +1,158 @@
+/*
+ * ebfi_b200.h — C ABI of the B200-native event-frame alignment kernels.
+ *
+ * This is the drop-in boundary for the three hot-path operators of
+ * WarranWeng/EBFI-BE:
+ *
+ *   - DCNv2 modulated deformable convolution, forward + backward
+ *       replaces  _ext.dcn_v2_forward / _ext.dcn_v2_backward
+ *       (reference: models/DCNv2/src/dcn_v2.h:9-92, vision.cpp:4-9,
+ *        src/cuda/dcn_v2_cuda.cu:20-216, src/cuda/dcn_v2_im2col_cuda.cu:125-402)
+ *   - FAC KernelConv2D per-pixel K x K filter, forward + backward
+ *       replaces  kernelconv2d_cuda.forward / kernelconv2d_cuda.backward
+ *       (reference: models/FAC/kernelconv2d/KernelConv2D_cuda.cpp:10-61,
+ *        KernelConv2D_kernel.cu:25-204)
+ *   - event -> image / voxel / polarity-stack encoders
+ *       replaces the index_put_ scatters of dataloader/encodings.py:243-377
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer unless its name ends in `_host`.
+ *   - Tensors are dense, row-major NCHW fp32 exactly as the reference's
+ *     `data_ptr<float>()` callers hand them over (dcn_v2_cuda.cu:79-86,
+ *     KernelConv2D_kernel.cu:68-77).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *     Nothing here synchronises the stream or the device.
+ *   - Return value: 0 on success, a negative EBFI_ERR_* otherwise; no C++
+ *     exception ever crosses this boundary. ebfi_last_error() returns a
+ *     thread-local, human readable message for the last failing call.
+ *   - There is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef EBFI_B200_H_
+#define EBFI_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EBFI_OK               0
+#define EBFI_ERR_INVALID     -1   /* bad shape / null pointer / unsupported argument */
+#define EBFI_ERR_CUDA        -2   /* a CUDA runtime call or kernel launch failed */
+#define EBFI_ERR_WORKSPACE   -3   /* workspace too small (query the *_workspace_bytes fn) */
+#define EBFI_ERR_UNSUPPORTED -4   /* valid request this build does not implement */
+
+#define EBFI_ABI_VERSION 1
+
+/* ---- library ---------------------------------------------------------------- */
+
+int         ebfi_abi_version(void);
+const char *ebfi_last_error(void);
+/* Compute capability major*10+minor of the current device, or a negative error. */
+int         ebfi_device_arch(void);
+
+/* ---- DCNv2 modulated deformable convolution --------------------------------- */
+
+/* Geometry of one call; same fields, same meaning and same order as the integer
+ * tail of _ext.dcn_v2_forward (models/DCNv2/src/dcn_v2.h:9-23). */
+typedef struct ebfi_dcn_geom {
+    int batch, channels, height, width;   /* input  (B, C, H, W)                */
+    int channels_out;                     /* weight (Cout, C, kernel_h, kernel_w) */
+    int kernel_h, kernel_w;
+    int stride_h, stride_w;
+    int pad_h, pad_w;
+    int dilation_h, dilation_w;
+    int deformable_group;                 /* offset (B, 2*dg*kh*kw, Ho, Wo); mask (B, dg*kh*kw, Ho, Wo) */
+} ebfi_dcn_geom;
+
+/* Output spatial size, formula of dcn_v2_cuda.cu:64-65. Returns EBFI_ERR_INVALID
+ * when the geometry is inconsistent (non-positive sizes, C % dg != 0, ...). */
+int ebfi_dcnv2_output_size(const ebfi_dcn_geom *g, int *height_out, int *width_out);
+
+/* Scratch the backward pass needs (per-CTA grad_weight / grad_bias partials and
+ * the col-grad staging buffer). The forward pass needs none: the column buffer
+ * of the reference (dcn_v2_cuda.cu:68) never exists in HBM here. */
+size_t ebfi_dcnv2_backward_workspace_bytes(const ebfi_dcn_geom *g);
+
+/* out[b,co,h,w] = bias[co] + sum_{c,i,j} weight[co,c,i,j] * mask * bilinear(input[b,c], ...)
+ * Replaces dcn_v2_cuda_forward (dcn_v2_cuda.cu:20-95). `output` is written in
+ * full (no pre-zeroing needed). */
+int ebfi_dcnv2_forward(void *stream, const ebfi_dcn_geom *g,
+                       const float *input, const float *weight, const float *bias,
+                       const float *offset, const float *mask,
+                       float *output);
+
+/* All five gradients of dcn_v2_cuda_backward (dcn_v2_cuda.cu:97-216), every
+ * output written in full. grad_offset / grad_mask / grad_weight / grad_bias are
+ * reduced in a fixed order (bit-reproducible run to run).
+ * Reference quirk kept on purpose: the grad_input scatter uses pad_h for BOTH
+ * paddings (dcn_v2_im2col_cuda.cu:368 passes `pad_h, pad_h`). */
+int ebfi_dcnv2_backward(void *stream, const ebfi_dcn_geom *g,
+                        const float *input, const float *weight, const float *bias,
+                        const float *offset, const float *mask,
+                        const float *grad_output,
+                        float *grad_input, float *grad_offset, float *grad_mask,
+                        float *grad_weight, float *grad_bias,
+                        void *workspace, size_t workspace_bytes);
+
+/* ---- FAC KernelConv2D ------------------------------------------------------- */
+
+/* input  : (B, C, H+K-1, W+K-1)   already padded by the caller (KernelConv2D.py:82-86)
+ * kernel : (B, C*K*K, H, W)       channel order c*K*K + ky*K + kx (KernelConv2D_kernel.cu:47)
+ * output : (B, C, H, W)           every element written
+ * Replaces KernelConv2D_forward_cuda (KernelConv2D_cuda.cpp:10-30). */
+int ebfi_fac_forward(void *stream, const float *input, const float *kernel, float *output,
+                     int batch, int channels, int height_out, int width_out, int kernel_size);
+
+/* grad_input  : (B, C, H+K-1, W+K-1), grad_kernel : (B, C*K*K, H, W); both written
+ * in full — the caller's zero fill (KernelConv2D.py:50-51) is not relied upon.
+ * One fused pass: grad_output and kernel are each read once.
+ * Replaces KernelConv2D_backward_cuda (KernelConv2D_cuda.cpp:32-56). */
+int ebfi_fac_backward(void *stream, const float *input, const float *kernel,
+                      const float *grad_output, float *grad_input, float *grad_kernel,
+                      int batch, int channels, int height_out, int width_out, int kernel_size);
+
+/* ---- event encoders --------------------------------------------------------- */
+
+/* Coordinate / timestamp arrays may be fp32 or fp64, like the tensors the
+ * datasets build (dataloader/h5dataset.py:327-349 yields fp64). */
+#define EBFI_F32 0
+#define EBFI_F64 1
+
+/* events_to_image (dataloader/encodings.py:243-268).
+ *   img[(long)ys[i], (long)xs[i]] += ps[i]   for in-range events;
+ * out-of-range events get xs=ys=ps=0 written back IN PLACE when `write_back`
+ * is non-zero (that is what the reference does to its arguments, :254-256).
+ * `img` (H, W) fp32 is ACCUMULATED into; the caller zero-fills it.
+ * `binary` != 0 gives events_to_mask (:353-377): img[...] = |ps| (last writer wins;
+ * all writers must then carry the same |ps| for a reproducible result). */
+int ebfi_events_to_image(void *stream, void *xs, void *ys, float *ps, int coord_dtype,
+                         int64_t n_events, int height, int width,
+                         float *img, int write_back, int binary);
+
+/* events_to_voxel (encodings.py:271-286): temporal-bilinear voxel grid.
+ *   t = ts[i] * (num_bins-1);  voxel[b] += ps[i] * max(0, 1 - |t - b|)
+ * xs, ys, ts share `dtype`; ps is fp32. Out-of-range events follow the
+ * reference's in-place rule: they are dropped from bin 0 and land on pixel
+ * (0,0) for bins >= 1 (a side effect of :254-256 being applied once per bin).
+ * voxel : (num_bins, H, W) fp32, accumulated into (caller zero-fills). */
+int ebfi_events_to_voxel(void *stream, void *xs, void *ys, const void *ts, const float *ps,
+                         int dtype, int64_t n_events, int num_bins, int height, int width,
+                         float *voxel, int write_back);
+
+/* events_to_stack (encodings.py:307-350): per-bin positive / negative counts.
+ * The bin boundaries are found on the device with the reference's own binary
+ * search (encodings.py:77-99), so boundary-equal timestamps are counted in both
+ * adjacent bins exactly like the reference does.
+ * stack : (2, num_bins, H, W) fp32, accumulated into (caller zero-fills).
+ * bounds : (2*num_bins) int64 scratch, receives [beg_0,end_0,beg_1,end_1,...].
+ * The early-out `ts.sum()==0 or len<=3` (:319-320) is the host wrapper's job. */
+int ebfi_events_to_stack(void *stream, void *xs, void *ys, const void *ts, const float *ps,
+                         int dtype, int64_t n_events, int num_bins, int height, int width,
+                         float *stack, int64_t *bounds, int write_back);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EBFI_B200_H_ */

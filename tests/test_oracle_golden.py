@@ -1,0 +1,89 @@
+"""CPU: pin the oracle (oracle/liboracle.so) against the reference's golden vectors.
+
+The vectors in tests/golden/ were produced by the reference itself (see
+tests/golden/make_golden.py): its CPU DCNv2 build for the five gradients,
+torchvision for the DCN forward (the reference CPU forward returns uninitialised
+memory), dataloader/encodings.py for the encoders, and an F.unfold/autograd
+restatement for FAC (no reference CPU path exists).
+"""
+import numpy as np
+import pytest
+
+from conftest import (DCN_CASES, EVENT_CASES, FAC_CASES, FWD_TOL, GRAD_TOL, load_golden, rel_err)
+
+
+def _geom(g):
+    kh, kw, sh, sw, ph, pw, dh, dw, dg = (int(v) for v in g["geom"])
+    return (sh, sw), (ph, pw), (dh, dw), dg
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+@pytest.mark.parametrize("case", DCN_CASES + ["dcn_zero_offset"])
+def test_dcn_forward_matches_reference(oracle, case, precision):
+    g = load_golden(case)
+    s, p, d, dg = _geom(g)
+    out = oracle.dcn_forward(g["input"], g["offset"], g["mask"], g["weight"], g["bias"], s, p, d, dg,
+                             precision)
+    assert rel_err(out, g["output"]) < FWD_TOL
+
+
+def test_dcn_zero_offset_known_answer(oracle):
+    # testcuda.py:32-67 — identity weights, zero offsets, mask 0.5  =>  2*out == input
+    g = load_golden("dcn_zero_offset")
+    s, p, d, dg = _geom(g)
+    out = oracle.dcn_forward(g["input"], g["offset"], g["mask"], g["weight"], g["bias"], s, p, d, dg, "f32")
+    assert np.abs(2 * out - g["input"]).max() < 1e-10
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+@pytest.mark.parametrize("case", DCN_CASES)
+def test_dcn_backward_matches_reference_cpu_build(oracle, case, precision):
+    g = load_golden(case)
+    s, p, d, dg = _geom(g)
+    grads = oracle.dcn_backward(g["input"], g["offset"], g["mask"], g["weight"], g["bias"],
+                                g["grad_output"], s, p, d, dg, precision)
+    for name, got in zip(["grad_input", "grad_offset", "grad_mask", "grad_weight", "grad_bias"], grads):
+        assert rel_err(got, g[name]) < GRAD_TOL, name
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+@pytest.mark.parametrize("case", FAC_CASES)
+def test_fac_matches_unfold_restatement(oracle, case, precision):
+    g = load_golden(case)
+    K = int(g["K"])
+    out = oracle.fac_forward(g["input"], g["kernel"], K, precision)
+    assert rel_err(out, g["output"]) < FWD_TOL
+    gi, gk = oracle.fac_backward(g["input"], g["kernel"], g["grad_output"], K, precision)
+    assert rel_err(gi, g["grad_input"]) < GRAD_TOL
+    assert rel_err(gk, g["grad_kernel"]) < GRAD_TOL
+
+
+@pytest.mark.parametrize("case", EVENT_CASES)
+def test_event_encoders_bit_exact(oracle, case):
+    g = load_golden(case)
+    H, W = (int(v) for v in g["sensor"])
+    img, xs, ys, ps = oracle.events_to_image(g["xs"], g["ys"], g["ps"], (H, W))
+    assert np.array_equal(img, g["image"])
+    # the reference zeroes out-of-range events in its arguments (encodings.py:254-256)
+    assert np.array_equal(xs, g["image_xs"]) and np.array_equal(ys, g["image_ys"])
+    assert np.array_equal(ps, g["image_ps"])
+    msk, *_ = oracle.events_to_image(g["xs"], g["ys"], g["ps"], (H, W), binary=True)
+    assert np.array_equal(msk, g["mask"])
+    if "voxel5" in g:
+        vox, xs, ys = oracle.events_to_voxel(g["xs"], g["ys"], g["ts"], g["ps"], 5, (H, W))
+        assert np.array_equal(vox, g["voxel5"])
+        assert np.array_equal(xs, g["voxel_xs"]) and np.array_equal(ys, g["voxel_ys"])
+    for nb in (4, 16):
+        st, xs, ys, _ = oracle.events_to_stack(g["xs"], g["ys"], g["ts"], g["ps"], nb, (H, W))
+        assert np.array_equal(st, g[f"stack{nb}"]), nb
+        assert np.array_equal(xs, g[f"stack{nb}_xs"]) and np.array_equal(ys, g[f"stack{nb}_ys"])
+
+
+def test_event_stack_degenerate(oracle):
+    g = load_golden("events_degenerate")
+    z = np.zeros(5, np.float32)
+    st, *_ = oracle.events_to_stack(z, z, z, np.ones(5, np.float32), 3, (4, 4))
+    assert np.array_equal(st, g["stack_tssum0"])
+    a = np.array([1, 2, 3], np.float32)
+    st, *_ = oracle.events_to_stack(a, a, np.array([0, .5, 1], np.float32), np.ones(3, np.float32), 3, (4, 4))
+    assert np.array_equal(st, g["stack_len3"])
