@@ -1,0 +1,480 @@
+// dcn.cu — DCNv2 modulated deformable convolution, forward + backward, for sm_100a.
+//
+// Replaces dcn_v2_cuda_forward / dcn_v2_cuda_backward (models/DCNv2/src/cuda/dcn_v2_cuda.cu:20-216)
+// and the three SIMT kernels behind them (src/cuda/dcn_v2_im2col_cuda.cu:125-327).
+//
+// What is different from the reference, structurally:
+//   * The column buffer (B, C*kh*kw, Ho*Wo) — 151 MB at the benchmark shape, written and read
+//     back by the reference (dcn_v2_cuda.cu:68,78-92) — never exists in HBM. A CTA samples a
+//     [k-chunk x pixel-tile] slab straight into shared memory and contracts it with the
+//     weights in the same kernel.
+//   * Offsets and masks are read once per (pixel, tap, group) instead of once per channel
+//     (the reference re-reads them for each of the 8 channels of a group, im2col_cuda.cu:168-173).
+//   * Backward is ONE pass over the pixels per deformable group: col-grad GEMM, coordinate /
+//     mask gradients, grad_input scatter, the recomputed columns and the grad_weight partial
+//     all come from the same slab. The reference loops over the batch on the host and runs
+//     3 kernels + 3 GEMMs per sample, sampling twice (dcn_v2_cuda.cu:150-211).
+//   * grad_offset / grad_mask are owned by one thread each (no atomics and none of the reference's
+//     duplicated Δh/Δw bilinear work, im2col_cuda.cu:283-320);
+//     grad_weight / grad_bias are per-CTA partials reduced in a fixed order.
+//
+// Arithmetic follows the reference exactly where it is observable: the (-1, H) x (-1, W)
+// sampling window (im2col_cuda.cu:180), per-corner bounds (:38-48), the coordinate weights
+// (:82-123), and the pad_h-for-both-paddings quirk of the grad_input scatter (:368).
+#include "common.cuh"
+
+#include <algorithm>
+
+namespace {
+
+using ebfi::ceil_div;
+
+constexpr int TP = 64;        // output pixels per tile
+constexpr int COT = 64;       // output channels per tile
+constexpr int KC_MAX = 96;    // rows of the sampled slab (channels-in-chunk * kh*kw)
+constexpr int NT = 256;       // threads per CTA
+constexpr int TPP = TP + 1;   // padded pitch of the backward slab (scalar, conflict-free by row)
+constexpr int GP = TP + 1;    // padded pitch of the grad_output tile
+
+struct DcnDims {
+    int B, C, H, W, Co, Ho, Wo;
+    int kh, kw, sh, sw, ph, pw, dh, dw, dg;
+    int cpg;          // channels per deformable group
+    int cch;          // channels per chunk (<= cpg, cch*KK <= KC_MAX)
+    int nchunk;       // chunks per group
+    int KK;           // kh*kw
+    int ntile;        // pixel tiles per sample
+};
+
+// One bilinear tap: corner indices, validity and weights (im2col_cuda.cu:25-54, :180).
+struct Tap {
+    int i00, i01, i10, i11;    // plane offsets of the four corners
+    bool c00, c01, c10, c11;   // corner inside the image AND sample inside the window
+    float hy, hx, ly, lx;
+};
+
+__device__ __forceinline__ Tap make_tap(float y, float x, int H, int W)
+{
+    Tap t;
+    const bool inside = (y > -1.f) && (x > -1.f) && (y < (float)H) && (x < (float)W);
+    const float fy = floorf(y), fx = floorf(x);
+    const int y0 = (int)fy, x0 = (int)fx;
+    t.ly = y - fy; t.lx = x - fx;
+    t.hy = 1.f - t.ly; t.hx = 1.f - t.lx;
+    const bool ya = y0 >= 0, yb = y0 + 1 <= H - 1, xa = x0 >= 0, xb = x0 + 1 <= W - 1;
+    t.c00 = inside && ya && xa; t.c01 = inside && ya && xb;
+    t.c10 = inside && yb && xa; t.c11 = inside && yb && xb;
+    t.i00 = y0 * W + x0; t.i01 = t.i00 + 1; t.i10 = t.i00 + W; t.i11 = t.i10 + 1;
+    return t;
+}
+
+__device__ __forceinline__ void tap_coords(const DcnDims &d, const float *__restrict__ off_bg,
+                                           const float *__restrict__ mask_bg, int t, int pix,
+                                           float &y, float &x, float &xq, float &m)
+{
+    const size_t plane = (size_t)d.Ho * d.Wo;
+    const int ho = pix / d.Wo, wo = pix - ho * d.Wo;
+    const int i = t / d.kw, j = t - i * d.kw;
+    const float oy = __ldg(off_bg + (size_t)(2 * t) * plane + pix);
+    const float ox = __ldg(off_bg + (size_t)(2 * t + 1) * plane + pix);
+    m = __ldg(mask_bg + (size_t)t * plane + pix);
+    y = (float)(ho * d.sh - d.ph + i * d.dh) + oy;
+    x = (float)(wo * d.sw - d.pw + j * d.dw) + ox;
+    xq = (float)(wo * d.sw - d.ph + j * d.dw) + ox;   // the scatter's x (pad_h quirk, :368)
+}
+
+// ------------------------------------------------------------------ forward ---
+// grid = (pixel tiles per sample, Cout tiles, B). Each CTA walks all deformable groups /
+// channel chunks, sampling a [KC x TP] slab into smem and accumulating a [COT x TP] output
+// tile in registers (4 co x 4 px per thread).
+__global__ void __launch_bounds__(NT)
+dcn_fwd_kernel(const float *__restrict__ input, const float *__restrict__ weight,
+               const float *__restrict__ bias, const float *__restrict__ offset,
+               const float *__restrict__ mask, float *__restrict__ output, DcnDims d)
+{
+    extern __shared__ __align__(16) float smem[];
+    float *col_s = smem;                         // [KC_MAX][TP]
+    float *w_s = smem + KC_MAX * TP;             // [KC_MAX][COT]
+
+    const int tid = threadIdx.x;
+    const int b = blockIdx.z, co_base = blockIdx.y * COT, pix_base = blockIdx.x * TP;
+    const int npix = d.Ho * d.Wo;
+    const size_t plane = (size_t)npix, in_plane = (size_t)d.H * d.W;
+    const int Kdim = d.C * d.KK;
+    const int pq = tid % 16, cq = tid / 16;      // 4 px x 4 co per thread
+
+    float acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+
+    for (int g = 0; g < d.dg; ++g) {
+        const float *off_bg = offset + ((size_t)b * d.dg + g) * 2 * d.KK * plane;
+        const float *mask_bg = mask + ((size_t)b * d.dg + g) * d.KK * plane;
+        for (int ch = 0; ch < d.nchunk; ++ch) {
+            const int c0 = g * d.cpg + ch * d.cch;
+            const int nc = min(d.cch, d.cpg - ch * d.cch);
+            const int KC = nc * d.KK;
+            __syncthreads();                      // previous slab fully consumed
+            // weights of this chunk: w_s[kk][co] = weight[co_base+co][c0*KK + kk]
+            for (int e = tid; e < KC * COT; e += NT) {
+                const int co = e % COT, kk = e / COT;
+                w_s[kk * COT + co] = (co_base + co < d.Co)
+                    ? __ldg(weight + (size_t)(co_base + co) * Kdim + (size_t)c0 * d.KK + kk) : 0.f;
+            }
+            // sample: item = (tap, pixel), pixel fastest
+            for (int it = tid; it < d.KK * TP; it += NT) {
+                const int p = it % TP, t = it / TP, pix = pix_base + p;
+                if (pix < npix) {
+                    float y, x, xq, m;
+                    tap_coords(d, off_bg, mask_bg, t, pix, y, x, xq, m);
+                    const Tap tp = make_tap(y, x, d.H, d.W);
+                    const float w1 = tp.hy * tp.hx, w2 = tp.hy * tp.lx, w3 = tp.ly * tp.hx, w4 = tp.ly * tp.lx;
+                    const float *ip = input + ((size_t)b * d.C + c0) * in_plane;
+                    for (int cc = 0; cc < nc; ++cc, ip += in_plane) {
+                        const float v1 = tp.c00 ? __ldg(ip + tp.i00) : 0.f;
+                        const float v2 = tp.c01 ? __ldg(ip + tp.i01) : 0.f;
+                        const float v3 = tp.c10 ? __ldg(ip + tp.i10) : 0.f;
+                        const float v4 = tp.c11 ? __ldg(ip + tp.i11) : 0.f;
+                        col_s[(cc * d.KK + t) * TP + p] = (w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4) * m;
+                    }
+                } else {
+                    for (int cc = 0; cc < nc; ++cc) col_s[(cc * d.KK + t) * TP + p] = 0.f;
+                }
+            }
+            __syncthreads();
+            // contract: acc[co][px] += w_s[kk][co] * col_s[kk][px]
+#pragma unroll 4
+            for (int kk = 0; kk < KC; ++kk) {
+                const float4 a = *reinterpret_cast<const float4 *>(w_s + kk * COT + cq * 4);
+                const float4 c = *reinterpret_cast<const float4 *>(col_s + kk * TP + pq * 4);
+                const float av[4] = {a.x, a.y, a.z, a.w}, cv[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[r][q] += av[r] * cv[q];
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int co = co_base + cq * 4 + r;
+        if (co >= d.Co) continue;
+        const float bv = __ldg(bias + co);
+        float *op = output + ((size_t)b * d.Co + co) * plane;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int pix = pix_base + pq * 4 + q;
+            if (pix < npix) op[pix] = acc[r][q] + bv;
+        }
+    }
+}
+
+// ----------------------------------------------------------------- backward ---
+// grid = (splits S, dg, Cout tiles), one launch per channel chunk `ch` of the groups (one chunk
+// for every shape with channels-per-group * taps <= KC_MAX). CTA (s, g, ct) owns the k-rows of chunk `ch`
+// and walks the pixel tiles s, s+S, ... of ALL samples. For ct == 0 it produces grad_offset,
+// grad_mask, grad_input for its chunk; every ct accumulates its [COT x KC] grad_weight
+// partial in registers across all its tiles and writes it once at the end.
+// Partials: gw_part[S][Co][Kdim], gb_part[S][Co] -> dcn_reduce_partials (fixed order).
+__global__ void __launch_bounds__(NT)
+dcn_bwd_kernel(const float *__restrict__ input, const float *__restrict__ weight,
+               const float *__restrict__ offset, const float *__restrict__ mask,
+               const float *__restrict__ gout, float *__restrict__ gin,
+               float *__restrict__ goff, float *__restrict__ gmask,
+               float *__restrict__ gw_part, float *__restrict__ gb_part, DcnDims d, int ch)
+{
+    extern __shared__ __align__(16) float smem[];
+    float *slab = smem;                          // [KC_MAX][TPP]  col-grad, then columns
+    float *go_s = slab + KC_MAX * TPP;           // [COT][GP]      grad_output tile
+    float *w_s = go_s + COT * GP;                // [COT][KC_MAX]  weights of the chunk
+
+    const int tid = threadIdx.x;
+    const int S = gridDim.x, s = blockIdx.x;
+    const int g = blockIdx.y;
+    const int ct = blockIdx.z, co_base = ct * COT, nco = min(COT, d.Co - co_base);
+    const bool lead = (ct == 0);                 // this CTA also does the data gradients
+    const int c0 = g * d.cpg + ch * d.cch;
+    const int nc = min(d.cch, d.cpg - ch * d.cch);
+    const int KC = nc * d.KK, Kdim = d.C * d.KK;
+    const int npix = d.Ho * d.Wo;
+    const size_t plane = (size_t)npix, in_plane = (size_t)d.H * d.W;
+    const int n_cot = gridDim.z;
+
+    const int kq = tid % 16, cq = tid / 16;      // grad_weight: rows kq+16i, 4 co per thread
+    float gw_acc[4][KC_MAX / 16];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int i = 0; i < KC_MAX / 16; ++i) gw_acc[r][i] = 0.f;
+    float gb_acc = 0.f;                          // thread tid < nco owns bias co_base+tid
+
+    for (int tile = s; tile < d.B * d.ntile; tile += S) {
+        const int b = tile / d.ntile, pix_base = (tile % d.ntile) * TP;
+        const float *off_bg = offset + ((size_t)b * d.dg + g) * 2 * d.KK * plane;
+        const float *mask_bg = mask + ((size_t)b * d.dg + g) * d.KK * plane;
+        __syncthreads();
+        // ---- (a) col-grad slab = W_chunk^T . gO_tile, accumulated over Cout tiles (lead only)
+        if (lead) {
+            float cg[KC_MAX / 16][4];
+#pragma unroll
+            for (int i = 0; i < KC_MAX / 16; ++i)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) cg[i][q] = 0.f;
+            const int pq = tid / 16;             // 4 px per thread, rows kq+16i
+            for (int cb = 0; cb < n_cot; ++cb) {
+                const int cbase = cb * COT, ncb = min(COT, d.Co - cbase);
+                if (cb) __syncthreads();
+                for (int e = tid; e < COT * TP; e += NT) {
+                    const int p = e % TP, co = e / TP, pix = pix_base + p;
+                    go_s[co * GP + p] = (co < ncb && pix < npix)
+                        ? __ldg(gout + ((size_t)b * d.Co + cbase + co) * plane + pix) : 0.f;
+                }
+                for (int e = tid; e < COT * KC; e += NT) {
+                    const int kk = e % KC, co = e / KC;
+                    w_s[co * KC_MAX + kk] = (co < ncb)
+                        ? __ldg(weight + (size_t)(cbase + co) * Kdim + (size_t)c0 * d.KK + kk) : 0.f;
+                }
+                __syncthreads();
+                for (int co = 0; co < ncb; ++co) {
+                    float gv[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) gv[q] = go_s[co * GP + pq * 4 + q];
+#pragma unroll
+                    for (int i = 0; i < KC_MAX / 16; ++i) {
+                        const int kk = kq + 16 * i;
+                        const float wv = kk < KC ? w_s[co * KC_MAX + kk] : 0.f;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) cg[i][q] += wv * gv[q];
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < KC_MAX / 16; ++i) {
+                const int kk = kq + 16 * i;
+                if (kk < KC)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) slab[kk * TPP + pq * 4 + q] = cg[i][q];
+            }
+            __syncthreads();
+        }
+        // ---- (b) sampling: data gradients (lead) and the recomputed columns (all)
+        for (int it = tid; it < d.KK * TP; it += NT) {
+            const int p = it % TP, t = it / TP, pix = pix_base + p;
+            if (pix >= npix) {
+                for (int cc = 0; cc < nc; ++cc) slab[(cc * d.KK + t) * TPP + p] = 0.f;
+                continue;
+            }
+            float y, x, xq, m;
+            tap_coords(d, off_bg, mask_bg, t, pix, y, x, xq, m);
+            const Tap tp = make_tap(y, x, d.H, d.W);
+            const Tap tq = (d.ph == d.pw) ? tp : make_tap(y, xq, d.H, d.W);
+            const float w1 = tp.hy * tp.hx, w2 = tp.hy * tp.lx, w3 = tp.ly * tp.hx, w4 = tp.ly * tp.lx;
+            const float q1 = tq.hy * tq.hx, q2 = tq.hy * tq.lx, q3 = tq.ly * tq.hx, q4 = tq.ly * tq.lx;
+            float s_m = 0.f, s_y = 0.f, s_x = 0.f;
+            const float *ip = input + ((size_t)b * d.C + c0) * in_plane;
+            float *gp = gin + ((size_t)b * d.C + c0) * in_plane;
+            for (int cc = 0; cc < nc; ++cc, ip += in_plane, gp += in_plane) {
+                const float v1 = tp.c00 ? __ldg(ip + tp.i00) : 0.f;
+                const float v2 = tp.c01 ? __ldg(ip + tp.i01) : 0.f;
+                const float v3 = tp.c10 ? __ldg(ip + tp.i10) : 0.f;
+                const float v4 = tp.c11 ? __ldg(ip + tp.i11) : 0.f;
+                const float val = w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4;
+                float *cell = slab + (cc * d.KK + t) * TPP + p;
+                if (lead) {
+                    const float gc = *cell;
+                    s_m += gc * val;                                     // grad_mask (:311)
+                    // coordinate weights (:99-120); invalid corners already read as 0
+                    const float wy = -tp.hx * v1 - tp.lx * v2 + tp.hx * v3 + tp.lx * v4;
+                    const float wx = -tp.hy * v1 + tp.hy * v2 - tp.ly * v3 + tp.ly * v4;
+                    const float top = gc * m;
+                    s_y += wy * top;
+                    s_x += wx * top;
+                    // grad_input scatter (:236-251), x position with pad_h
+                    if (tq.c00) atomicAdd(gp + tq.i00, q1 * top);
+                    if (tq.c01) atomicAdd(gp + tq.i01, q2 * top);
+                    if (tq.c10) atomicAdd(gp + tq.i10, q3 * top);
+                    if (tq.c11) atomicAdd(gp + tq.i11, q4 * top);
+                }
+                *cell = val * m;                                          // column for grad_weight
+            }
+            if (lead) {
+                float *gy = goff + (((size_t)b * d.dg + g) * 2 * d.KK + 2 * t) * plane + pix;
+                float *gm = gmask + (((size_t)b * d.dg + g) * d.KK + t) * plane + pix;
+                if (ch == 0) { gy[0] = s_y; gy[plane] = s_x; *gm = s_m; }
+                else { gy[0] += s_y; gy[plane] += s_x; *gm += s_m; }     // chunks are separate, ordered launches
+            }
+        }
+        // ---- (c) grad_weight partial: gw[co][kk] += sum_p gO[co][p] * col[kk][p]
+        if (!lead || n_cot > 1) {
+            __syncthreads();
+            for (int e = tid; e < COT * TP; e += NT) {
+                const int p = e % TP, co = e / TP, pix = pix_base + p;
+                go_s[co * GP + p] = (co < nco && pix < npix)
+                    ? __ldg(gout + ((size_t)b * d.Co + co_base + co) * plane + pix) : 0.f;
+            }
+        }
+        __syncthreads();
+        for (int p = 0; p < TP; ++p) {
+            float gv[4], cv[KC_MAX / 16];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) gv[r] = go_s[(cq * 4 + r) * GP + p];
+#pragma unroll
+            for (int i = 0; i < KC_MAX / 16; ++i) cv[i] = (kq + 16 * i < KC) ? slab[(kq + 16 * i) * TPP + p] : 0.f;
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int i = 0; i < KC_MAX / 16; ++i) gw_acc[r][i] += gv[r] * cv[i];
+        }
+        if (g == 0 && ch == 0 && tid < nco) {
+            float sb = 0.f;
+            for (int p = 0; p < TP; ++p) sb += go_s[tid * GP + p];
+            gb_acc += sb;
+        }
+    }
+    // ---- write the per-CTA partials
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int co = co_base + cq * 4 + r;
+        if (co >= d.Co) continue;
+#pragma unroll
+        for (int i = 0; i < KC_MAX / 16; ++i) {
+            const int kk = kq + 16 * i;
+            if (kk < KC) gw_part[((size_t)s * d.Co + co) * Kdim + (size_t)c0 * d.KK + kk] = gw_acc[r][i];
+        }
+    }
+    if (g == 0 && ch == 0 && tid < nco) gb_part[(size_t)s * d.Co + co_base + tid] = gb_acc;
+}
+
+// grad_weight[e] = sum_s gw_part[s][e], grad_bias likewise — fixed order, one thread per element.
+__global__ void dcn_reduce_partials(const float *__restrict__ gw_part, const float *__restrict__ gb_part,
+                                    float *__restrict__ gw, float *__restrict__ gb, int S, int n_w, int n_b)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n_w) {
+        float a = 0.f;
+        for (int s = 0; s < S; ++s) a += gw_part[(size_t)s * n_w + e];
+        gw[e] = a;
+    } else if (e < n_w + n_b) {
+        const int c = e - n_w;
+        float a = 0.f;
+        for (int s = 0; s < S; ++s) a += gb_part[(size_t)s * n_b + c];
+        gb[c] = a;
+    }
+}
+
+int fill_dims(const ebfi_dcn_geom *q, DcnDims &d)
+{
+    EBFI_REQUIRE(q != nullptr, "dcn: null geometry");
+    int Ho = 0, Wo = 0;
+    if (ebfi_dcnv2_output_size(q, &Ho, &Wo) != EBFI_OK) return EBFI_ERR_INVALID;
+    d.B = q->batch; d.C = q->channels; d.H = q->height; d.W = q->width; d.Co = q->channels_out;
+    d.Ho = Ho; d.Wo = Wo;
+    d.kh = q->kernel_h; d.kw = q->kernel_w; d.sh = q->stride_h; d.sw = q->stride_w;
+    d.ph = q->pad_h; d.pw = q->pad_w; d.dh = q->dilation_h; d.dw = q->dilation_w;
+    d.dg = q->deformable_group;
+    d.cpg = d.C / d.dg;
+    d.KK = d.kh * d.kw;
+    if (d.KK > KC_MAX)
+        return ebfi::fail(EBFI_ERR_UNSUPPORTED, "dcn: kernel %dx%d has more than %d taps", d.kh, d.kw, KC_MAX);
+    d.cch = std::max(1, std::min(d.cpg, KC_MAX / d.KK));
+    d.nchunk = ceil_div(d.cpg, d.cch);
+    d.ntile = ceil_div(Ho * Wo, TP);
+    EBFI_REQUIRE((long)d.H * d.W < (1L << 30) && (long)Ho * Wo < (1L << 30), "dcn: plane too large");
+    EBFI_REQUIRE(d.B <= 65535 && ceil_div(d.Co, COT) <= 65535, "dcn: batch / Cout too large for the grid");
+    return EBFI_OK;
+}
+
+int bwd_splits(const DcnDims &d)
+{
+    // enough CTAs for ~2 per SM over all (group, chunk, Cout-tile) rows, never more than tiles
+    const int rows = d.dg * ceil_div(d.Co, COT);
+    int S = std::max(1, ceil_div(2 * ebfi::sm_count(), rows));
+    return std::min(S, d.B * d.ntile);
+}
+
+constexpr size_t kFwdSmem = (size_t)(KC_MAX * TP + KC_MAX * COT) * sizeof(float);
+constexpr size_t kBwdSmem = (size_t)(KC_MAX * TPP + COT * GP + COT * KC_MAX) * sizeof(float);
+
+}  // namespace
+
+extern "C" {
+
+int ebfi_dcnv2_output_size(const ebfi_dcn_geom *q, int *height_out, int *width_out)
+{
+    EBFI_REQUIRE(q && height_out && width_out, "dcn: null argument");
+    EBFI_REQUIRE(q->batch > 0 && q->channels > 0 && q->height > 0 && q->width > 0 && q->channels_out > 0,
+                 "dcn: non-positive tensor size");
+    EBFI_REQUIRE(q->kernel_h > 0 && q->kernel_w > 0 && q->stride_h > 0 && q->stride_w > 0 &&
+                 q->dilation_h > 0 && q->dilation_w > 0 && q->pad_h >= 0 && q->pad_w >= 0,
+                 "dcn: bad kernel/stride/dilation/padding");
+    EBFI_REQUIRE(q->deformable_group > 0 && q->channels % q->deformable_group == 0,
+                 "dcn: channels (%d) not divisible by deformable_group (%d)", q->channels, q->deformable_group);
+    const int Ho = (q->height + 2 * q->pad_h - (q->dilation_h * (q->kernel_h - 1) + 1)) / q->stride_h + 1;
+    const int Wo = (q->width + 2 * q->pad_w - (q->dilation_w * (q->kernel_w - 1) + 1)) / q->stride_w + 1;
+    EBFI_REQUIRE(Ho > 0 && Wo > 0, "dcn: empty output %dx%d", Ho, Wo);
+    *height_out = Ho; *width_out = Wo;
+    return EBFI_OK;
+}
+
+size_t ebfi_dcnv2_backward_workspace_bytes(const ebfi_dcn_geom *q)
+{
+    DcnDims d{};
+    if (fill_dims(q, d) != EBFI_OK) return 0;
+    const size_t S = (size_t)bwd_splits(d);
+    return S * ((size_t)d.Co * d.C * d.KK + d.Co) * sizeof(float) + 256;
+}
+
+int ebfi_dcnv2_forward(void *stream, const ebfi_dcn_geom *q, const float *input, const float *weight,
+                       const float *bias, const float *offset, const float *mask, float *output)
+{
+    DcnDims d{};
+    if (int rc = fill_dims(q, d)) return rc;
+    EBFI_REQUIRE(input && weight && bias && offset && mask && output, "dcn_forward: null pointer");
+    cudaStream_t st = ebfi::as_stream(stream);
+    EBFI_CUDA_OK(cudaFuncSetAttribute(dcn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
+    dim3 grid(d.ntile, ceil_div(d.Co, COT), d.B);
+    dcn_fwd_kernel<<<grid, NT, kFwdSmem, st>>>(input, weight, bias, offset, mask, output, d);
+    EBFI_LAUNCH_OK("dcn_fwd_kernel");
+    return EBFI_OK;
+}
+
+int ebfi_dcnv2_backward(void *stream, const ebfi_dcn_geom *q, const float *input, const float *weight,
+                        const float *bias, const float *offset, const float *mask,
+                        const float *grad_output, float *grad_input, float *grad_offset,
+                        float *grad_mask, float *grad_weight, float *grad_bias,
+                        void *workspace, size_t workspace_bytes)
+{
+    (void)bias;
+    DcnDims d{};
+    if (int rc = fill_dims(q, d)) return rc;
+    EBFI_REQUIRE(input && weight && offset && mask && grad_output && grad_input && grad_offset &&
+                 grad_mask && grad_weight && grad_bias, "dcn_backward: null pointer");
+    cudaStream_t st = ebfi::as_stream(stream);
+    const int S = bwd_splits(d);
+    const size_t n_w = (size_t)d.Co * d.C * d.KK, n_b = (size_t)d.Co;
+    const size_t need = (size_t)S * (n_w + n_b) * sizeof(float);
+    if (!workspace || workspace_bytes < need)
+        return ebfi::fail(EBFI_ERR_WORKSPACE, "dcn_backward: workspace %zu < %zu bytes", workspace_bytes, need);
+    float *gw_part = static_cast<float *>(workspace);
+    float *gb_part = gw_part + (size_t)S * n_w;
+    EBFI_CUDA_OK(cudaFuncSetAttribute(dcn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
+    EBFI_CUDA_OK(cudaMemsetAsync(grad_input, 0, (size_t)d.B * d.C * d.H * d.W * sizeof(float), st));
+    const int n_cot = ceil_div(d.Co, COT);
+    // Chunks of one group accumulate into the same grad_offset / grad_mask elements; separate,
+    // stream-ordered launches keep that read-modify-write race-free. nchunk is 1 unless
+    // channels-per-group * taps exceeds the KC_MAX-row slab.
+    for (int ch = 0; ch < d.nchunk; ++ch) {
+        dim3 grid(S, d.dg, n_cot);
+        dcn_bwd_kernel<<<grid, NT, kBwdSmem, st>>>(input, weight, offset, mask, grad_output, grad_input,
+                                                   grad_offset, grad_mask, gw_part, gb_part, d, ch);
+        EBFI_LAUNCH_OK("dcn_bwd_kernel");
+    }
+    const int n = (int)(n_w + n_b);
+    dcn_reduce_partials<<<ceil_div(n, 256), 256, 0, st>>>(gw_part, gb_part, grad_weight, grad_bias, S, (int)n_w, (int)n_b);
+    EBFI_LAUNCH_OK("dcn_reduce_partials");
+    return EBFI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,275 @@
+// events.cu — event -> image / voxel-grid / polarity-stack encoders for sm_100a.
+//
+// GPU scatter kernels for the bins of /root/reference/dataloader/encodings.py
+// (events_to_image :243-268, events_to_voxel :271-286, events_to_stack :307-350,
+// events_to_mask :353-377). The reference runs these on the CPU in DataLoader workers as
+// B (or 2B) full passes of index_put_(accumulate=True) over all events; here ONE pass reads
+// each event once (struct-of-arrays, coalesced) and issues at most 2 (voxel) / 2 per
+// containing bin (stack) reductions into the L2-resident grid.
+//
+// Reference side effects that are observable in the OUTPUT are reproduced:
+//   * events_to_image zeroes out-of-range events in the caller's tensors (:254-256). Because
+//     events_to_voxel calls it once per bin with the same xs/ys, an out-of-range event is
+//     dropped from bin 0 but lands on pixel (0,0) in bins >= 1; events_to_stack shows the
+//     same effect between its positive and negative pass and between overlapping bins.
+//   * events_to_stack finds bin boundaries with binary_search_torch_tensor (:77-99), whose
+//     early exits decide how duplicate / boundary-equal timestamps are split; the same
+//     search runs here on the device.
+// Polarity-count outputs (stack, channels, image of +-1) are sums of small integers and are
+// therefore exact and order-independent in fp32; the temporally-weighted voxel grid is
+// accumulated with fp32 reductions whose order is not fixed (|diff| vs the CPU's sequential
+// order is a few ulp; see tests for the bound).
+#include "common.cuh"
+
+namespace {
+
+using ebfi::ceil_div;
+
+template <typename T> __device__ __forceinline__ bool out_of_range(T x, T y, int H, int W)
+{
+    // (xs >= W) + (xs < 0) + (ys >= H) + (ys < 0), encodings.py:251-253
+    return (x >= (T)W) || (x < (T)0) || (y >= (T)H) || (y < (T)0);
+}
+
+__device__ __forceinline__ void red_add(float *p, float v)
+{
+    if (v != 0.f) atomicAdd(p, v);     // result unused -> RED.ADD.F32; adding +-0 is a no-op
+}
+
+template <typename T>
+__global__ void events_image_kernel(T *__restrict__ xs, T *__restrict__ ys, float *__restrict__ ps,
+                                    int64_t n, int H, int W, float *__restrict__ img, int write_back)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const T x = xs[i], y = ys[i];
+        if (out_of_range(x, y, H, W)) {
+            if (write_back) { xs[i] = (T)0; ys[i] = (T)0; ps[i] = 0.f; }
+            continue;
+        }
+        red_add(img + (int64_t)y * W + (int64_t)x, ps[i]);   // .long() truncation, :262-265
+    }
+}
+
+// events_to_mask: index_put_(accumulate=False) on the CPU = the LAST event of a pixel wins.
+// Pass 1 records the largest event index per pixel, pass 2 lets exactly that event write.
+// Out-of-range events take part at pixel (0,0) with value 0, as in the reference.
+template <typename T>
+__global__ void events_mask_last_kernel(const T *__restrict__ xs, const T *__restrict__ ys, int64_t n,
+                                        int H, int W, long long *__restrict__ last)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const T x = xs[i], y = ys[i];
+        const int64_t pix = out_of_range(x, y, H, W) ? 0 : (int64_t)y * W + (int64_t)x;
+        atomicMax(last + pix, (long long)i);
+    }
+}
+
+template <typename T>
+__global__ void events_mask_write_kernel(T *__restrict__ xs, T *__restrict__ ys, float *__restrict__ ps,
+                                         int64_t n, int H, int W, const long long *__restrict__ last,
+                                         float *__restrict__ img, int write_back)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const T x = xs[i], y = ys[i];
+        const bool oob = out_of_range(x, y, H, W);
+        const int64_t pix = oob ? 0 : (int64_t)y * W + (int64_t)x;
+        if (last[pix] == (long long)i) img[pix] = oob ? 0.f : fabsf(ps[i]);
+        if (oob && write_back) { xs[i] = (T)0; ys[i] = (T)0; ps[i] = 0.f; }
+    }
+}
+
+// Temporal-bilinear weight of bin b, evaluated operation by operation in the dtype of ts like
+// the tensor expression `ps * max(0, 1 - |ts*(bins-1) - b|)` (:279-283); no FMA contraction.
+__device__ __forceinline__ float voxel_value(float t_scaled, int b, float p)
+{
+    const float k = __fsub_rn(1.0f, fabsf(__fsub_rn(t_scaled, (float)b)));
+    return __fmul_rn(p, k > 0.f ? k : 0.f);
+}
+__device__ __forceinline__ float voxel_value(double t_scaled, int b, float p)
+{
+    const double k = __dsub_rn(1.0, fabs(__dsub_rn(t_scaled, (double)b)));
+    return (float)__dmul_rn((double)p, k > 0.0 ? k : 0.0);
+}
+__device__ __forceinline__ float scale_ts(float t, int bins) { return __fmul_rn(t, (float)(bins - 1)); }
+__device__ __forceinline__ double scale_ts(double t, int bins) { return __dmul_rn(t, (double)(bins - 1)); }
+
+template <typename T>
+__global__ void events_voxel_kernel(T *__restrict__ xs, T *__restrict__ ys, const T *__restrict__ ts,
+                                    const float *__restrict__ ps, int64_t n, int bins, int H, int W,
+                                    float *__restrict__ voxel, int write_back)
+{
+    const int64_t plane = (int64_t)H * W;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const T x = xs[i], y = ys[i];
+        const bool oob = out_of_range(x, y, H, W);
+        const int64_t pix = oob ? 0 : (int64_t)y * W + (int64_t)x;
+        const T tsc = scale_ts(ts[i], bins);
+        const float p = ps[i];
+        // only bins floor(t), floor(t)+1 can carry a non-zero weight
+        const int b0 = (int)floor((double)tsc);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int b = b0 + k;
+            if (b < 0 || b >= bins) continue;
+            if (oob && b == 0) continue;            // zeroed by the first bin's events_to_image call
+            red_add(voxel + (int64_t)b * plane + pix, voxel_value(tsc, b, p));
+        }
+        if (oob && write_back) { xs[i] = (T)0; ys[i] = (T)0; }
+    }
+}
+
+// binary_search_torch_tensor (:77-99) for all 2*bins boundaries, one thread each.
+template <typename T>
+__global__ void stack_bounds_kernel(const T *__restrict__ ts, int64_t n, int bins, int64_t *__restrict__ bounds)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 2 * bins) return;
+    const int bi = e >> 1, right = e & 1;
+    // dt = ts[-1]-ts[0]+1e-6; delta = dt/B; tstart = ts[0]+delta*bi; tend = tstart+delta (:324-329),
+    // every step rounded in the dtype of ts
+    const T t0 = ts[0];
+    const T dt = (T)((T)(ts[n - 1] - t0) + (T)1e-6);
+    const T delta = dt / (T)bins;
+    T target;
+    if (sizeof(T) == 4) {
+        const float a = __fadd_rn((float)t0, __fmul_rn((float)delta, (float)bi));
+        target = (T)(right ? __fadd_rn(a, (float)delta) : a);
+    } else {
+        const double a = __dadd_rn((double)t0, __dmul_rn((double)delta, (double)bi));
+        target = (T)(right ? __dadd_rn(a, (double)delta) : a);
+    }
+    int64_t l = 0, r = n - 1, res = -2;
+    while (l <= r) {
+        if (ts[l] == target) { res = l; break; }
+        if (ts[r] == target) { res = r; break; }
+        const int64_t mid = l + (r - l) / 2;
+        const T mv = ts[mid];
+        if (mv == target) { res = mid; break; }
+        else if (mv < target) l = mid + 1;
+        else r = mid - 1;
+    }
+    if (res == -2) res = right ? r : l;
+    bounds[e] = right ? res + 1 : res;
+}
+
+template <typename T>
+__global__ void events_stack_kernel(T *__restrict__ xs, T *__restrict__ ys, const float *__restrict__ ps,
+                                    int64_t n, int bins, int H, int W, const int64_t *__restrict__ bounds,
+                                    float *__restrict__ stack, int write_back)
+{
+    extern __shared__ int64_t s_bounds[];
+    for (int e = threadIdx.x; e < 2 * bins; e += blockDim.x) s_bounds[e] = bounds[e];
+    __syncthreads();
+    const int64_t plane = (int64_t)H * W;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const T x = xs[i], y = ys[i];
+        const bool oob = out_of_range(x, y, H, W);
+        const int64_t pix = oob ? 0 : (int64_t)y * W + (int64_t)x;
+        const float p = ps[i];
+        const float vpos = p * (p < 0.f ? 0.f : p);    // ps * mask_pos, :333-336
+        const float vneg = p * (p > 0.f ? 0.f : p);    // ps * mask_neg
+        bool seen = false;
+        for (int b = 0; b < bins; ++b) {
+            if (i < s_bounds[2 * b] || i >= s_bounds[2 * b + 1]) continue;
+            // first slice that holds an out-of-range event: its positive pass sees value 0
+            if (!(oob && !seen)) red_add(stack + (int64_t)b * plane + pix, vpos);
+            red_add(stack + ((int64_t)bins + b) * plane + pix, vneg);
+            seen = true;
+        }
+        if (oob && seen && write_back) { xs[i] = (T)0; ys[i] = (T)0; }
+    }
+}
+
+unsigned grid_for(int64_t n)
+{
+    const int64_t want = ceil_div(n, (int64_t)256);
+    const int64_t cap = (int64_t)ebfi::sm_count() * 16;
+    return (unsigned)(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+int check_common(const void *xs, const void *ys, int dtype, int64_t n, int H, int W)
+{
+    EBFI_REQUIRE(dtype == EBFI_F32 || dtype == EBFI_F64, "events: dtype must be EBFI_F32 or EBFI_F64");
+    EBFI_REQUIRE(n >= 0 && H > 0 && W > 0, "events: bad sizes n=%lld H=%d W=%d", (long long)n, H, W);
+    EBFI_REQUIRE(n == 0 || (xs && ys), "events: null coordinate array");
+    return EBFI_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ebfi_events_to_image(void *stream, void *xs, void *ys, float *ps, int coord_dtype, int64_t n,
+                         int height, int width, float *img, int write_back)
+{
+    if (int rc = check_common(xs, ys, coord_dtype, n, height, width)) return rc;
+    EBFI_REQUIRE(img && (n == 0 || ps), "events_to_image: null pointer");
+    if (n == 0) return EBFI_OK;
+    cudaStream_t st = ebfi::as_stream(stream);
+    if (coord_dtype == EBFI_F32)
+        events_image_kernel<float><<<grid_for(n), 256, 0, st>>>((float *)xs, (float *)ys, ps, n, height, width, img, write_back);
+    else
+        events_image_kernel<double><<<grid_for(n), 256, 0, st>>>((double *)xs, (double *)ys, ps, n, height, width, img, write_back);
+    EBFI_LAUNCH_OK("events_image_kernel");
+    return EBFI_OK;
+}
+
+int ebfi_events_to_mask(void *stream, void *xs, void *ys, float *ps, int coord_dtype, int64_t n,
+                        int height, int width, float *img, int64_t *last_index_scratch, int write_back)
+{
+    if (int rc = check_common(xs, ys, coord_dtype, n, height, width)) return rc;
+    EBFI_REQUIRE(img && last_index_scratch && (n == 0 || ps), "events_to_mask: null pointer");
+    if (n == 0) return EBFI_OK;
+    cudaStream_t st = ebfi::as_stream(stream);
+    long long *last = reinterpret_cast<long long *>(last_index_scratch);
+    EBFI_CUDA_OK(cudaMemsetAsync(last, 0xFF, (size_t)height * width * sizeof(long long), st));   // -1
+    if (coord_dtype == EBFI_F32) {
+        events_mask_last_kernel<float><<<grid_for(n), 256, 0, st>>>((float *)xs, (float *)ys, n, height, width, last);
+        events_mask_write_kernel<float><<<grid_for(n), 256, 0, st>>>((float *)xs, (float *)ys, ps, n, height, width, last, img, write_back);
+    } else {
+        events_mask_last_kernel<double><<<grid_for(n), 256, 0, st>>>((double *)xs, (double *)ys, n, height, width, last);
+        events_mask_write_kernel<double><<<grid_for(n), 256, 0, st>>>((double *)xs, (double *)ys, ps, n, height, width, last, img, write_back);
+    }
+    EBFI_LAUNCH_OK("events_mask kernels");
+    return EBFI_OK;
+}
+
+int ebfi_events_to_voxel(void *stream, void *xs, void *ys, const void *ts, const float *ps, int dtype,
+                         int64_t n, int num_bins, int height, int width, float *voxel, int write_back)
+{
+    if (int rc = check_common(xs, ys, dtype, n, height, width)) return rc;
+    EBFI_REQUIRE(num_bins > 0, "events_to_voxel: num_bins must be positive");
+    EBFI_REQUIRE(voxel && (n == 0 || (ts && ps)), "events_to_voxel: null pointer");
+    if (n == 0) return EBFI_OK;
+    cudaStream_t st = ebfi::as_stream(stream);
+    if (dtype == EBFI_F32)
+        events_voxel_kernel<float><<<grid_for(n), 256, 0, st>>>((float *)xs, (float *)ys, (const float *)ts, ps, n, num_bins, height, width, voxel, write_back);
+    else
+        events_voxel_kernel<double><<<grid_for(n), 256, 0, st>>>((double *)xs, (double *)ys, (const double *)ts, ps, n, num_bins, height, width, voxel, write_back);
+    EBFI_LAUNCH_OK("events_voxel_kernel");
+    return EBFI_OK;
+}
+
+int ebfi_events_to_stack(void *stream, void *xs, void *ys, const void *ts, const float *ps, int dtype,
+                         int64_t n, int num_bins, int height, int width, float *stack, int64_t *bounds,
+                         int write_back)
+{
+    if (int rc = check_common(xs, ys, dtype, n, height, width)) return rc;
+    EBFI_REQUIRE(num_bins > 0 && num_bins <= 2048, "events_to_stack: num_bins must be in [1, 2048]");
+    EBFI_REQUIRE(stack && bounds && (n == 0 || (ts && ps)), "events_to_stack: null pointer");
+    if (n == 0) return EBFI_OK;
+    cudaStream_t st = ebfi::as_stream(stream);
+    const int nb2 = 2 * num_bins;
+    const size_t smem = (size_t)nb2 * sizeof(int64_t);
+    if (dtype == EBFI_F32) {
+        stack_bounds_kernel<float><<<ceil_div(nb2, 64), 64, 0, st>>>((const float *)ts, n, num_bins, bounds);
+        events_stack_kernel<float><<<grid_for(n), 256, smem, st>>>((float *)xs, (float *)ys, ps, n, num_bins, height, width, bounds, stack, write_back);
+    } else {
+        stack_bounds_kernel<double><<<ceil_div(nb2, 64), 64, 0, st>>>((const double *)ts, n, num_bins, bounds);
+        events_stack_kernel<double><<<grid_for(n), 256, smem, st>>>((double *)xs, (double *)ys, ps, n, num_bins, height, width, bounds, stack, write_back);
+    }
+    EBFI_LAUNCH_OK("events_stack kernels");
+    return EBFI_OK;
+}
+
+}  // extern "C"

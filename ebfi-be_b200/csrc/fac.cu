@@ -1,0 +1,488 @@
+// fac.cu — FAC KernelConv2D (per-pixel K x K kernel-prediction filter) for sm_100a.
+//
+// Replaces the three SIMT kernels of the reference
+// (models/FAC/kernelconv2d/KernelConv2D_kernel.cu:25-53 forward, :91-125 grad-input,
+// :128-150 grad-kernel). The op is pure HBM streaming: the (B, C*K*K, H, W) kernel tensor
+// is 92 % of the bytes, so the design goal is "touch every byte of it exactly once, with
+// 128-bit coalesced accesses, and never write or read anything that is not algorithmic".
+//
+// Layout facts used: for a fixed (b, c) the K*K kernel planes, the output plane and the
+// grad_output plane are contiguous H*W arrays; only `input` has the (W+K-1) pitch.
+//
+// "march" kernels: a thread owns PX (4 or 1) adjacent output columns and walks down a
+// segment of rows. The K input rows it needs live in a register window that is shifted by
+// one row per step, so every input value is loaded once per thread. Forward is then
+// 25 streaming 128-bit loads + 1 store per 4 outputs.
+//
+// Backward is ONE fused pass (the reference runs two kernels and reads `kernel` twice):
+// per row it streams kernel + grad_output in, grad_kernel out, and scatters
+// kernel*grad_output into a K-row register accumulator of grad_input. Column halos are
+// exchanged between neighbouring threads through shared memory once per row; row halos
+// between neighbouring segments (CTAs) go through a small workspace and are merged by
+// whichever of the two CTAs finishes second. Every grad_input element is a sum of the same
+// terms in the same order on every run (two-operand merge adds commute), so the result is
+// bit-reproducible without atomics on data.
+#include "common.cuh"
+
+namespace {
+
+using ebfi::ceil_div;
+
+// PX-wide vectors of fp32 with streaming (evict-first) global access.
+template <int PX> struct Vec;
+template <> struct Vec<4> {
+    float v[4];
+    __device__ __forceinline__ static Vec load_stream(const float *p)
+    {
+        float4 t = __ldcs(reinterpret_cast<const float4 *>(p));
+        return Vec{{t.x, t.y, t.z, t.w}};
+    }
+    __device__ __forceinline__ void store_stream(float *p) const
+    {
+        __stcs(reinterpret_cast<float4 *>(p), make_float4(v[0], v[1], v[2], v[3]));
+    }
+};
+template <> struct Vec<1> {
+    float v[1];
+    __device__ __forceinline__ static Vec load_stream(const float *p) { return Vec{{__ldcs(p)}}; }
+    __device__ __forceinline__ void store_stream(float *p) const { __stcs(p, v[0]); }
+};
+
+struct FacDims {
+    int H, W;          // output size
+    int seg_rows;      // rows per segment
+    int nseg;          // segments per plane
+    int nxb;           // thread blocks along x (forward only)
+};
+
+// ------------------------------------------------------------------ forward ---
+template <int K, int PX>
+__global__ void __launch_bounds__(128)
+fac_fwd_march(const float *__restrict__ in, const float *__restrict__ ker, float *__restrict__ out,
+              FacDims d)
+{
+    constexpr int WIN = PX + K - 1;
+    int bid = blockIdx.x;
+    const int xb = bid % d.nxb;  bid /= d.nxb;
+    const int seg = bid % d.nseg;
+    const int plane = bid / d.nseg;
+    const int x = (xb * blockDim.x + threadIdx.x) * PX;
+    if (x >= d.W) return;
+
+    const int H = d.H, W = d.W, Wi = W + K - 1;
+    const int y0 = seg * d.seg_rows, y1 = min(H, y0 + d.seg_rows);
+    const float *inp = in + (size_t)plane * (H + K - 1) * Wi + x;
+    const float *kp = ker + (size_t)plane * K * K * H * W + x;
+    float *op = out + (size_t)plane * H * W + x;
+
+    float win[K][WIN];
+#pragma unroll
+    for (int r = 1; r < K; ++r)
+#pragma unroll
+        for (int j = 0; j < WIN; ++j) win[r][j] = __ldg(inp + (size_t)(y0 + r - 1) * Wi + j);
+
+    for (int y = y0; y < y1; ++y) {
+        Vec<PX> kv[K * K];
+#pragma unroll
+        for (int k = 0; k < K * K; ++k) kv[k] = Vec<PX>::load_stream(kp + ((size_t)k * H + y) * W);
+#pragma unroll
+        for (int r = 0; r < K - 1; ++r)
+#pragma unroll
+            for (int j = 0; j < WIN; ++j) win[r][j] = win[r + 1][j];
+#pragma unroll
+        for (int j = 0; j < WIN; ++j) win[K - 1][j] = __ldg(inp + (size_t)(y + K - 1) * Wi + j);
+
+        Vec<PX> acc;
+#pragma unroll
+        for (int i = 0; i < PX; ++i) acc.v[i] = 0.f;
+        // same tap order as the reference's loop (KernelConv2D_kernel.cu:44-49)
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+                for (int i = 0; i < PX; ++i) acc.v[i] += win[ky][kx + i] * kv[ky * K + kx].v[i];
+        acc.store_stream(op + (size_t)y * W);
+    }
+}
+
+// ----------------------------------------------------------------- backward ---
+// Workspace layout: [planes * (nseg-1)] int arrival counters (zeroed by the launcher),
+// then [planes * (nseg-1)][K-1][Wi] fp32 overhang rows.
+template <int K, int PX>
+__global__ void __launch_bounds__(256)
+fac_bwd_march(const float *__restrict__ in, const float *__restrict__ ker,
+              const float *__restrict__ gout, float *__restrict__ gin, float *__restrict__ gker,
+              int *__restrict__ counters, float *__restrict__ overhang, FacDims d)
+{
+    constexpr int WIN = PX + K - 1;
+    constexpr int R = K - 1;                       // halo width
+    constexpr int RS = R > 0 ? R : 1;
+    constexpr int D = R > 0 ? (R + PX - 1) / PX : 0;   // how many left neighbours reach into my columns
+    extern __shared__ float xchg[];                // [2][blockDim.x][RS]
+    __shared__ int s_flag[2];
+
+    const int seg = blockIdx.x % d.nseg;
+    const int plane = blockIdx.x / d.nseg;
+    const int H = d.H, W = d.W, Wi = W + R;
+    const int t = threadIdx.x, nthr = blockDim.x;
+    const int x = t * PX;
+    const bool active = x < W;
+    const int nact = ceil_div(W, PX);              // threads that own output columns
+    const int y0 = seg * d.seg_rows, y1 = min(H, y0 + d.seg_rows);
+    const bool wi_vec = (PX == 4) && (Wi % 4 == 0);
+
+    const float *inp = in + (size_t)plane * (H + R) * Wi + x;
+    const float *kp = ker + (size_t)plane * K * K * H * W + x;
+    const float *gp = gout + (size_t)plane * H * W + x;
+    float *gkp = gker + (size_t)plane * K * K * H * W + x;
+    float *gip = gin + (size_t)plane * (H + R) * Wi;
+
+    float win[K][WIN], acc[K][WIN];
+#pragma unroll
+    for (int r = 0; r < K; ++r)
+#pragma unroll
+        for (int j = 0; j < WIN; ++j) { acc[r][j] = 0.f; win[r][j] = 0.f; }
+    if (active) {
+#pragma unroll
+        for (int r = 1; r < K; ++r)
+#pragma unroll
+            for (int j = 0; j < WIN; ++j) win[r][j] = __ldg(inp + (size_t)(y0 + r - 1) * Wi + j);
+    }
+
+    // Emits one finished (or segment-partial) grad_input row held in acc[0] after the
+    // neighbour exchange. `dst` is the row base (Wi floats) in gin or in the overhang buffer.
+    auto emit_row = [&](const float (&row)[WIN], float *dst, int parity) {
+        float *xb = xchg + (size_t)parity * nthr * RS;
+        if constexpr (R > 0) {
+#pragma unroll
+            for (int j = 0; j < R; ++j) xb[t * RS + j] = row[PX + j];
+        }
+        __syncthreads();
+        if (active) {
+            float o[PX];
+#pragma unroll
+            for (int j = 0; j < PX; ++j) o[j] = row[j];
+#pragma unroll
+            for (int dd = 1; dd <= D; ++dd) {
+                if (t - dd >= 0) {
+#pragma unroll
+                    for (int j = 0; j < PX; ++j) {
+                        const int c = j + PX * dd;           // column of thread t-dd's row
+                        if (c < WIN) o[j] += xb[(t - dd) * RS + (c - PX)];
+                    }
+                }
+            }
+            if (wi_vec) {
+                *reinterpret_cast<float4 *>(dst + x) = make_float4(o[0], o[PX > 1 ? 1 : 0], o[PX > 2 ? 2 : 0], o[PX > 3 ? 3 : 0]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < PX; ++j) dst[x + j] = o[j];
+            }
+        }
+        if constexpr (R > 0) {
+            // right halo columns W .. W+R-1 have no owner thread: the first R threads gather them
+            if (t < R) {
+                const int X = W + t, tv = X / PX, j = X % PX;
+                float o = 0.f;
+                for (int dd = 1; dd <= D; ++dd) {
+                    const int src = tv - dd, c = j + PX * dd;
+                    if (src >= 0 && src < nact && c < WIN) o += xb[src * RS + (c - PX)];
+                }
+                dst[X] = o;
+            }
+        }
+    };
+
+    int parity = 0;
+    for (int y = y0; y < y1; ++y) {
+        if (active) {
+            Vec<PX> kv[K * K];
+#pragma unroll
+            for (int k = 0; k < K * K; ++k) kv[k] = Vec<PX>::load_stream(kp + ((size_t)k * H + y) * W);
+            const Vec<PX> g = Vec<PX>::load_stream(gp + (size_t)y * W);
+#pragma unroll
+            for (int r = 0; r < K - 1; ++r)
+#pragma unroll
+                for (int j = 0; j < WIN; ++j) win[r][j] = win[r + 1][j];
+#pragma unroll
+            for (int j = 0; j < WIN; ++j) win[K - 1][j] = __ldg(inp + (size_t)(y + K - 1) * Wi + j);
+#pragma unroll
+            for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < K; ++kx) {
+                    Vec<PX> gk;
+#pragma unroll
+                    for (int i = 0; i < PX; ++i) {
+                        gk.v[i] = win[ky][kx + i] * g.v[i];                 // grad_kernel (:149)
+                        acc[ky][kx + i] += kv[ky * K + kx].v[i] * g.v[i];   // grad_input scatter (:117-120)
+                    }
+                    gk.store_stream(gkp + ((size_t)(ky * K + kx) * H + y) * W);
+                }
+        }
+        emit_row(acc[0], gip + (size_t)y * Wi, parity);
+        parity ^= 1;
+#pragma unroll
+        for (int r = 0; r < K - 1; ++r)
+#pragma unroll
+            for (int j = 0; j < WIN; ++j) acc[r][j] = acc[r + 1][j];
+#pragma unroll
+        for (int j = 0; j < WIN; ++j) acc[K - 1][j] = 0.f;
+    }
+
+    if constexpr (R > 0) {
+        // rows y1 .. y1+R-1: complete for the last segment, overhang for the others
+        const bool last = (seg == d.nseg - 1);
+        float *oh = last ? nullptr : overhang + ((size_t)plane * (d.nseg - 1) + seg) * R * Wi;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float *dst = last ? gip + (size_t)(y1 + r) * Wi : oh + (size_t)r * Wi;
+            emit_row(acc[r], dst, parity);
+            parity ^= 1;
+        }
+        if (d.nseg == 1) return;
+
+        // Hand-off: each boundary between segments s|s+1 has two parties; the second one to
+        // arrive adds the upper segment's overhang rows onto the lower segment's partial rows.
+        __threadfence();
+        __syncthreads();
+        if (t == 0) {
+            s_flag[0] = seg > 0 ? atomicAdd(&counters[plane * (d.nseg - 1) + seg - 1], 1) : 0;
+            s_flag[1] = !last ? atomicAdd(&counters[plane * (d.nseg - 1) + seg], 1) : 0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            if (s_flag[side] != 1) continue;
+            __threadfence();
+            const int bseg = side == 0 ? seg - 1 : seg;             // upper segment of the boundary
+            const int yb = (bseg + 1) * d.seg_rows;                 // first row of the lower segment
+            const float *src = overhang + ((size_t)plane * (d.nseg - 1) + bseg) * R * Wi;
+            float *dst = gip + (size_t)yb * Wi;
+            for (int e = t; e < R * Wi; e += nthr) dst[e] = __ldcg(dst + e) + __ldcg(src + e);
+        }
+    }
+}
+
+// ------------------------------------------------- generic fallback kernels ---
+// Any K, any size: one thread per element, no data-dependent reductions.
+__global__ void fac_fwd_generic(const float *__restrict__ in, const float *__restrict__ ker,
+                                float *__restrict__ out, int planes, int H, int W, int K)
+{
+    const size_t n = (size_t)planes * H * W;
+    const int Wi = W + K - 1, Hi = H + K - 1;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        const int x = e % W, y = (e / W) % H;
+        const size_t plane = e / ((size_t)H * W);
+        const float *ip = in + (plane * Hi + y) * Wi + x;
+        const float *kp = ker + plane * K * K * H * W + (size_t)y * W + x;
+        float s = 0.f;
+        for (int ky = 0; ky < K; ++ky)
+            for (int kx = 0; kx < K; ++kx) s += ip[(size_t)ky * Wi + kx] * kp[(size_t)(ky * K + kx) * H * W];
+        out[e] = s;
+    }
+}
+
+__global__ void fac_bwd_generic(const float *__restrict__ in, const float *__restrict__ ker,
+                                const float *__restrict__ gout, float *__restrict__ gin,
+                                float *__restrict__ gker, int planes, int H, int W, int K)
+{
+    const int Wi = W + K - 1, Hi = H + K - 1;
+    const size_t n_in = (size_t)planes * Hi * Wi, n_k = (size_t)planes * K * K * H * W;
+    const size_t stride = (size_t)gridDim.x * blockDim.x, tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    for (size_t e = tid; e < n_in; e += stride) {
+        const int X = e % Wi, Y = (e / Wi) % Hi;
+        const size_t plane = e / ((size_t)Hi * Wi);
+        const float *kp = ker + plane * K * K * H * W, *gp = gout + plane * H * W;
+        float s = 0.f;
+        for (int ky = 0; ky < K; ++ky)
+            for (int kx = 0; kx < K; ++kx) {
+                const int y = Y - ky, x = X - kx;
+                if (y >= 0 && y < H && x >= 0 && x < W)
+                    s += kp[((size_t)(ky * K + kx) * H + y) * W + x] * gp[(size_t)y * W + x];
+            }
+        gin[e] = s;
+    }
+    for (size_t e = tid; e < n_k; e += stride) {
+        const int x = e % W, y = (e / W) % H, k = (e / ((size_t)H * W)) % (K * K);
+        const size_t plane = e / ((size_t)K * K * H * W);
+        gker[e] = in[(plane * Hi + y + k / K) * Wi + x + k % K] * gout[(plane * H + y) * W + x];
+    }
+}
+
+// ------------------------------------------------------------------ dispatch ---
+struct FacPlan {
+    int px;            // 4, 1, or 0 = generic
+    FacDims d;
+    int threads;
+};
+
+int env_int(const char *name, int dflt)
+{
+    const char *s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+// Rows per segment: enough CTAs for several waves, segments at least K-1 (and 4) rows tall.
+int choose_seg(int planes, int H, int K)
+{
+    int seg = env_int("EBFI_FAC_SEG", 0);
+    if (seg <= 0) {
+        seg = 16;
+        while (seg < H && (long)planes * ceil_div(H, seg) > 32768) seg *= 2;
+    }
+    if (seg < 4) seg = 4;
+    if (seg < K - 1) seg = K - 1;
+    if (seg > H) seg = H;
+    return seg;
+}
+
+FacPlan make_plan(const void *const *ptrs, int nptr, int planes, int H, int W, int K, bool backward)
+{
+    FacPlan p{};
+    p.d.H = H; p.d.W = W;
+    const bool k_ok = (K == 1 || K == 3 || K == 5 || K == 7);
+    bool al = true;
+    for (int i = 0; i < nptr; ++i) al = al && ebfi::aligned16(ptrs[i]);
+    const int max_thr = backward ? 256 : 128;
+    // K = 7 at 4 px/thread needs more than 255 registers; it runs on the 1 px/thread variant.
+    if (k_ok && K <= 5 && W % 4 == 0 && al && (!backward || W / 4 <= max_thr)) p.px = 4;
+    else if (k_ok && (!backward || W <= max_thr)) p.px = 1;
+    else p.px = 0;
+    if (env_int("EBFI_FAC_FORCE_PX", -1) >= 0 && p.px != 0) {
+        const int f = env_int("EBFI_FAC_FORCE_PX", -1);
+        if (f == 0 || f == 1) p.px = f;
+    }
+    if (p.px == 0) return p;
+    const int seg = choose_seg(planes, H, K);
+    // the last segment must be the only one allowed to be shorter than K-1 rows (see merge)
+    p.d.seg_rows = seg;
+    p.d.nseg = ceil_div(H, seg);
+    const int cols = ceil_div(W, p.px);
+    if (backward) {
+        p.threads = ebfi::round_up(cols, 32);
+        p.d.nxb = 1;
+    } else {
+        p.threads = cols >= 128 ? 128 : ebfi::round_up(cols, 32);
+        p.d.nxb = ceil_div(cols, p.threads);
+    }
+    return p;
+}
+
+template <int PX>
+int launch_fwd(cudaStream_t st, const FacPlan &p, const float *in, const float *ker, float *out,
+               int planes, int K)
+{
+    const unsigned grid = (unsigned)((size_t)planes * p.d.nseg * p.d.nxb);
+    switch (K) {
+    case 1: fac_fwd_march<1, PX><<<grid, p.threads, 0, st>>>(in, ker, out, p.d); break;
+    case 3: fac_fwd_march<3, PX><<<grid, p.threads, 0, st>>>(in, ker, out, p.d); break;
+    case 5: fac_fwd_march<5, PX><<<grid, p.threads, 0, st>>>(in, ker, out, p.d); break;
+    case 7: if constexpr (PX == 1) { fac_fwd_march<7, 1><<<grid, p.threads, 0, st>>>(in, ker, out, p.d); break; }
+            return ebfi::fail(EBFI_ERR_INVALID, "fac: K=7 runs 1 px/thread only");
+    default: return ebfi::fail(EBFI_ERR_INVALID, "fac: unsupported K=%d in march path", K);
+    }
+    EBFI_LAUNCH_OK("fac_fwd_march");
+    return EBFI_OK;
+}
+
+template <int PX>
+int launch_bwd(cudaStream_t st, const FacPlan &p, const float *in, const float *ker,
+               const float *gout, float *gin, float *gker, int *counters, float *overhang,
+               int planes, int K)
+{
+    const unsigned grid = (unsigned)((size_t)planes * p.d.nseg);
+    const size_t smem = (size_t)2 * p.threads * (K > 1 ? K - 1 : 1) * sizeof(float);
+    switch (K) {
+    case 1: fac_bwd_march<1, PX><<<grid, p.threads, smem, st>>>(in, ker, gout, gin, gker, counters, overhang, p.d); break;
+    case 3: fac_bwd_march<3, PX><<<grid, p.threads, smem, st>>>(in, ker, gout, gin, gker, counters, overhang, p.d); break;
+    case 5: fac_bwd_march<5, PX><<<grid, p.threads, smem, st>>>(in, ker, gout, gin, gker, counters, overhang, p.d); break;
+    case 7: if constexpr (PX == 1) { fac_bwd_march<7, 1><<<grid, p.threads, smem, st>>>(in, ker, gout, gin, gker, counters, overhang, p.d); break; }
+            return ebfi::fail(EBFI_ERR_INVALID, "fac: K=7 runs 1 px/thread only");
+    default: return ebfi::fail(EBFI_ERR_INVALID, "fac: unsupported K=%d in march path", K);
+    }
+    EBFI_LAUNCH_OK("fac_bwd_march");
+    return EBFI_OK;
+}
+
+int check_dims(int B, int C, int H, int W, int K)
+{
+    EBFI_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "fac: non-positive size B=%d C=%d H=%d W=%d", B, C, H, W);
+    EBFI_REQUIRE(K > 0 && (K & 1), "fac: kernel_size must be odd and positive, got %d", K);
+    EBFI_REQUIRE((long)B * C < (1L << 24), "fac: B*C too large");
+    return EBFI_OK;
+}
+
+size_t ws_counter_bytes(int planes, int nseg)
+{
+    return ebfi::round_up((size_t)planes * (size_t)(nseg > 1 ? nseg - 1 : 1) * sizeof(int), (size_t)256);
+}
+
+}  // namespace
+
+extern "C" {
+
+int ebfi_fac_forward(void *stream, const float *input, const float *kernel, float *output,
+                     int batch, int channels, int height_out, int width_out, int kernel_size)
+{
+    if (int rc = check_dims(batch, channels, height_out, width_out, kernel_size)) return rc;
+    EBFI_REQUIRE(input && kernel && output, "fac_forward: null pointer");
+    const int planes = batch * channels, H = height_out, W = width_out, K = kernel_size;
+    cudaStream_t st = ebfi::as_stream(stream);
+    const void *ptrs[] = {kernel, output};
+    const FacPlan p = make_plan(ptrs, 2, planes, H, W, K, false);
+    if (p.px == 4) return launch_fwd<4>(st, p, input, kernel, output, planes, K);
+    if (p.px == 1) return launch_fwd<1>(st, p, input, kernel, output, planes, K);
+    const size_t n = (size_t)planes * H * W;
+    const unsigned grid = (unsigned)min((size_t)ebfi::sm_count() * 16, ceil_div(n, (size_t)256));
+    fac_fwd_generic<<<grid, 256, 0, st>>>(input, kernel, output, planes, H, W, K);
+    EBFI_LAUNCH_OK("fac_fwd_generic");
+    return EBFI_OK;
+}
+
+size_t ebfi_fac_backward_workspace_bytes(int batch, int channels, int height_out, int width_out,
+                                         int kernel_size)
+{
+    if (batch <= 0 || channels <= 0 || height_out <= 0 || width_out <= 0 || kernel_size <= 1) return 256;
+    const int planes = batch * channels, R = kernel_size - 1;
+    const int nseg = ceil_div(height_out, choose_seg(planes, height_out, kernel_size));
+    if (nseg <= 1) return 256;
+    return ws_counter_bytes(planes, nseg) +
+           (size_t)planes * (nseg - 1) * R * (size_t)(width_out + R) * sizeof(float);
+}
+
+int ebfi_fac_backward(void *stream, const float *input, const float *kernel,
+                      const float *grad_output, float *grad_input, float *grad_kernel,
+                      int batch, int channels, int height_out, int width_out, int kernel_size,
+                      void *workspace, size_t workspace_bytes)
+{
+    if (int rc = check_dims(batch, channels, height_out, width_out, kernel_size)) return rc;
+    EBFI_REQUIRE(input && kernel && grad_output && grad_input && grad_kernel, "fac_backward: null pointer");
+    const int planes = batch * channels, H = height_out, W = width_out, K = kernel_size;
+    cudaStream_t st = ebfi::as_stream(stream);
+    const void *ptrs[] = {kernel, grad_output, grad_kernel, grad_input};
+    const FacPlan p = make_plan(ptrs, 4, planes, H, W, K, true);
+    if (p.px == 0) {
+        const size_t n = (size_t)planes * K * K * H * W;
+        const unsigned grid = (unsigned)min((size_t)ebfi::sm_count() * 16, ceil_div(n, (size_t)256));
+        fac_bwd_generic<<<grid, 256, 0, st>>>(input, kernel, grad_output, grad_input, grad_kernel, planes, H, W, K);
+        EBFI_LAUNCH_OK("fac_bwd_generic");
+        return EBFI_OK;
+    }
+    int *counters = nullptr;
+    float *overhang = nullptr;
+    if (p.d.nseg > 1 && K > 1) {
+        const size_t cb = ws_counter_bytes(planes, p.d.nseg);
+        const size_t need = cb + (size_t)planes * (p.d.nseg - 1) * (K - 1) * (size_t)(W + K - 1) * sizeof(float);
+        if (!workspace || workspace_bytes < need)
+            return ebfi::fail(EBFI_ERR_WORKSPACE, "fac_backward: workspace %zu < %zu bytes", workspace_bytes, need);
+        EBFI_REQUIRE(ebfi::aligned16(workspace), "fac_backward: workspace must be 16-byte aligned");
+        counters = static_cast<int *>(workspace);
+        overhang = reinterpret_cast<float *>(static_cast<char *>(workspace) + cb);
+        EBFI_CUDA_OK(cudaMemsetAsync(counters, 0, (size_t)planes * (p.d.nseg - 1) * sizeof(int), st));
+    }
+    if (p.px == 4) return launch_bwd<4>(st, p, input, kernel, grad_output, grad_input, grad_kernel, counters, overhang, planes, K);
+    return launch_bwd<1>(st, p, input, kernel, grad_output, grad_input, grad_kernel, counters, overhang, planes, K);
+}
+
+}  // extern "C"

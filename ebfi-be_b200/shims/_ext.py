@@ -1,0 +1,110 @@
+"""`_ext` — same functions, argument order and error behaviour as the reference's pybind module
+(models/DCNv2/src/vision.cpp:4-9, src/dcn_v2.h:9-92), backed by libebfi_b200.so.
+
+Differences, all deliberate:
+  * CUDA only. The reference dispatches CPU tensors to dcn_v2_cpu_* (dcn_v2.h:35-44), whose
+    forward returns uninitialised memory (cpu/dcn_v2_cpu.cpp:65,127); here a CPU tensor raises.
+  * the deformable PS-ROI pooling pair (dcn_v2.h:94-190) is out of scope and raises
+    NotImplementedError (it is never imported by EBFI-BE).
+"""
+import torch
+
+try:
+    from ebfi_be_b200 import _lib as L
+except ImportError:  # shims directory used stand-alone on sys.path
+    import importlib.util as _u
+    import os as _os
+    import sys as _sys
+    _root = _os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
+    _sys.path.insert(0, _root)
+    from ebfi_be_b200 import _lib as L
+
+
+def _geom(input, weight, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w,
+          dilation_h, dilation_w, deformable_group):
+    if input.dim() != 4 or weight.dim() != 4:
+        raise RuntimeError("dcn_v2: input and weight must be 4-D")
+    channels_out, channels_kernel, kh_, kw_ = weight.shape
+    # same two shape checks as dcn_v2_cuda.cu:58-62
+    if kh_ != kernel_h or kw_ != kernel_w:
+        raise RuntimeError("Input shape and kernel shape wont match: (%d x %d vs %d x %d)."
+                           % (kernel_h, kernel_w, kh_, kw_))
+    if input.shape[1] != channels_kernel:
+        raise RuntimeError("Input shape and kernel channels wont match: (%d vs %d)."
+                           % (input.shape[1], channels_kernel))
+    g = L.DcnGeom(input.shape[0], input.shape[1], input.shape[2], input.shape[3], channels_out,
+                  kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w,
+                  deformable_group)
+    ho, wo = L.c_int(), L.c_int()
+    L.check(L.load().ebfi_dcnv2_output_size(g, ho, wo), "dcn_v2 geometry")
+    return g, ho.value, wo.value
+
+
+def _check_cuda(**named):
+    for k, t in named.items():
+        if not t.is_cuda:
+            raise RuntimeError(f"{k} must be a CUDA tensor")   # AT_ASSERTM, dcn_v2_cuda.cu:38-42
+    L.require_f32(**named)
+
+
+def _check_offset_mask(g, ho, wo, offset, mask):
+    kk = g.kernel_h * g.kernel_w
+    want_o = (g.batch, 2 * g.deformable_group * kk, ho, wo)
+    want_m = (g.batch, g.deformable_group * kk, ho, wo)
+    if tuple(offset.shape) != want_o or tuple(mask.shape) != want_m:
+        raise RuntimeError(f"dcn_v2: offset/mask shapes {tuple(offset.shape)}/{tuple(mask.shape)} "
+                           f"do not match the geometry (expected {want_o}/{want_m})")
+
+
+def dcn_v2_forward(input, weight, bias, offset, mask, kernel_h, kernel_w, stride_h, stride_w,
+                   pad_h, pad_w, dilation_h, dilation_w, deformable_group):
+    """dcn_v2_cuda_forward (src/cuda/dcn_v2_cuda.cu:20-95). Returns a new (B, Cout, Ho, Wo) tensor."""
+    _check_cuda(input=input, weight=weight, bias=bias, offset=offset, mask=mask)
+    g, ho, wo = _geom(input, weight, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w,
+                      dilation_h, dilation_w, deformable_group)
+    _check_offset_mask(g, ho, wo, offset, mask)
+    input, weight, bias, offset, mask = (t.contiguous() for t in (input, weight, bias, offset, mask))
+    with torch.cuda.device(input.device):
+        output = torch.empty((g.batch, g.channels_out, ho, wo), dtype=input.dtype, device=input.device)
+        L.check(L.load().ebfi_dcnv2_forward(L.stream_ptr(input.device), g, L.ptr(input), L.ptr(weight),
+                                            L.ptr(bias), L.ptr(offset), L.ptr(mask), L.ptr(output)),
+                "dcn_v2_forward")
+    return output
+
+
+def dcn_v2_backward(input, weight, bias, offset, mask, grad_output, kernel_h, kernel_w, stride_h,
+                    stride_w, pad_h, pad_w, dilation_h, dilation_w, deformable_group):
+    """dcn_v2_cuda_backward (dcn_v2_cuda.cu:97-216).
+    Returns [grad_input, grad_offset, grad_mask, grad_weight, grad_bias]."""
+    # THArgCheck(input.is_contiguous()) / (weight.is_contiguous()), dcn_v2_cuda.cu:110-111
+    if not input.is_contiguous():
+        raise RuntimeError("input tensor has to be contiguous")
+    if not weight.is_contiguous():
+        raise RuntimeError("weight tensor has to be contiguous")
+    _check_cuda(input=input, weight=weight, bias=bias, offset=offset, mask=mask, grad_output=grad_output)
+    g, ho, wo = _geom(input, weight, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w,
+                      dilation_h, dilation_w, deformable_group)
+    _check_offset_mask(g, ho, wo, offset, mask)
+    if tuple(grad_output.shape) != (g.batch, g.channels_out, ho, wo):
+        raise RuntimeError("dcn_v2_backward: grad_output has the wrong shape")
+    bias, offset, mask, grad_output = (t.contiguous() for t in (bias, offset, mask, grad_output))
+    lib = L.load()
+    with torch.cuda.device(input.device):
+        grads = [torch.empty_like(t) for t in (input, offset, mask, weight, bias)]
+        nbytes = lib.ebfi_dcnv2_backward_workspace_bytes(g)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=input.device)
+        L.check(lib.ebfi_dcnv2_backward(L.stream_ptr(input.device), g, L.ptr(input), L.ptr(weight),
+                                        L.ptr(bias), L.ptr(offset), L.ptr(mask), L.ptr(grad_output),
+                                        *(L.ptr(t) for t in grads), L.ptr(ws), nbytes),
+                "dcn_v2_backward")
+    return grads
+
+
+def dcn_v2_psroi_pooling_forward(*args, **kwargs):
+    raise NotImplementedError("deformable PS-ROI pooling is outside the EBFI-BE alignment hot path "
+                              "(models/DCNv2/src/dcn_v2.h:94-145); not provided by ebfi_be_b200")
+
+
+def dcn_v2_psroi_pooling_backward(*args, **kwargs):
+    raise NotImplementedError("deformable PS-ROI pooling is outside the EBFI-BE alignment hot path "
+                              "(models/DCNv2/src/dcn_v2.h:147-190); not provided by ebfi_be_b200")

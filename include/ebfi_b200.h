@@ -105,13 +105,21 @@ int ebfi_dcnv2_backward(void *stream, const ebfi_dcn_geom *g,
 int ebfi_fac_forward(void *stream, const float *input, const float *kernel, float *output,
                      int batch, int channels, int height_out, int width_out, int kernel_size);
 
+/* Scratch for ebfi_fac_backward: the K-1 overhang rows each row segment hands to the
+ * segment below it, plus one arrival counter per hand-off. An upper bound for the
+ * given shape; 16-byte aligned device memory. */
+size_t ebfi_fac_backward_workspace_bytes(int batch, int channels, int height_out, int width_out,
+                                         int kernel_size);
+
 /* grad_input  : (B, C, H+K-1, W+K-1), grad_kernel : (B, C*K*K, H, W); both written
  * in full — the caller's zero fill (KernelConv2D.py:50-51) is not relied upon.
- * One fused pass: grad_output and kernel are each read once.
+ * One fused pass: grad_output and kernel are each read once, and grad_input is
+ * reduced in a fixed order (bit-reproducible, no atomics on data).
  * Replaces KernelConv2D_backward_cuda (KernelConv2D_cuda.cpp:32-56). */
 int ebfi_fac_backward(void *stream, const float *input, const float *kernel,
                       const float *grad_output, float *grad_input, float *grad_kernel,
-                      int batch, int channels, int height_out, int width_out, int kernel_size);
+                      int batch, int channels, int height_out, int width_out, int kernel_size,
+                      void *workspace, size_t workspace_bytes);
 
 /* ---- event encoders --------------------------------------------------------- */
 
@@ -124,12 +132,17 @@ int ebfi_fac_backward(void *stream, const float *input, const float *kernel,
  *   img[(long)ys[i], (long)xs[i]] += ps[i]   for in-range events;
  * out-of-range events get xs=ys=ps=0 written back IN PLACE when `write_back`
  * is non-zero (that is what the reference does to its arguments, :254-256).
- * `img` (H, W) fp32 is ACCUMULATED into; the caller zero-fills it.
- * `binary` != 0 gives events_to_mask (:353-377): img[...] = |ps| (last writer wins;
- * all writers must then carry the same |ps| for a reproducible result). */
+ * `img` (H, W) fp32 is ACCUMULATED into; the caller zero-fills it. */
 int ebfi_events_to_image(void *stream, void *xs, void *ys, float *ps, int coord_dtype,
                          int64_t n_events, int height, int width,
-                         float *img, int write_back, int binary);
+                         float *img, int write_back);
+
+/* events_to_mask (encodings.py:353-377): img[...] = |ps| with accumulate=False, i.e.
+ * the LAST event of a pixel wins (out-of-range events write 0 at pixel (0,0), like the
+ * reference). `last_index_scratch` is (H*W) int64 device scratch. */
+int ebfi_events_to_mask(void *stream, void *xs, void *ys, float *ps, int coord_dtype,
+                        int64_t n_events, int height, int width,
+                        float *img, int64_t *last_index_scratch, int write_back);
 
 /* events_to_voxel (encodings.py:271-286): temporal-bilinear voxel grid.
  *   t = ts[i] * (num_bins-1);  voxel[b] += ps[i] * max(0, 1 - |t - b|)

@@ -1,0 +1,107 @@
+"""CPU: the C-ABI library loads, exports every symbol include/ebfi_b200.h declares, and the host
+side fails loudly (no CPU fallback). No kernel is launched here."""
+import ctypes
+import os
+import re
+import sys
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+import ebfi_be_b200
+from ebfi_be_b200 import _lib as L
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "ebfi_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ebfi_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_is_built_in_tree():
+    assert os.path.exists(L.LIB_PATH), "run `python ebfi-be_b200/build.py`"
+    assert os.path.commonpath([ROOT, L.LIB_PATH]) == ROOT
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    lib = ctypes.CDLL(L.LIB_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 14
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/ebfi_b200.h but not exported"
+        assert name in L.SIGNATURES, f"{name} has no ctypes prototype in _lib.SIGNATURES"
+    assert sorted(L.SIGNATURES) == declared
+
+
+def test_abi_version_and_error_string():
+    lib = L.load()
+    assert lib.ebfi_abi_version() == 1
+    assert isinstance(lib.ebfi_last_error(), bytes)
+
+
+def test_geometry_is_validated_without_a_gpu():
+    lib = L.load()
+    ho, wo = L.c_int(), L.c_int()
+    g = L.DcnGeom(1, 64, 256, 256, 64, 3, 3, 1, 1, 1, 1, 1, 1, 8)
+    assert lib.ebfi_dcnv2_output_size(g, ho, wo) == 0 and (ho.value, wo.value) == (256, 256)
+    g = L.DcnGeom(1, 8, 12, 10, 8, 3, 3, 2, 2, 1, 1, 1, 1, 4)
+    assert lib.ebfi_dcnv2_output_size(g, ho, wo) == 0 and (ho.value, wo.value) == (6, 5)
+    bad = L.DcnGeom(1, 6, 8, 8, 4, 3, 3, 1, 1, 1, 1, 1, 1, 4)          # 6 % 4 != 0
+    assert lib.ebfi_dcnv2_output_size(bad, ho, wo) == -1
+    assert b"deformable_group" in lib.ebfi_last_error()
+    assert lib.ebfi_dcnv2_backward_workspace_bytes(L.DcnGeom(1, 64, 256, 256, 64, 3, 3, 1, 1, 1, 1, 1, 1, 8)) > 0
+    assert lib.ebfi_fac_backward_workspace_bytes(4, 64, 256, 256, 5) > 0
+
+
+def test_null_and_bad_arguments_return_error_codes():
+    lib = L.load()
+    assert lib.ebfi_fac_forward(None, None, None, None, 1, 1, 8, 8, 5) == -1
+    assert lib.ebfi_fac_forward(None, None, None, None, 1, 1, 8, 8, 4) == -1      # even K
+    assert b"odd" in lib.ebfi_last_error()
+    assert lib.ebfi_events_to_voxel(None, None, None, None, None, 7, 10, 5, 4, 4, None, 0) == -1
+
+
+def test_ops_refuse_cpu_tensors():
+    from ebfi_be_b200 import dcn_v2, encodings, kernelconv2d
+    x = torch.randn(1, 2, 6, 6)
+    with pytest.raises(NotImplementedError):                       # KernelConv2D.py:38-39
+        kernelconv2d.KernelConv2DFunction.apply(x, torch.randn(1, 18, 4, 4), 3)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):          # dcn_v2_cuda.cu:38
+        dcn_v2.dcn_v2_conv(x, torch.zeros(1, 18, 6, 6), torch.ones(1, 9, 6, 6),
+                           torch.randn(2, 2, 3, 3), torch.zeros(2), 1, 1, 1, 1)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        encodings.events_to_image(torch.zeros(3), torch.zeros(3), torch.ones(3), (4, 4))
+
+
+def test_module_parameters_match_reference_layout():
+    from ebfi_be_b200 import dcn_v2
+    m = dcn_v2.DCN_sep(64, 64, 3, stride=1, padding=1, dilation=1, deformable_groups=8)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    # dcn_v2.py:118-119,203-205 -> checkpoint compatibility
+    assert shapes == {"weight": (64, 64, 3, 3), "bias": (64,),
+                      "conv_offset_mask.weight": (216, 64, 3, 3), "conv_offset_mask.bias": (216,)}
+    assert float(m.conv_offset_mask.weight.abs().sum()) == 0.0 and float(m.bias.abs().sum()) == 0.0
+    assert float(m.weight.abs().max()) <= 1.0 / (64 * 9) ** 0.5
+
+
+def test_psroi_pooling_is_declared_out_of_scope():
+    _ext, _ = ebfi_be_b200.install_shims()
+    with pytest.raises(NotImplementedError):
+        _ext.dcn_v2_psroi_pooling_forward()
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="reference tree not present")
+def test_reference_wrappers_import_unchanged_on_our_shims():
+    """models/DCNv2/dcn_v2.py and models/FAC/kernelconv2d/KernelConv2D.py import `_ext` /
+    `kernelconv2d_cuda` at module load; with the shims installed they import as they are."""
+    import importlib.util
+    ebfi_be_b200.install_shims()
+    for rel, attr in (("models/DCNv2/dcn_v2.py", "DCN_sep"),
+                      ("models/FAC/kernelconv2d/KernelConv2D.py", "KernelConv2D")):
+        spec = importlib.util.spec_from_file_location("ref_" + attr, os.path.join("/root/reference", rel))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        assert hasattr(mod, attr)
+    sys.modules.pop("_ext", None), sys.modules.pop("kernelconv2d_cuda", None)

@@ -1,0 +1,191 @@
+"""GPU parity of DCNv2: CUDA path (through the C ABI / autograd Function) vs the CPU oracle, the
+reference-generated golden vectors and the reference's own CUDA kernels (oracle/_ref/dcn_cuda).
+Gates (BASELINE.json north_star): forward 1e-5, gradients 1e-4, relative to max|ref| per tensor."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import DCN_CASES, FWD_TOL, GRAD_TOL, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+GRADS = ["grad_input", "grad_offset", "grad_mask", "grad_weight", "grad_bias"]
+
+
+@pytest.fixture(scope="module")
+def dcn():
+    from ebfi_be_b200 import dcn_v2
+    return dcn_v2
+
+
+def _run(dcn, x, off, msk, w, b, go, stride, pad, dil, dg):
+    from gpu_util import n, t
+    ts = [t(a).requires_grad_() for a in (x, off, msk, w, b)]
+    out = dcn.dcn_v2_conv(*ts, stride, pad, dil, dg)
+    out.backward(t(go))
+    return n(out), [n(v.grad) for v in ts]
+
+
+def _geom(g):
+    kh, kw, sh, sw, ph, pw, dh, dw, dg = (int(v) for v in g["geom"])
+    return (sh, sw), (ph, pw), (dh, dw), dg
+
+
+@pytest.mark.parametrize("case", DCN_CASES)
+def test_golden_vectors(dcn, case):
+    g = load_golden(case)
+    s, p, d, dg = _geom(g)
+    out, grads = _run(dcn, g["input"], g["offset"], g["mask"], g["weight"], g["bias"], g["grad_output"], s, p, d, dg)
+    assert rel_err(out, g["output"]) < FWD_TOL
+    order = ["grad_input", "grad_offset", "grad_mask", "grad_weight", "grad_bias"]
+    for name, got in zip(order, grads):
+        assert rel_err(got, g[name]) < GRAD_TOL, name
+
+
+def test_zero_offset_known_answer(dcn):
+    # reference fixture testcuda.py:32-67: identity weights, zero offsets, mask 0.5 => 2*out == input
+    from gpu_util import n, t
+    g = load_golden("dcn_zero_offset")
+    out = dcn.dcn_v2_conv(t(g["input"]), t(g["offset"]), t(g["mask"]), t(g["weight"]), t(g["bias"]), 1, 1, 1, 1)
+    assert np.abs(2 * n(out) - g["input"]).max() < 1e-10
+
+
+# (B, C, Co, H, W, k, stride, pad, dil, dg, offset scale)
+SHAPES = [(1, 64, 64, 32, 32, 3, 1, 1, 1, 8, 2.0),      # benchmark geometry, small image
+          (2, 16, 24, 19, 23, 3, 1, 1, 1, 4, 2.0),      # ragged pixels, Cout not a multiple of 4
+          (1, 8, 70, 12, 12, 3, 1, 1, 1, 2, 2.0),       # two Cout tiles
+          (1, 6, 5, 14, 9, 3, 2, 1, 1, 3, 1.0),         # stride 2
+          (1, 4, 4, 11, 13, 3, 1, 2, 2, 1, 10.0),       # dilation 2, large offsets (far out of window)
+          (2, 4, 6, 8, 8, 1, 1, 0, 1, 2, 1.5),          # 1x1 kernel
+          (1, 2, 3, 9, 9, 5, 1, 2, 1, 1, 2.0),          # 5x5 kernel
+          (1, 24, 8, 10, 10, 3, 1, 1, 1, 2, 2.0)]       # 12 channels/group * 9 taps > slab: two chunks
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_against_oracle(dcn, oracle, shape):
+    B, C, Co, H, W, k, s, p, d, dg, osc = shape
+    rng = np.random.default_rng(abs(hash(shape)) % (2 ** 32))
+    Ho = (H + 2 * p - (d * (k - 1) + 1)) // s + 1
+    Wo = (W + 2 * p - (d * (k - 1) + 1)) // s + 1
+    x = rng.standard_normal((B, C, H, W), dtype=np.float32)
+    w = (rng.random((Co, C, k, k), dtype=np.float32) * 2 - 1) / np.sqrt(C * k * k)
+    b = rng.standard_normal(Co, dtype=np.float32)
+    off = (rng.standard_normal((B, 2 * dg * k * k, Ho, Wo)) * osc).astype(np.float32)
+    msk = (1 / (1 + np.exp(-rng.standard_normal((B, dg * k * k, Ho, Wo))))).astype(np.float32)
+    go = rng.standard_normal((B, Co, Ho, Wo), dtype=np.float32)
+    out, grads = _run(dcn, x, off, msk, w, b, go, s, p, d, dg)
+    assert rel_err(out, oracle.dcn_forward(x, off, msk, w, b, s, p, d, dg)) < FWD_TOL
+    want = oracle.dcn_backward(x, off, msk, w, b, go, s, p, d, dg)
+    for name, got, ref in zip(GRADS, grads, want):
+        assert rel_err(got, ref) < GRAD_TOL, name
+
+
+def test_window_edges_match_oracle(dcn, oracle):
+    """Samples exactly on -1, 0, H-1, H and integer coordinates: the (-1, H) window, per-corner
+    bounds and zero-weight corners of im2col_cuda.cu:38-48,180."""
+    B, C, Co, H, W, dg = 1, 4, 4, 6, 7, 2
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((B, C, H, W), dtype=np.float32)
+    w = rng.standard_normal((Co, C, 3, 3), dtype=np.float32) * 0.2
+    b = np.zeros(Co, np.float32)
+    off = rng.choice(np.array([-2.0, -1.0, -0.5, 0.0, 0.5, 1.0, 2.0, 5.0, -7.0], np.float32), (B, 2 * dg * 9, H, W))
+    msk = np.ones((B, dg * 9, H, W), np.float32)
+    go = rng.standard_normal((B, Co, H, W), dtype=np.float32)
+    out, grads = _run(dcn, x, off, msk, w, b, go, 1, 1, 1, dg)
+    assert rel_err(out, oracle.dcn_forward(x, off, msk, w, b, 1, 1, 1, dg)) < FWD_TOL
+    for name, got, ref in zip(GRADS, grads, oracle.dcn_backward(x, off, msk, w, b, go, 1, 1, 1, dg)):
+        assert rel_err(got, ref) < GRAD_TOL, name
+
+
+def test_reductions_are_bit_reproducible(dcn):
+    """grad_offset / grad_mask / grad_weight / grad_bias use fixed-order reductions."""
+    from gpu_util import dev
+    torch.manual_seed(1)
+    B, C, H, W, dg = 2, 64, 48, 48, 8
+    x = torch.randn(B, C, H, W, device=dev())
+    off = 2 * torch.randn(B, 2 * dg * 9, H, W, device=dev())
+    msk = torch.sigmoid(torch.randn(B, dg * 9, H, W, device=dev()))
+    w = torch.randn(64, C, 3, 3, device=dev()) / 24
+    b = torch.randn(64, device=dev())
+    go = torch.randn(B, 64, H, W, device=dev())
+    runs = []
+    for _ in range(3):
+        ts = [v.clone().requires_grad_() for v in (x, off, msk, w, b)]
+        dcn.dcn_v2_conv(*ts, 1, 1, 1, dg).backward(go)
+        runs.append([v.grad.clone() for v in ts])
+    for r in runs[1:]:
+        for i in (1, 2, 3, 4):
+            assert torch.equal(r[i], runs[0][i]), GRADS[i]
+        assert rel_err(r[0].cpu().numpy(), runs[0][0].cpu().numpy()) < 1e-5
+
+
+def test_matches_reference_cuda_kernels(dcn):
+    """The reference's own dcn_v2_im2col_cuda.cu kernels compiled unmodified for sm_100a."""
+    from gpu_util import dev, load_ref_ext
+    ref = load_ref_ext("dcn_cuda", "_ext_cuda_ref")
+    if ref is None:
+        pytest.skip("oracle/_ref/dcn_cuda not built (needs /root/reference at build time)")
+    torch.manual_seed(2)
+    B, C, Co, H, W, dg = 2, 64, 64, 40, 40, 8
+    x = torch.randn(B, C, H, W, device=dev())
+    off = 2 * torch.randn(B, 2 * dg * 9, H, W, device=dev())
+    msk = torch.sigmoid(torch.randn(B, dg * 9, H, W, device=dev()))
+    w = (torch.rand(Co, C, 3, 3, device=dev()) * 2 - 1) / 24
+    b = torch.randn(Co, device=dev())
+    go = torch.randn(B, Co, H, W, device=dev())
+    allow = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        r_out = ref.dcn_v2_forward(x, w, b, off, msk, 3, 3, 1, 1, 1, 1, 1, 1, dg)
+        r_grads = ref.dcn_v2_backward(x, w, b, off, msk, go, 3, 3, 1, 1, 1, 1, 1, 1, dg)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = allow
+    ts = [v.clone().requires_grad_() for v in (x, off, msk, w, b)]
+    out = dcn.dcn_v2_conv(*ts, 1, 1, 1, dg)
+    out.backward(go)
+    assert rel_err(out.detach().cpu().numpy(), r_out.cpu().numpy()) < FWD_TOL
+    for name, v, r in zip(GRADS, ts, r_grads):
+        assert rel_err(v.grad.cpu().numpy(), r.cpu().numpy()) < GRAD_TOL, name
+
+
+def test_modules_forward_backward(dcn):
+    """example_dconv of the reference (testcuda.py:169-180): DCN(64,64,3,pad 1,dg 2) on 2x64x128x128."""
+    from gpu_util import dev
+    torch.manual_seed(0)
+    m = dcn.DCN(64, 64, kernel_size=(3, 3), stride=1, padding=1, deformable_groups=2).to(dev())
+    x = torch.randn(2, 64, 128, 128, device=dev())
+    out = m(x)
+    assert out.shape == x.shape
+    out.norm().backward()
+    assert m.weight.grad.shape == m.weight.shape and torch.isfinite(m.weight.grad).all()
+    # zero-initialised offset conv => plain 3x3 convolution with mask 0.5
+    want = 0.5 * torch.nn.functional.conv2d(x.double(), m.weight.double(), None, 1, 1) + m.bias.double().view(1, -1, 1, 1)
+    assert rel_err(out.detach().cpu().numpy(), want.detach().cpu().numpy()) < FWD_TOL
+    sep = dcn.DCN_sep(64, 64, 3, stride=1, padding=1, deformable_groups=8).to(dev())
+    assert sep(x, torch.randn_like(x)).shape == x.shape
+
+
+def test_full_size_properties(dcn):
+    """BASELINE config 1 (B=1, C=64->64, 3x3, dg=8, 256x256). Size-independent properties:
+    zero offsets + unit mask == ordinary convolution; the op is linear in input and in weight,
+    so <gO, out - bias> == <grad_input, input> == <grad_weight, weight>; grad_bias == sum gO."""
+    from gpu_util import dev, dot
+    torch.manual_seed(0)
+    B, C, H, W, dg = 1, 64, 256, 256, 8
+    x = torch.randn(B, C, H, W, device=dev())
+    w = (torch.rand(64, C, 3, 3, device=dev()) * 2 - 1) / 24
+    b = torch.randn(64, device=dev())
+    out0 = dcn.dcn_v2_conv(x, torch.zeros(B, 2 * dg * 9, H, W, device=dev()),
+                           torch.ones(B, dg * 9, H, W, device=dev()), w, b, 1, 1, 1, dg)
+    want = torch.nn.functional.conv2d(x.double(), w.double(), b.double(), 1, 1)
+    assert rel_err(out0.cpu().numpy(), want.cpu().numpy()) < FWD_TOL
+    off = 2 * torch.randn(B, 2 * dg * 9, H, W, device=dev())
+    msk = torch.sigmoid(torch.randn(B, dg * 9, H, W, device=dev()))
+    go = torch.randn(B, 64, H, W, device=dev())
+    ts = [v.clone().requires_grad_() for v in (x, off, msk, w, b)]
+    out = dcn.dcn_v2_conv(*ts, 1, 1, 1, dg)
+    out.backward(go)
+    a = dot(go, out.detach() - b.view(1, -1, 1, 1))
+    assert abs(a - dot(ts[0].grad, x)) <= 1e-4 * abs(a)
+    assert abs(a - dot(ts[3].grad, w)) <= 1e-4 * abs(a)
+    assert abs(a - dot(ts[2].grad, msk)) <= 1e-4 * abs(a)          # linear in mask, too
+    assert rel_err(ts[4].grad.cpu().numpy(), go.double().sum((0, 2, 3)).cpu().numpy()) < GRAD_TOL
