@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py — DCNv2+FAC fwd+bwd Mpix/s on B200 (BASELINE.json metric), with roofline and CPU baseline.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # reference CPU path (rank 0)
+
+One "step" = one pass of the alignment hot path over one synthetic GoPro-shaped batch, exactly
+BASELINE.json configs[0] + configs[1]:
+    DCNv2  3x3, C=64->64, deformable_groups=8, B=1, 256x256, fp32, forward + backward
+    FAC    KernelConv2D k=5, C=64,            B=4, 256x256, fp32, forward + backward
+Mpix/s = (1 + 4) * 256 * 256 output pixels / step time. Every rank runs the same per-GPU batch
+(weak scaling); with N > 1 the DCN weight/bias gradients are all-reduced over NCCL each step.
+
+`value`   : inputs resident in HBM, ops called through the drop-in extension modules (`_ext`,
+            `kernelconv2d_cuda` shims -> C ABI), CUDA events on the launching stream.
+`e2e`     : same step through the autograd Functions with HOST (pinned) inputs and outputs; the
+            H2D copies of every input and the D2H copies of every output/gradient are inside the
+            timed region.
+`roofline`: the dominant kernel (FAC backward): algorithmic bytes per launch / its average
+            CUDA-event duration inside the timed region, against MEASURED_PEAKS.json.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H = W = 256
+C = 64
+DG = 8
+B_DCN, B_FAC, K_FAC = 1, 4, 5
+MPIX_PER_STEP = (B_DCN + B_FAC) * H * W / 1e6
+
+# Algorithmic bytes (SURVEY.md §8d / DESIGN.md): every tensor of the op read or written once.
+_F = 4
+DCN_FWD_BYTES = _F * (B_DCN * C * H * W + B_DCN * 2 * DG * 9 * H * W + B_DCN * DG * 9 * H * W + C * C * 9 + C
+                      + B_DCN * C * H * W)
+DCN_BWD_BYTES = _F * (2 * B_DCN * C * H * W + B_DCN * 3 * DG * 9 * H * W + C * C * 9            # reads
+                      + B_DCN * C * H * W + B_DCN * 3 * DG * 9 * H * W + C * C * 9 + C)         # writes
+FAC_IN = B_FAC * C * (H + 4) * (W + 4)
+FAC_KER = B_FAC * C * 25 * H * W
+FAC_OUT = B_FAC * C * H * W
+FAC_FWD_BYTES = _F * (FAC_IN + FAC_KER + FAC_OUT)
+FAC_BWD_BYTES = _F * (FAC_KER + FAC_OUT + FAC_IN + FAC_IN + FAC_KER)
+STEP_BYTES = DCN_FWD_BYTES + DCN_BWD_BYTES + FAC_FWD_BYTES + FAC_BWD_BYTES
+# kernels of ours per step: dcn_fwd, dcn_bwd, dcn_reduce_partials, fac_fwd_march, fac_bwd_march
+LAUNCHES_PER_STEP = 5
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.th.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def make_inputs(torch, dev, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    r = lambda *s: torch.randn(*s, generator=g)
+    d = dict(
+        x=r(B_DCN, C, H, W), off=2 * r(B_DCN, 2 * DG * 9, H, W), msk=torch.sigmoid(r(B_DCN, DG * 9, H, W)),
+        w=(torch.rand(C, C, 3, 3, generator=g) * 2 - 1) / 24, b=r(C), go_d=r(B_DCN, C, H, W),
+        xi=r(B_FAC, C, H + 4, W + 4), ker=0.1 * r(B_FAC, C * 25, H, W), go_f=r(B_FAC, C, H, W))
+    return d
+
+
+# --------------------------------------------------------------------- ours ---
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import ebfi_be_b200
+    from ebfi_be_b200 import dcn_v2, kernelconv2d
+    from ebfi_be_b200.shims import _ext, kernelconv2d_cuda as kc
+
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}; launch with torch.distributed.run"
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ebfi_be_b200._lib.load()
+    host = make_inputs(torch, dev, 1234 + rank)
+    d = {k: v.to(dev) for k, v in host.items()}
+    geom = (3, 3, 1, 1, 1, 1, 1, 1, DG)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    out_f = torch.empty(B_FAC, C, H, W, device=dev)
+    gi_f, gk_f = torch.empty_like(d["xi"]), torch.empty_like(d["ker"])
+    op_names = ["dcn_fwd", "dcn_bwd", "fac_fwd", "fac_bwd"]
+
+    def step(marks=None):
+        """One pass of the hot path, device-resident, through the drop-in extension modules."""
+        def mark():
+            if marks is not None:
+                e = ev(); e.record(); marks.append(e)
+        mark()
+        _ext.dcn_v2_forward(d["x"], d["w"], d["b"], d["off"], d["msk"], *geom)
+        mark()
+        grads = _ext.dcn_v2_backward(d["x"], d["w"], d["b"], d["off"], d["msk"], d["go_d"], *geom)
+        if world > 1:   # data-parallel weight-gradient all-reduce (the only collective on the path)
+            dist.all_reduce(grads[3]); dist.all_reduce(grads[4])
+        mark()
+        kc.forward(d["xi"], d["ker"], K_FAC, out_f)
+        mark()
+        kc.backward(d["xi"], d["ker"], K_FAC, d["go_f"], gi_f, gk_f)
+        mark()
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    marks, t0, t1 = [], ev(), ev()
+    with ClockSampler(local) as clk:
+        t0.record()
+        for _ in range(args.steps):
+            step(marks)
+        t1.record()
+        torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms_total = t0.elapsed_time(t1)
+    if world > 1:
+        tt = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total = float(tt)
+    ms_step = ms_total / args.steps
+    op_ms = {n: 0.0 for n in op_names}
+    for s in range(args.steps):
+        for i, n in enumerate(op_names):
+            op_ms[n] += marks[5 * s + i].elapsed_time(marks[5 * s + i + 1]) / args.steps
+
+    # ---- e2e: autograd Functions, pinned host buffers in and out, copies inside the timed region
+    pin = {k: v.pin_memory() for k, v in host.items()}
+    res_names = ["out_d", "g_x", "g_off", "g_msk", "g_w", "g_b", "out_f", "g_xi", "g_ker"]
+    res_like = [host["go_d"], host["x"], host["off"], host["msk"], host["w"], host["b"], host["go_f"], host["xi"], host["ker"]]
+    pin_out = {n: torch.empty_like(t).pin_memory() for n, t in zip(res_names, res_like)}
+    h2d = sum(v.numel() * 4 for v in pin.values()); d2h = sum(v.numel() * 4 for v in pin_out.values())
+
+    def e2e_step():
+        g = {k: v.to(dev, non_blocking=True) for k, v in pin.items()}
+        leaves = [g[k].requires_grad_() for k in ("x", "off", "msk", "w", "b")]
+        out = dcn_v2.dcn_v2_conv(*leaves, 1, 1, 1, DG)
+        out.backward(g["go_d"])
+        if world > 1:
+            dist.all_reduce(leaves[3].grad); dist.all_reduce(leaves[4].grad)
+        xi, ker = g["xi"].requires_grad_(), g["ker"].requires_grad_()
+        of = kernelconv2d.KernelConv2DFunction.apply(xi, ker, K_FAC)
+        of.backward(g["go_f"])
+        for n, t in zip(res_names, [out.detach()] + [l.grad for l in leaves] + [of.detach(), xi.grad, ker.grad]):
+            pin_out[n].copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the step's results are on the host
+
+    e2e_steps = 1 if args.kernels_only else max(3, min(args.steps, 10))
+    for _ in range(0 if args.kernels_only else 2):
+        e2e_step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    w0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - w0
+    if world > 1:
+        tt = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt)
+
+    # ---- per-config breakdown with an explicit L2 flush before every timed call (DCN's 90 MB of
+    # inputs fit in the 126 MB L2, so back-to-back calls would otherwise be measured warm)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    def timed(fn, n=1 if args.kernels_only else 10):
+        ts = []
+        for _ in range(n):
+            flush.zero_()
+            a, b = ev(), ev()
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return statistics.median(ts)
+    cold = {
+        "dcn_fwd": timed(lambda: _ext.dcn_v2_forward(d["x"], d["w"], d["b"], d["off"], d["msk"], *geom)),
+        "dcn_bwd": timed(lambda: _ext.dcn_v2_backward(d["x"], d["w"], d["b"], d["off"], d["msk"], d["go_d"], *geom)),
+        "fac_fwd": timed(lambda: kc.forward(d["xi"], d["ker"], K_FAC, out_f)),
+        "fac_bwd": timed(lambda: kc.backward(d["xi"], d["ker"], K_FAC, d["go_f"], gi_f, gk_f)),
+    }
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = peaks()
+    op_bytes = {"dcn_fwd": DCN_FWD_BYTES, "dcn_bwd": DCN_BWD_BYTES, "fac_fwd": FAC_FWD_BYTES, "fac_bwd": FAC_BWD_BYTES}
+    gbs = lambda nbytes, ms: nbytes / (ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get("fac_bwd_march")
+    dom = "fac_bwd"
+    line = {
+        "metric": "DCNv2+FAC fwd+bwd Mpix/s", "value": round(world * MPIX_PER_STEP / (ms_step * 1e-3), 3),
+        "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[0]+[1]: DCNv2 3x3 C=64 dg=8 B=1 256x256 fwd+bwd, then FAC "
+                               "KernelConv2D k=5 C=64 B=4 256x256 fwd+bwd, per GPU",
+                   "pixels_per_step_per_gpu": int(MPIX_PER_STEP * 1e6), "parallelism": f"dp{world} (batch-sharded)",
+                   "l2": "inputs larger than L2: each step streams 5.4 GB of FAC tensors (>> 126 MB L2) "
+                         "between consecutive DCN calls; breakdown.cold_ms flushes L2 explicitly",
+                   "collective": "NCCL all-reduce of DCN grad_weight+grad_bias" if world > 1 else "none"},
+        "roofline": {"bound": "hbm", "kernel": "fac_bwd_march<5,4> (FAC fused backward)",
+                     "achieved": round(gbs(op_bytes[dom], op_ms[dom]), 1), "peak": peak, "unit": "GB/s",
+                     "frac": round(gbs(op_bytes[dom], op_ms[dom]) / peak, 4), "traffic": traffic,
+                     "algorithmic_bytes_per_launch": op_bytes[dom], "peak_source": peak_src,
+                     "step_frac": round(gbs(STEP_BYTES, ms_step) / peak, 4)},
+        "breakdown": {n: {"ms": round(op_ms[n], 4), "cold_ms": round(cold[n], 4),
+                          "algorithmic_GBps": round(gbs(op_bytes[n], op_ms[n]), 1),
+                          "hbm_frac": round(gbs(op_bytes[n], op_ms[n]) / peak, 4)} for n in op_names},
+        "configs_mpix_s": {
+            "cfg1_dcn_B1": round(B_DCN * H * W / 1e6 / ((cold["dcn_fwd"] + cold["dcn_bwd"]) * 1e-3), 2),
+            "cfg2_fac_B4": round(B_FAC * H * W / 1e6 / ((op_ms["fac_fwd"] + op_ms["fac_bwd"]) * 1e-3), 2)},
+        "e2e": {"value": round(world * MPIX_PER_STEP * e2e_steps / e2e_s, 3), "unit": "Mpix/s",
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "api": "dcn_v2_conv / KernelConv2DFunction.apply (autograd), pinned host in/out"},
+        "gpu_launches": LAUNCHES_PER_STEP * args.steps,
+        "clocks": clk.summary(),
+    }
+    if world == 1 and not (args.no_cpu_baseline or args.kernels_only):
+        line["cpu_baseline"] = cpu_baseline(budget_s=20.0)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------- CPU arms ---
+def _load_ref_dcn_cpu():
+    """The reference's own CPU DCNv2 (oracle/_ref/dcn_cpu/_ext*.so, built from the unmodified
+    sources by oracle/build_ref.py); None when it did not travel / does not load."""
+    import importlib.util
+    d = os.path.join(ROOT, "oracle", "_ref", "dcn_cpu")
+    if not os.path.isdir(d):
+        return None
+    for f in os.listdir(d):
+        if f.startswith("_ext.") and f.endswith(".so"):
+            try:
+                spec = importlib.util.spec_from_file_location("_ext", os.path.join(d, f))
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                return mod
+            except Exception:
+                return None
+    return None
+
+
+def _cpu_step(torch, ref_dcn, oracle, rows, data):
+    """DCN fwd+bwd on (1, 64, rows, 256) and FAC fwd+bwd on (4, 64, rows, 256) on the host CPU."""
+    geom = (3, 3, 1, 1, 1, 1, 1, 1, DG)
+    x, off, msk, go = (data[k][:, :, :rows].contiguous() for k in ("x", "off", "msk", "go_d"))
+    w, b = data["w"], data["b"]
+    t0 = time.perf_counter()
+    if ref_dcn is not None:
+        ref_dcn.dcn_v2_forward(x, w, b, off, msk, *geom)
+        ref_dcn.dcn_v2_backward(x, w, b, off, msk, go, *geom)
+    else:
+        a = [t.numpy() for t in (x, off, msk, w, b)]
+        oracle.dcn_forward(*a, 1, 1, 1, DG, "f32")
+        oracle.dcn_backward(*a, go.numpy(), 1, 1, 1, DG, "f32")
+    t1 = time.perf_counter()
+    xi = data["xi"][:, :, :rows + 4].contiguous().numpy()
+    ker = data["ker"][:, :, :rows].contiguous().numpy()
+    gof = data["go_f"][:, :, :rows].contiguous().numpy()
+    oracle.fac_forward(xi, ker, K_FAC, "f32")
+    oracle.fac_backward(xi, ker, gof, K_FAC, "f32")
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1
+
+
+def cpu_baseline(budget_s=20.0):
+    import torch
+    from oracle import oracle
+    oracle.lib()
+    ref_dcn = _load_ref_dcn_cpu()
+    data = make_inputs(torch, None, 1234)
+    td, tf = _cpu_step(torch, ref_dcn, oracle, 8, data)               # probe: 8 rows
+    rows = int(max(8, min(H, 8 * budget_s / max(td + tf, 1e-6))))
+    td, tf = _cpu_step(torch, ref_dcn, oracle, rows, data)
+    mpix = (B_DCN + B_FAC) * rows * W / 1e6
+    return {"value": round(mpix / (td + tf), 5), "unit": "Mpix/s", "cores": torch.get_num_threads(),
+            "kind": "reference" if ref_dcn is not None else "port",
+            "sample": f"top {rows} of 256 rows of the same step (DCN B=1 + FAC B=4, fwd+bwd): "
+                      f"DCN {td:.2f} s via " + ("the reference's CPU build oracle/_ref/dcn_cpu (serial loops + MKL GEMM)"
+                                               if ref_dcn is not None else "the oracle C port")
+                      + f", FAC {tf:.2f} s via the oracle C port with OpenMP (the reference has no CPU FAC path)"}
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the path on the host cores."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    import torch
+    from oracle import oracle
+    oracle.lib()
+    ref_dcn = _load_ref_dcn_cpu()
+    data = make_inputs(torch, None, 1234)
+    total = args.steps + args.warmup
+    td, tf = _cpu_step(torch, ref_dcn, oracle, 8, data)
+    rows = int(max(4, min(H, 8 * (150.0 / total) / max(td + tf, 1e-6))))
+    for _ in range(args.warmup):
+        _cpu_step(torch, ref_dcn, oracle, rows, data)
+    t0 = time.perf_counter()
+    sd = sf = 0.0
+    for _ in range(args.steps):
+        a, b = _cpu_step(torch, ref_dcn, oracle, rows, data)
+        sd += a; sf += b
+    dt = time.perf_counter() - t0
+    mpix = (B_DCN + B_FAC) * rows * W / 1e6
+    val = round(mpix * args.steps / dt, 5)
+    kind = "reference" if ref_dcn is not None else "port"
+    sample = (f"each step = top {rows} of 256 rows of the step (DCN B=1 + FAC B=4, fwd+bwd); DCN via "
+              + ("oracle/_ref/dcn_cpu (reference CPU build)" if ref_dcn is not None else "oracle C port")
+              + "; FAC via oracle C port + OpenMP (reference has no CPU FAC)")
+    print(json.dumps({
+        "impl": "reference", "metric": "DCNv2+FAC fwd+bwd Mpix/s", "value": val, "unit": "Mpix/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[0]+[1] (DCNv2 B=1 + FAC B=4, 256x256, fwd+bwd), CPU, bounded sample",
+                   "rows_per_step": rows},
+        "cpu_baseline": {"value": val, "unit": "Mpix/s", "cores": torch.get_num_threads(), "kind": kind, "sample": sample},
+        "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "breakdown": {"dcn_s_per_step": round(sd / args.steps, 3), "fac_s_per_step": round(sf / args.steps, 3)},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernels-only", action="store_true",
+                    help="profiling runs: skip the e2e, cold-breakdown and CPU-baseline legs")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -21,67 +21,26 @@
 // Arithmetic follows the reference exactly where it is observable: the (-1, H) x (-1, W)
 // sampling window (im2col_cuda.cu:180), per-corner bounds (:38-48), the coordinate weights
 // (:82-123), and the pad_h-for-both-paddings quirk of the grad_input scatter (:368).
-#include "common.cuh"
+#include "dcn_common.cuh"
 
 #include <algorithm>
+
+namespace ebfi_dcn {
+// tensor-core forward (dcn_tc.cu); returns EBFI_ERR_UNSUPPORTED when the shape is not eligible
+int forward_tc(cudaStream_t st, const DcnDims &d, const float *input, const float *weight, const float *bias,
+               const float *offset, const float *mask, float *output);
+}
 
 namespace {
 
 using ebfi::ceil_div;
+using namespace ebfi_dcn;
 
 constexpr int TP = 64;        // output pixels per tile
 constexpr int COT = 64;       // output channels per tile
-constexpr int KC_MAX = 96;    // rows of the sampled slab (channels-in-chunk * kh*kw)
 constexpr int NT = 256;       // threads per CTA
 constexpr int TPP = TP + 1;   // padded pitch of the backward slab (scalar, conflict-free by row)
 constexpr int GP = TP + 1;    // padded pitch of the grad_output tile
-
-struct DcnDims {
-    int B, C, H, W, Co, Ho, Wo;
-    int kh, kw, sh, sw, ph, pw, dh, dw, dg;
-    int cpg;          // channels per deformable group
-    int cch;          // channels per chunk (<= cpg, cch*KK <= KC_MAX)
-    int nchunk;       // chunks per group
-    int KK;           // kh*kw
-    int ntile;        // pixel tiles per sample
-};
-
-// One bilinear tap: corner indices, validity and weights (im2col_cuda.cu:25-54, :180).
-struct Tap {
-    int i00, i01, i10, i11;    // plane offsets of the four corners
-    bool c00, c01, c10, c11;   // corner inside the image AND sample inside the window
-    float hy, hx, ly, lx;
-};
-
-__device__ __forceinline__ Tap make_tap(float y, float x, int H, int W)
-{
-    Tap t;
-    const bool inside = (y > -1.f) && (x > -1.f) && (y < (float)H) && (x < (float)W);
-    const float fy = floorf(y), fx = floorf(x);
-    const int y0 = (int)fy, x0 = (int)fx;
-    t.ly = y - fy; t.lx = x - fx;
-    t.hy = 1.f - t.ly; t.hx = 1.f - t.lx;
-    const bool ya = y0 >= 0, yb = y0 + 1 <= H - 1, xa = x0 >= 0, xb = x0 + 1 <= W - 1;
-    t.c00 = inside && ya && xa; t.c01 = inside && ya && xb;
-    t.c10 = inside && yb && xa; t.c11 = inside && yb && xb;
-    t.i00 = y0 * W + x0; t.i01 = t.i00 + 1; t.i10 = t.i00 + W; t.i11 = t.i10 + 1;
-    return t;
-}
-
-__device__ __forceinline__ void tap_coords(const DcnDims &d, const float *__restrict__ off_bg,
-                                           const float *__restrict__ mask_bg, int t, int pix,
-                                           float &y, float &x, float &xq, float &m)
-{
-    const size_t plane = (size_t)d.Ho * d.Wo;
-    const int ho = pix / d.Wo, wo = pix - ho * d.Wo;
-    const int i = t / d.kw, j = t - i * d.kw;
-    const float oy = __ldg(off_bg + (size_t)(2 * t) * plane + pix);
-    const float ox = __ldg(off_bg + (size_t)(2 * t + 1) * plane + pix);
-    m = __ldg(mask_bg + (size_t)t * plane + pix);
-    y = (float)(ho * d.sh - d.ph + i * d.dh) + oy;
-    x = (float)(wo * d.sw - d.pw + j * d.dw) + ox;
-    xq = (float)(wo * d.sw - d.ph + j * d.dw) + ox;   // the scatter's x (pad_h quirk, :368)
-}
 
 // ------------------------------------------------------------------ forward ---
 // grid = (pixel tiles per sample, Cout tiles, B). Each CTA walks all deformable groups /
@@ -433,6 +392,13 @@ int ebfi_dcnv2_forward(void *stream, const ebfi_dcn_geom *q, const float *input,
     if (int rc = fill_dims(q, d)) return rc;
     EBFI_REQUIRE(input && weight && bias && offset && mask && output, "dcn_forward: null pointer");
     cudaStream_t st = ebfi::as_stream(stream);
+    // Tensor-core path (dcn_tc.cu) for the shapes it covers; EBFI_DCN_IMPL=simt forces the
+    // CUDA-core kernel below, which handles every shape.
+    const char *impl = getenv("EBFI_DCN_IMPL");
+    if (!(impl && impl[0] == 's')) {
+        const int rc = forward_tc(st, d, input, weight, bias, offset, mask, output);
+        if (rc != EBFI_ERR_UNSUPPORTED) return rc;
+    }
     EBFI_CUDA_OK(cudaFuncSetAttribute(dcn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
     dim3 grid(d.ntile, ceil_div(d.Co, COT), d.B);
     dcn_fwd_kernel<<<grid, NT, kFwdSmem, st>>>(input, weight, bias, offset, mask, output, d);

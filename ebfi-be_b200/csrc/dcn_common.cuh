@@ -1,0 +1,58 @@
+// dcn_common.cuh — geometry and bilinear-tap helpers shared by the DCNv2 kernels
+// (SIMT fallback in dcn.cu, tensor-core path in dcn_tc.cu).
+#pragma once
+#include "common.cuh"
+
+namespace ebfi_dcn {
+
+constexpr int KC_MAX = 96;    // rows of the sampled slab in the SIMT kernels (channels-in-chunk * kh*kw)
+
+struct DcnDims {
+    int B, C, H, W, Co, Ho, Wo;
+    int kh, kw, sh, sw, ph, pw, dh, dw, dg;
+    int cpg;          // channels per deformable group
+    int cch;          // channels per chunk (<= cpg, cch*KK <= KC_MAX)
+    int nchunk;       // chunks per group
+    int KK;           // kh*kw
+    int ntile;        // pixel tiles per sample
+};
+
+// One bilinear tap: corner indices, validity and weights (im2col_cuda.cu:25-54, :180).
+struct Tap {
+    int i00, i01, i10, i11;    // plane offsets of the four corners
+    bool c00, c01, c10, c11;   // corner inside the image AND sample inside the window
+    float hy, hx, ly, lx;
+};
+
+__device__ __forceinline__ Tap make_tap(float y, float x, int H, int W)
+{
+    Tap t;
+    const bool inside = (y > -1.f) && (x > -1.f) && (y < (float)H) && (x < (float)W);
+    const float fy = floorf(y), fx = floorf(x);
+    const int y0 = (int)fy, x0 = (int)fx;
+    t.ly = y - fy; t.lx = x - fx;
+    t.hy = 1.f - t.ly; t.hx = 1.f - t.lx;
+    const bool ya = y0 >= 0, yb = y0 + 1 <= H - 1, xa = x0 >= 0, xb = x0 + 1 <= W - 1;
+    t.c00 = inside && ya && xa; t.c01 = inside && ya && xb;
+    t.c10 = inside && yb && xa; t.c11 = inside && yb && xb;
+    t.i00 = y0 * W + x0; t.i01 = t.i00 + 1; t.i10 = t.i00 + W; t.i11 = t.i10 + 1;
+    return t;
+}
+
+__device__ __forceinline__ void tap_coords(const DcnDims &d, const float *__restrict__ off_bg,
+                                           const float *__restrict__ mask_bg, int t, int pix,
+                                           float &y, float &x, float &xq, float &m)
+{
+    const size_t plane = (size_t)d.Ho * d.Wo;
+    const int ho = pix / d.Wo, wo = pix - ho * d.Wo;
+    const int i = t / d.kw, j = t - i * d.kw;
+    const float oy = __ldg(off_bg + (size_t)(2 * t) * plane + pix);
+    const float ox = __ldg(off_bg + (size_t)(2 * t + 1) * plane + pix);
+    m = __ldg(mask_bg + (size_t)t * plane + pix);
+    y = (float)(ho * d.sh - d.ph + i * d.dh) + oy;
+    x = (float)(wo * d.sw - d.pw + j * d.dw) + ox;
+    xq = (float)(wo * d.sw - d.ph + j * d.dw) + ox;   // the scatter's x (pad_h quirk, :368)
+}
+
+
+}  // namespace ebfi_dcn

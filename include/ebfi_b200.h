@@ -165,6 +165,21 @@ int ebfi_events_to_stack(void *stream, void *xs, void *ys, const void *ts, const
                          int dtype, int64_t n_events, int num_bins, int height, int width,
                          float *stack, int64_t *bounds, int write_back);
 
+/* ---- self test --------------------------------------------------------------- */
+
+/* One-CTA GEMM on the tcgen05 tensor-core path with the 3xTF32 split the DCN kernels use:
+ * C[M x N] = A[M x K] * B[N x K]^T, fp32 in / fp32 out, ~fp32 accuracy.
+ * M in {64, 128}; N <= 128, multiple of 16 (M=128) or 8 (M=64); K multiple of 8.
+ * A is row-major [M][K], or [K][M] when a_mn_major != 0 (M = 128 only); B is [N][K].
+ * Exists to validate descriptors / TMEM plumbing on real hardware; not a product entry. */
+int ebfi_selftest_gemm_tf32x3(void *stream, const float *A, const float *B, float *C,
+                              int M, int N, int K, int a_mn_major);
+
+/* Layout probe: C[128][8] receives, for every element A(m, k) of a 128 x 8 TF32 operand described
+ * by (lbo, sbo, major-ness), the float index inside shared memory that the tensor core fetched.
+ * Documents how the hardware interprets the descriptor fields. */
+int ebfi_selftest_umma_probe(void *stream, float *C, int lbo_bytes, int sbo_bytes, int a_mn_major);
+
 #ifdef __cplusplus
 }
 #endif
