@@ -32,7 +32,8 @@ SIGNATURES = {
     "ebfi_device_arch": (c_int, []),
     "ebfi_dcnv2_output_size": (c_int, [_GEOM_P, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "ebfi_dcnv2_backward_workspace_bytes": (c_size, [_GEOM_P]),
-    "ebfi_dcnv2_forward": (c_int, [c_void, _GEOM_P] + [c_void] * 6),
+    "ebfi_dcnv2_forward_workspace_bytes": (c_size, [_GEOM_P]),
+    "ebfi_dcnv2_forward": (c_int, [c_void, _GEOM_P] + [c_void] * 6 + [c_void, c_size]),
     "ebfi_dcnv2_backward": (c_int, [c_void, _GEOM_P] + [c_void] * 11 + [c_void, c_size]),
     "ebfi_fac_forward": (c_int, [c_void] * 4 + [c_int] * 5),
     "ebfi_fac_backward_workspace_bytes": (c_size, [c_int] * 5),

@@ -28,7 +28,8 @@
 namespace ebfi_dcn {
 // tensor-core forward (dcn_tc.cu); returns EBFI_ERR_UNSUPPORTED when the shape is not eligible
 int forward_tc(cudaStream_t st, const DcnDims &d, const float *input, const float *weight, const float *bias,
-               const float *offset, const float *mask, float *output);
+               const float *offset, const float *mask, float *output, void *workspace, size_t workspace_bytes);
+size_t forward_tc_workspace(const DcnDims &d);
 }
 
 namespace {
@@ -385,8 +386,16 @@ size_t ebfi_dcnv2_backward_workspace_bytes(const ebfi_dcn_geom *q)
     return S * ((size_t)d.Co * d.C * d.KK + d.Co) * sizeof(float) + 256;
 }
 
+size_t ebfi_dcnv2_forward_workspace_bytes(const ebfi_dcn_geom *q)
+{
+    DcnDims d{};
+    if (fill_dims(q, d) != EBFI_OK) return 0;
+    return forward_tc_workspace(d) + 256;
+}
+
 int ebfi_dcnv2_forward(void *stream, const ebfi_dcn_geom *q, const float *input, const float *weight,
-                       const float *bias, const float *offset, const float *mask, float *output)
+                       const float *bias, const float *offset, const float *mask, float *output,
+                       void *workspace, size_t workspace_bytes)
 {
     DcnDims d{};
     if (int rc = fill_dims(q, d)) return rc;
@@ -396,7 +405,7 @@ int ebfi_dcnv2_forward(void *stream, const ebfi_dcn_geom *q, const float *input,
     // CUDA-core kernel below, which handles every shape.
     const char *impl = getenv("EBFI_DCN_IMPL");
     if (!(impl && impl[0] == 's')) {
-        const int rc = forward_tc(st, d, input, weight, bias, offset, mask, output);
+        const int rc = forward_tc(st, d, input, weight, bias, offset, mask, output, workspace, workspace_bytes);
         if (rc != EBFI_ERR_UNSUPPORTED) return rc;
     }
     EBFI_CUDA_OK(cudaFuncSetAttribute(dcn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));

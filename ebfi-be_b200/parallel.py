@@ -1,0 +1,77 @@
+"""Data-parallel plumbing for the alignment ops: one process per GPU, torch.distributed (NCCL over
+NVLink on the GPU box, gloo in the CPU tests).
+
+The three operators shard by batch with no data-path exchange: samples are
+independent in DCNv2 (the reference itself loops over the batch, dcn_v2_cuda.cu:150), FAC has no
+parameters, and every rank encodes its own event windows like the reference's DataLoader workers.
+The only cross-sample reduction on the path is DCNv2's grad_weight / grad_bias (dcn_v2_cuda.cu:203-208);
+in data-parallel training that is one small all-reduce per step, bucketed here into a single flat
+buffer (147 KB + 256 B at the benchmark shape). The reference never all-reduces gradients at all
+(every backward runs under `no_sync`, train_ours.py:250-272) — this is the correct behaviour
+BASELINE.json asks for, not parity with that bug.
+"""
+import torch
+import torch.distributed as dist
+
+
+def world():
+    """(rank, world_size) of the default process group, (0, 1) when not initialised."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_range(n_items, rank=None, world_size=None):
+    """Contiguous [start, end) slice of `n_items` batch entries owned by `rank`; the first
+    n_items % world_size ranks get one extra entry, so every entry is owned exactly once."""
+    if rank is None or world_size is None:
+        rank, world_size = world()
+    base, extra = divmod(n_items, world_size)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def shard_batch(*tensors, rank=None, world_size=None):
+    """Slice every tensor along dim 0 to this rank's shard."""
+    out = []
+    for t in tensors:
+        s, e = shard_range(t.shape[0], rank, world_size)
+        out.append(t[s:e])
+    return out if len(out) > 1 else out[0]
+
+
+def allreduce_weight_grads(grads, group=None, average=False):
+    """Sum (or average) parameter gradients across ranks with ONE collective: the tensors are packed
+    into a flat bucket, all-reduced, and copied back in place. Deterministic for a fixed world size
+    (NCCL/gloo ring order is fixed). Returns the list it was given."""
+    grads = [g for g in grads if g is not None]
+    if not grads or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return grads
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        flat /= dist.get_world_size(group)
+    o = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[o:o + n].view_as(g))
+        o += n
+    return grads
+
+
+def dcn_backward_data_parallel(backward_fn, input, weight, bias, offset, mask, grad_output, *geom, group=None):
+    """Run `backward_fn` (signature of `_ext.dcn_v2_backward`) on this rank's batch shard and
+    all-reduce grad_weight / grad_bias. Returns the shard's grad_input / grad_offset / grad_mask
+    and the GLOBAL grad_weight / grad_bias."""
+    x, off, msk, go = shard_batch(input, offset, mask, grad_output)
+    g_in, g_off, g_msk, g_w, g_b = backward_fn(x.contiguous(), weight, bias, off.contiguous(),
+                                                msk.contiguous(), go.contiguous(), *geom)
+    allreduce_weight_grads([g_w, g_b], group=group)
+    return g_in, g_off, g_msk, g_w, g_b
+
+
+def encode_windows_data_parallel(encode_fn, windows):
+    """Each rank encodes the event windows it owns (no collective): `windows` is a list of argument
+    tuples for `encode_fn`; returns [(global_index, encoded)] for this rank's share."""
+    s, e = shard_range(len(windows))
+    return [(i, encode_fn(*windows[i])) for i in range(s, e)]

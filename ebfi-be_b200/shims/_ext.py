@@ -66,8 +66,11 @@ def dcn_v2_forward(input, weight, bias, offset, mask, kernel_h, kernel_w, stride
     input, weight, bias, offset, mask = (t.contiguous() for t in (input, weight, bias, offset, mask))
     with torch.cuda.device(input.device):
         output = torch.empty((g.batch, g.channels_out, ho, wo), dtype=input.dtype, device=input.device)
-        L.check(L.load().ebfi_dcnv2_forward(L.stream_ptr(input.device), g, L.ptr(input), L.ptr(weight),
-                                            L.ptr(bias), L.ptr(offset), L.ptr(mask), L.ptr(output)),
+        lib = L.load()
+        nbytes = lib.ebfi_dcnv2_forward_workspace_bytes(g)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=input.device)
+        L.check(lib.ebfi_dcnv2_forward(L.stream_ptr(input.device), g, L.ptr(input), L.ptr(weight),
+                                       L.ptr(bias), L.ptr(offset), L.ptr(mask), L.ptr(output), L.ptr(ws), nbytes),
                 "dcn_v2_forward")
     return output
 

@@ -70,10 +70,14 @@ typedef struct ebfi_dcn_geom {
  * when the geometry is inconsistent (non-positive sizes, C % dg != 0, ...). */
 int ebfi_dcnv2_output_size(const ebfi_dcn_geom *g, int *height_out, int *width_out);
 
-/* Scratch the backward pass needs (per-CTA grad_weight / grad_bias partials and
- * the col-grad staging buffer). The forward pass needs none: the column buffer
- * of the reference (dcn_v2_cuda.cu:68) never exists in HBM here. */
+/* Scratch the backward pass needs (per-CTA grad_weight / grad_bias partials). The column
+ * buffer of the reference (dcn_v2_cuda.cu:68) never exists in HBM in either pass. */
 size_t ebfi_dcnv2_backward_workspace_bytes(const ebfi_dcn_geom *g);
+
+/* Scratch for the forward pass: the TF32 hi/lo weight images the tensor-core kernel streams
+ * into shared memory (2 x the weight tensor). 16-byte aligned device memory. Without it (NULL /
+ * too small) the forward falls back to its CUDA-core kernel, which needs none. */
+size_t ebfi_dcnv2_forward_workspace_bytes(const ebfi_dcn_geom *g);
 
 /* out[b,co,h,w] = bias[co] + sum_{c,i,j} weight[co,c,i,j] * mask * bilinear(input[b,c], ...)
  * Replaces dcn_v2_cuda_forward (dcn_v2_cuda.cu:20-95). `output` is written in
@@ -81,7 +85,7 @@ size_t ebfi_dcnv2_backward_workspace_bytes(const ebfi_dcn_geom *g);
 int ebfi_dcnv2_forward(void *stream, const ebfi_dcn_geom *g,
                        const float *input, const float *weight, const float *bias,
                        const float *offset, const float *mask,
-                       float *output);
+                       float *output, void *workspace, size_t workspace_bytes);
 
 /* All five gradients of dcn_v2_cuda_backward (dcn_v2_cuda.cu:97-216), every
  * output written in full. grad_offset / grad_mask / grad_weight / grad_bias are
