@@ -30,6 +30,11 @@ namespace ebfi_dcn {
 int forward_tc(cudaStream_t st, const DcnDims &d, const float *input, const float *weight, const float *bias,
                const float *offset, const float *mask, float *output, void *workspace, size_t workspace_bytes);
 size_t forward_tc_workspace(const DcnDims &d);
+// tensor-core backward (dcn_bwd_tc.cu); splits == 0 when the shape is not eligible
+int backward_tc_splits(const DcnDims &d);
+int backward_tc(cudaStream_t st, const DcnDims &d, const float *input, const float *weight, const float *offset,
+                const float *mask, const float *gout, float *gin, float *goff, float *gmask, float *gw_part,
+                float *gb_part, int S);
 }
 
 namespace {
@@ -382,7 +387,7 @@ size_t ebfi_dcnv2_backward_workspace_bytes(const ebfi_dcn_geom *q)
 {
     DcnDims d{};
     if (fill_dims(q, d) != EBFI_OK) return 0;
-    const size_t S = (size_t)bwd_splits(d);
+    const size_t S = (size_t)std::max(bwd_splits(d), backward_tc_splits(d));
     return S * ((size_t)d.Co * d.C * d.KK + d.Co) * sizeof(float) + 256;
 }
 
@@ -427,24 +432,33 @@ int ebfi_dcnv2_backward(void *stream, const ebfi_dcn_geom *q, const float *input
     EBFI_REQUIRE(input && weight && offset && mask && grad_output && grad_input && grad_offset &&
                  grad_mask && grad_weight && grad_bias, "dcn_backward: null pointer");
     cudaStream_t st = ebfi::as_stream(stream);
-    const int S = bwd_splits(d);
+    const char *impl = getenv("EBFI_DCN_IMPL");
+    const int S_tc = (impl && impl[0] == 's') ? 0 : backward_tc_splits(d);
+    const int S = S_tc > 0 ? S_tc : bwd_splits(d);
     const size_t n_w = (size_t)d.Co * d.C * d.KK, n_b = (size_t)d.Co;
     const size_t need = (size_t)S * (n_w + n_b) * sizeof(float);
     if (!workspace || workspace_bytes < need)
         return ebfi::fail(EBFI_ERR_WORKSPACE, "dcn_backward: workspace %zu < %zu bytes", workspace_bytes, need);
     float *gw_part = static_cast<float *>(workspace);
     float *gb_part = gw_part + (size_t)S * n_w;
-    EBFI_CUDA_OK(cudaFuncSetAttribute(dcn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
     EBFI_CUDA_OK(cudaMemsetAsync(grad_input, 0, (size_t)d.B * d.C * d.H * d.W * sizeof(float), st));
-    const int n_cot = ceil_div(d.Co, COT);
-    // Chunks of one group accumulate into the same grad_offset / grad_mask elements; separate,
-    // stream-ordered launches keep that read-modify-write race-free. nchunk is 1 unless
-    // channels-per-group * taps exceeds the KC_MAX-row slab.
-    for (int ch = 0; ch < d.nchunk; ++ch) {
-        dim3 grid(S, d.dg, n_cot);
-        dcn_bwd_kernel<<<grid, NT, kBwdSmem, st>>>(input, weight, offset, mask, grad_output, grad_input,
-                                                   grad_offset, grad_mask, gw_part, gb_part, d, ch);
-        EBFI_LAUNCH_OK("dcn_bwd_kernel");
+    if (S_tc > 0) {
+        // tensor-core path (dcn_bwd_tc.cu): cpg == 8, Cout == 64
+        if (int rc = backward_tc(st, d, input, weight, offset, mask, grad_output, grad_input, grad_offset, grad_mask,
+                                 gw_part, gb_part, S))
+            return rc;
+    } else {
+        EBFI_CUDA_OK(cudaFuncSetAttribute(dcn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
+        const int n_cot = ceil_div(d.Co, COT);
+        // Chunks of one group accumulate into the same grad_offset / grad_mask elements; separate,
+        // stream-ordered launches keep that read-modify-write race-free. nchunk is 1 unless
+        // channels-per-group * taps exceeds the KC_MAX-row slab.
+        for (int ch = 0; ch < d.nchunk; ++ch) {
+            dim3 grid(S, d.dg, n_cot);
+            dcn_bwd_kernel<<<grid, NT, kBwdSmem, st>>>(input, weight, offset, mask, grad_output, grad_input,
+                                                       grad_offset, grad_mask, gw_part, gb_part, d, ch);
+            EBFI_LAUNCH_OK("dcn_bwd_kernel");
+        }
     }
     const int n = (int)(n_w + n_b);
     dcn_reduce_partials<<<ceil_div(n, 256), 256, 0, st>>>(gw_part, gb_part, grad_weight, grad_bias, S, (int)n_w, (int)n_b);

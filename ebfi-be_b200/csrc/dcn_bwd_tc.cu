@@ -1,0 +1,341 @@
+// dcn_bwd_tc.cu — DCNv2 backward with both weight contractions on the sm_100a tensor cores.
+//
+// Group-specialised persistent CTAs, like the CUDA-core kernel in dcn.cu: CTA (s, g) owns
+// deformable group g (8 channels x KK taps = the K' columns) and walks the 128-pixel tiles
+// s, s+S, ... of all samples. Per tile, everything comes from ONE pass over the pixels:
+//   GEMM1  colgrad[128 px x K'] = gO_tile[128 x Co] . W_g[Co x K']       (tcgen05, bf16x3, D1 in TMEM)
+//   each thread (pixel p, tap) reads its 8 colgrad values straight from TMEM (lane = pixel),
+//   gathers the 8 channels at the 4 bilinear corners and produces
+//       grad_mask, grad_offset (one owner thread per element: no atomics, fixed order),
+//       the grad_input scatter (fp32 red.global.add, like the reference's atomicAdd, :249),
+//       and the recomputed column value * mask, written as the B operand of
+//   GEMM3  gW_g[Co x K'] += gO_tile^T[Co x 128 px] . col[128 px x K']     (tcgen05, accumulates in TMEM
+//          across ALL tiles of the CTA; an extra all-ones column yields grad_bias for free).
+// At the end the CTA writes its [Co x K'] partial; dcn_reduce_partials (dcn.cu) sums the S partials
+// in a fixed order. The reference runs 3 kernels + 3 cuBLAS GEMMs per sample and materialises the
+// 151 MB column buffer twice (dcn_v2_cuda.cu:150-211).
+//
+// Operand precision: bf16 hi/lo pairs, 3 MMAs per product (umma.cuh) -> ~2^-16 relative, inside the
+// 1e-4 gradient gate with a wide margin, at half the shared memory of TF32 pairs (two CTAs per SM).
+// grad_output is needed in two K-major layouts ([px][co] for GEMM1, [co][px] for GEMM3) because
+// kind::tf32/f16 MN-major no-swizzle operands are not usable; the [px][co] copy
+// shares its storage with the column operand, which is written only after GEMM1 has completed.
+#include "dcn_common.cuh"
+#include "umma.cuh"
+
+#include <algorithm>
+
+namespace ebfi_dcn {
+
+namespace {
+
+using ebfi::ceil_div;
+
+constexpr int TM = 128, TH = 8, TW = 16, NR = 3, NTHR = TM * NR;
+constexpr int CS = 8;                 // channels per group handled by this kernel
+constexpr int TMEM_COLS = 256;
+constexpr int COL_LBO = 144;          // padded K-chunk pitch of the column operand (bank-conflict-free 2-byte stores)
+
+struct BwdPlan {
+    int TPR;             // taps per thread row
+    int Kc;              // CS * KK  (real K' columns)
+    int N1;              // GEMM1 N: Kc rounded up to 16
+    int N3;              // GEMM3 N: Kc + 1 (ones column -> grad_bias) rounded up to 8
+    int kch1;            // Co / 8: K chunks of the Co-contraction operands
+    int tiles_x, tiles_y;
+    int wt_part, p_part, q_part, col_part, col_sbo;    // bytes of one (hi or lo) image
+    int smem;
+};
+
+__device__ __forceinline__ void st_bf16(unsigned char *base, int off, unsigned short v)
+{
+    *reinterpret_cast<unsigned short *>(base + off) = v;
+}
+
+// eight bf16 values -> one 16-byte K chunk
+__device__ __forceinline__ void st_bf16x8(unsigned char *base, int off, const unsigned short (&v)[8])
+{
+    const uint32_t a = v[0] | ((uint32_t)v[1] << 16), b = v[2] | ((uint32_t)v[3] << 16);
+    const uint32_t c = v[4] | ((uint32_t)v[5] << 16), e = v[6] | ((uint32_t)v[7] << 16);
+    *reinterpret_cast<uint4 *>(base + off) = make_uint4(a, b, c, e);
+}
+
+__global__ void __launch_bounds__(NTHR, 2)
+dcn_bwd_tc_kernel(const float *__restrict__ input, const float *__restrict__ weight,
+                  const float *__restrict__ offset, const float *__restrict__ mask,
+                  const float *__restrict__ gout, float *__restrict__ gin,
+                  float *__restrict__ goff, float *__restrict__ gmask,
+                  float *__restrict__ gw_part, float *__restrict__ gb_part, DcnDims d, BwdPlan pl)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char *wt_hi = smem, *wt_lo = smem + pl.wt_part;                       // B of GEMM1: [N1 rows k'][Co]
+    unsigned char *q_hi = smem + 2 * pl.wt_part, *q_lo = q_hi + pl.q_part;         // A of GEMM3: [Co rows][128 px]
+    unsigned char *u_base = q_lo + pl.q_part;                                      // union: P (A of GEMM1) | col (B of GEMM3)
+    unsigned char *p_hi = u_base, *p_lo = u_base + pl.p_part;                      //   P: [128 px rows][Co]
+    unsigned char *c_hi = u_base, *c_lo = u_base + pl.col_part;                    //   col: [N3 rows k'][128 px], LBO 144
+    __shared__ __align__(8) uint64_t bar1, bar3;
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int p = tid % TM, r = tid / TM;
+    const int S = gridDim.x, s = blockIdx.x, g = blockIdx.y;
+    const int c0 = g * d.cpg;
+    const int npix = d.Ho * d.Wo, Kdim = d.C * d.KK;
+    const size_t plane = (size_t)npix, in_plane = (size_t)d.H * d.W;
+    const int ntile = pl.tiles_x * pl.tiles_y;
+
+    if (warp == 0) umma::tmem_alloc<TMEM_COLS>(&tmem_slot);
+    if (tid == 0) { umma::mbar_init(&bar1, 1); umma::mbar_init(&bar3, 1); umma::mbar_fence_init(); }
+    // ---- W_g^T, resident for the whole CTA: wt[k'][co] = weight[co][(c0 + cc) * KK + tap], k' = tap * 8 + cc
+    for (int e = tid; e < pl.N1 * d.Co; e += NTHR) {
+        const int j = e & 7, rr = (e >> 3) & 7, rest = e >> 6;
+        const int kc = rest % pl.kch1, rg = rest / pl.kch1;
+        const int kp = rg * 8 + rr, co = kc * 8 + j;
+        unsigned short hi = 0, lo = 0;
+        if (kp < pl.Kc) {
+            const int t = kp >> 3, cc = kp & 7;
+            umma::split_bf16(__ldg(weight + (size_t)co * Kdim + (size_t)(c0 + cc) * d.KK + t), hi, lo);
+        }
+        st_bf16(wt_hi, e * 2, hi); st_bf16(wt_lo, e * 2, lo);
+    }
+    umma::fence_smem_to_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t d1 = tmem, d3h = tmem + pl.N1, d3x = tmem + pl.N1 + pl.N3;
+    const uint32_t idesc1 = umma::instr_desc_bf16(TM, pl.N1), idesc3 = umma::instr_desc_bf16(d.Co, pl.N3);
+    const uint32_t lane_base = (uint32_t)(warp & 3) * 32u;
+
+    uint32_t ph1 = 0, ph3 = 0;
+    int ntiles_done = 0;
+    for (int tile = s; tile < d.B * ntile; tile += S, ++ntiles_done) {
+        const int b = tile / ntile, tl = tile % ntile;
+        const int ty0 = (tl / pl.tiles_x) * TH, tx0 = (tl % pl.tiles_x) * TW;
+        const int ho = ty0 + p / TW, wo = tx0 + p % TW;
+        const bool valid = ho < d.Ho && wo < d.Wo;
+        const int pix = ho * d.Wo + wo;
+        const float *go_b = gout + (size_t)b * d.Co * plane;
+        if (ntiles_done > 0) {                       // GEMM3 of the previous tile has read Q and col
+            umma::mbar_wait(&bar3, ph3);
+            ph3 ^= 1;
+        }
+        // ---- grad_output tile in both K-major layouts (bf16 hi/lo)
+        // P[px][co]: item = (pixel, chunk of 8 co); lanes run over pixels -> coalesced plane reads
+        for (int it = tid; it < TM * pl.kch1; it += NTHR) {
+            const int pp = it % TM, kc = it / TM;
+            const int hh = ty0 + pp / TW, ww = tx0 + pp % TW;
+            unsigned short hi[8], lo[8];
+            const bool ok = hh < d.Ho && ww < d.Wo;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float v = ok ? __ldg(go_b + (size_t)(kc * 8 + j) * plane + (size_t)hh * d.Wo + ww) : 0.f;
+                umma::split_bf16(v, hi[j], lo[j]);
+            }
+            const int off = (pp >> 3) * (pl.kch1 * 128) + kc * 128 + (pp & 7) * 16;
+            st_bf16x8(p_hi, off, hi); st_bf16x8(p_lo, off, lo);
+        }
+        // Q[co][px]: item = (co, chunk of 8 consecutive tile pixels = half a tile row)
+        for (int it = tid; it < d.Co * (TM / 8); it += NTHR) {
+            const int pc = it % (TM / 8), co = it / (TM / 8);
+            const int hh = ty0 + (pc * 8) / TW, ww = tx0 + (pc * 8) % TW;
+            unsigned short hi[8], lo[8];
+            float v[8];
+            const float *src = go_b + (size_t)co * plane + (size_t)hh * d.Wo + ww;
+            if ((d.Wo & 3) == 0 && hh < d.Ho && ww + 7 < d.Wo) {
+                const float4 a = __ldg(reinterpret_cast<const float4 *>(src)), c = __ldg(reinterpret_cast<const float4 *>(src) + 1);
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = (hh < d.Ho && ww + j < d.Wo) ? __ldg(src + j) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) umma::split_bf16(v[j], hi[j], lo[j]);
+            const int off = (co >> 3) * ((TM / 8) * 128) + pc * 128 + (co & 7) * 16;
+            st_bf16x8(q_hi, off, hi); st_bf16x8(q_lo, off, lo);
+        }
+        umma::fence_smem_to_async();
+        __syncthreads();
+        // ---- GEMM1: D1[px][k'] = P . Wt^T   (K = Co)
+        if (tid == 0) {
+            umma::fence_after_sync();
+            for (int ks = 0; ks < d.Co / 16; ++ks) {
+                const uint32_t ko = ks * 256u, sb = pl.kch1 * 128u;
+                const uint64_t ah = umma::smem_desc(umma::smem_u32(p_hi) + ko, 128, sb), al = umma::smem_desc(umma::smem_u32(p_lo) + ko, 128, sb);
+                const uint64_t bh = umma::smem_desc(umma::smem_u32(wt_hi) + ko, 128, sb), bl = umma::smem_desc(umma::smem_u32(wt_lo) + ko, 128, sb);
+                umma::mma_f16(d1, al, bh, idesc1, ks > 0);
+                umma::mma_f16(d1, ah, bl, idesc1, true);
+                umma::mma_f16(d1, ah, bh, idesc1, true);
+            }
+            umma::commit(&bar1);
+        }
+        // ---- sampling positions of this thread's taps (overlaps GEMM1)
+        const float *off_bg = offset + ((size_t)b * d.dg + g) * 2 * d.KK * plane;
+        const float *mask_bg = mask + ((size_t)b * d.dg + g) * d.KK * plane;
+        umma::mbar_wait(&bar1, ph1);                 // D1 complete; P is dead, its storage becomes `col`
+        ph1 ^= 1;
+        umma::fence_after_sync();
+        for (int sidx = 0; sidx < pl.TPR; ++sidx) {
+            const int t = r * pl.TPR + sidx;
+            if (t >= d.KK) break;
+            float gc[8];
+            umma::tmem_ld8(umma::tmem_addr(tmem, lane_base, t * 8), gc);     // colgrad[p][t*8 .. t*8+7]
+            umma::tmem_ld_wait();
+            float colv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) colv[j] = 0.f;
+            if (valid) {
+                float y, x, xq, m;
+                tap_coords(d, off_bg, mask_bg, t, pix, y, x, xq, m);
+                const Tap tp = make_tap(y, x, d.H, d.W);
+                const Tap tq = (d.ph == d.pw) ? tp : make_tap(y, xq, d.H, d.W);
+                const float w1 = tp.hy * tp.hx, w2 = tp.hy * tp.lx, w3 = tp.ly * tp.hx, w4 = tp.ly * tp.lx;
+                const float q1 = tq.hy * tq.hx, q2 = tq.hy * tq.lx, q3 = tq.ly * tq.hx, q4 = tq.ly * tq.lx;
+                float s_m = 0.f, s_y = 0.f, s_x = 0.f;
+                const float *ip = input + ((size_t)b * d.C + c0) * in_plane;
+                float *gp = gin + ((size_t)b * d.C + c0) * in_plane;
+#pragma unroll
+                for (int cc = 0; cc < CS; ++cc, ip += in_plane, gp += in_plane) {
+                    const float v1 = tp.c00 ? __ldg(ip + tp.i00) : 0.f;
+                    const float v2 = tp.c01 ? __ldg(ip + tp.i01) : 0.f;
+                    const float v3 = tp.c10 ? __ldg(ip + tp.i10) : 0.f;
+                    const float v4 = tp.c11 ? __ldg(ip + tp.i11) : 0.f;
+                    const float val = w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4;
+                    s_m += gc[cc] * val;                                            // grad_mask (im2col_cuda.cu:311)
+                    const float wy = -tp.hx * v1 - tp.lx * v2 + tp.hx * v3 + tp.lx * v4;   // coordinate weights (:99-120)
+                    const float wx = -tp.hy * v1 + tp.hy * v2 - tp.ly * v3 + tp.ly * v4;
+                    const float top = gc[cc] * m;
+                    s_y += wy * top;
+                    s_x += wx * top;
+                    if (tq.c00) atomicAdd(gp + tq.i00, q1 * top);                   // grad_input scatter (:236-251)
+                    if (tq.c01) atomicAdd(gp + tq.i01, q2 * top);
+                    if (tq.c10) atomicAdd(gp + tq.i10, q3 * top);
+                    if (tq.c11) atomicAdd(gp + tq.i11, q4 * top);
+                    colv[cc] = val * m;
+                }
+                float *gy = goff + (((size_t)b * d.dg + g) * 2 * d.KK + 2 * t) * plane + pix;
+                gy[0] = s_y; gy[plane] = s_x;
+                gmask[(((size_t)b * d.dg + g) * d.KK + t) * plane + pix] = s_m;
+            }
+            // column operand: col[k' = t*8+cc][px = p]; rows t*8..t*8+7 are one 8-row group
+            const int off = t * pl.col_sbo + (p >> 3) * COL_LBO + (p & 7) * 2;
+#pragma unroll
+            for (int cc = 0; cc < CS; ++cc) {
+                unsigned short hi, lo;
+                umma::split_bf16(colv[cc], hi, lo);
+                st_bf16(c_hi, off + cc * 16, hi); st_bf16(c_lo, off + cc * 16, lo);
+            }
+        }
+        // last 8-row group: the ones column (grad_bias) and zero padding; rewritten every tile because
+        // the grad_output copy P overlays it
+        for (int it = tid; it < 8 * TM; it += NTHR) {
+            const int pp = it % TM, rr = it / TM;
+            const int hh = ty0 + pp / TW, ww = tx0 + pp % TW;
+            const int row = pl.Kc + rr;
+            if (row < pl.N3) {
+                const unsigned short one = (rr == 0 && hh < d.Ho && ww < d.Wo) ? 0x3F80 : 0;   // bf16(1.0)
+                const int off = (row >> 3) * pl.col_sbo + (pp >> 3) * COL_LBO + (row & 7) * 16 + (pp & 7) * 2;
+                st_bf16(c_hi, off, one); st_bf16(c_lo, off, 0);
+            }
+        }
+        umma::fence_smem_to_async();
+        umma::fence_before_sync();                   // orders this thread's tcgen05.ld of D1 before the sync
+        __syncthreads();
+        // ---- GEMM3: D3[co][k'] += Q . col^T   (K = 128 tile pixels), accumulated across tiles
+        if (tid == 0) {
+            umma::fence_after_sync();
+            for (int ks = 0; ks < TM / 16; ++ks) {
+                const uint32_t qo = ks * 256u, co_ = ks * 2u * COL_LBO, qsb = (TM / 8) * 128u;
+                const uint64_t ah = umma::smem_desc(umma::smem_u32(q_hi) + qo, 128, qsb), al = umma::smem_desc(umma::smem_u32(q_lo) + qo, 128, qsb);
+                const uint64_t bh = umma::smem_desc(umma::smem_u32(c_hi) + co_, COL_LBO, pl.col_sbo);
+                const uint64_t bl = umma::smem_desc(umma::smem_u32(c_lo) + co_, COL_LBO, pl.col_sbo);
+                const bool acc = ntiles_done > 0 || ks > 0;
+                umma::mma_f16(d3x, al, bh, idesc3, acc);
+                umma::mma_f16(d3x, ah, bl, idesc3, true);
+                umma::mma_f16(d3h, ah, bh, idesc3, acc);
+            }
+            umma::commit(&bar3);
+        }
+    }
+    // ---- partials of this CTA: gw_part[s][co][(c0+cc)*KK + t], gb_part[s][co]
+    if (ntiles_done > 0) {
+        umma::mbar_wait(&bar3, ph3);
+        umma::fence_after_sync();
+    }
+    // D3 is an M = Co accumulator: Co = 64 -> row co = 16*q + l lives in lane 32*q + l (l < 16);
+    // Co = 128 -> row = lane. Thread rows r split the 8-column blocks.
+    const int q4 = warp & 3;
+    const int co = (d.Co == 128) ? (q4 * 32 + lane) : (lane < 16 ? q4 * 16 + lane : -1);
+    for (int cb = r * 8; cb < pl.N3; cb += NR * 8) {
+        float v[8], u[8];
+        if (ntiles_done > 0) {
+            umma::tmem_ld8(umma::tmem_addr(tmem, lane_base, pl.N1 + cb), v);
+            umma::tmem_ld8(umma::tmem_addr(tmem, lane_base, pl.N1 + pl.N3 + cb), u);
+            umma::tmem_ld_wait();
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = u[i] = 0.f;
+        }
+        if (co >= 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int kp = cb + i;
+                const float val = v[i] + u[i];
+                if (kp < pl.Kc)
+                    gw_part[((size_t)s * d.Co + co) * Kdim + (size_t)(c0 + (kp & 7)) * d.KK + (kp >> 3)] = val;
+                else if (kp == pl.Kc && g == 0)
+                    gb_part[(size_t)s * d.Co + co] = val;
+            }
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc<TMEM_COLS>(tmem);
+}
+
+bool make_plan(const DcnDims &d, BwdPlan &pl)
+{
+    if (d.cpg != CS || d.Co != 64) return false;          // other shapes: CUDA-core kernel in dcn.cu
+    pl.TPR = ceil_div(d.KK, NR);
+    pl.Kc = CS * d.KK;
+    pl.N1 = ebfi::round_up(pl.Kc, 16);
+    pl.N3 = ebfi::round_up(pl.Kc + 1, 8);
+    if (pl.N1 + 2 * pl.N3 > TMEM_COLS) return false;      // 3x3: 80 + 2*80
+    pl.kch1 = d.Co / 8;
+    pl.tiles_x = ceil_div(d.Wo, TW);
+    pl.tiles_y = ceil_div(d.Ho, TH);
+    pl.wt_part = pl.N1 * d.Co * 2;
+    pl.p_part = TM * d.Co * 2;
+    pl.q_part = d.Co * TM * 2;
+    pl.col_sbo = (TM / 8) * COL_LBO;
+    pl.col_part = (pl.N3 / 8) * pl.col_sbo;
+    pl.smem = 2 * pl.wt_part + 2 * pl.q_part + 2 * std::max(pl.p_part, pl.col_part);
+    return pl.smem <= 110 * 1024;
+}
+
+}  // namespace
+
+int backward_tc_splits(const DcnDims &d)
+{
+    BwdPlan pl{};
+    if (!make_plan(d, pl)) return 0;
+    const int tiles = d.B * pl.tiles_x * pl.tiles_y;
+    return std::max(1, std::min(tiles, ceil_div(2 * ebfi::sm_count(), d.dg)));
+}
+
+// Launches the tensor-core backward main kernel (grad_input must already be zero). Partials:
+// gw_part[S][Co][C*KK], gb_part[S][Co] with S = backward_tc_splits(d).
+int backward_tc(cudaStream_t st, const DcnDims &d, const float *input, const float *weight, const float *offset,
+                const float *mask, const float *gout, float *gin, float *goff, float *gmask, float *gw_part,
+                float *gb_part, int S)
+{
+    BwdPlan pl{};
+    if (!make_plan(d, pl)) return EBFI_ERR_UNSUPPORTED;
+    EBFI_CUDA_OK(cudaFuncSetAttribute(dcn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
+    dim3 grid(S, d.dg);
+    dcn_bwd_tc_kernel<<<grid, NTHR, pl.smem, st>>>(input, weight, offset, mask, gout, gin, goff, gmask, gw_part, gb_part, d, pl);
+    EBFI_LAUNCH_OK("dcn_bwd_tc_kernel");
+    return EBFI_OK;
+}
+
+}  // namespace ebfi_dcn

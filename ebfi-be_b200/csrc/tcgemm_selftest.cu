@@ -136,6 +136,92 @@ extern "C" int ebfi_selftest_gemm_tf32x3(void *stream, const float *A, const flo
     return EBFI_OK;
 }
 
+// ---- bf16x3 variant ---------------------------------------------------------------------
+// Same GEMM with bf16 hi/lo pairs and kind::f16 MMAs (K = 16 per instruction); B may use a padded
+// LBO (144 B between K chunks), which the DCN backward uses to keep its 2-byte operand stores free
+// of bank conflicts.
+namespace {
+__global__ void __launch_bounds__(128)
+tc_gemm_bf16_selftest_kernel(const float *__restrict__ A, const float *__restrict__ B, float *__restrict__ C,
+                             int M, int N, int K, int b_lbo)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    // A: [M/8][K/8 chunks][8][8] bf16, LBO 128; B: [N/8][K/8 chunks at b_lbo][8 rows x 16 B]
+    const int kch = K / 8;
+    const int a_part = 128 * K * 2, b_sbo = kch * b_lbo, b_part = (128 / 8) * b_sbo;
+    unsigned short *a_hi = reinterpret_cast<unsigned short *>(smem), *a_lo = reinterpret_cast<unsigned short *>(smem + a_part);
+    unsigned char *b_hi = smem + 2 * a_part, *b_lo = smem + 2 * a_part + b_part;
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+    if (warp == 0) umma::tmem_alloc<256>(&tmem_slot);
+    if (tid == 0) { umma::mbar_init(&bar, 1); umma::mbar_fence_init(); }
+    for (int e = tid; e < M * K; e += blockDim.x) {
+        const int r = e / K, k = e % K;
+        unsigned short hi, lo;
+        umma::split_bf16(A[(size_t)r * K + k], hi, lo);
+        const int off = (r / 8) * (kch * 64) + (k / 8) * 64 + (r % 8) * 8 + (k % 8);
+        a_hi[off] = hi; a_lo[off] = lo;
+    }
+    for (int e = tid; e < N * K; e += blockDim.x) {
+        const int r = e / K, k = e % K;
+        unsigned short hi, lo;
+        umma::split_bf16(B[(size_t)r * K + k], hi, lo);
+        const int off = (r / 8) * b_sbo + (k / 8) * b_lbo + (r % 8) * 16 + (k % 8) * 2;
+        *reinterpret_cast<unsigned short *>(b_hi + off) = hi;
+        *reinterpret_cast<unsigned short *>(b_lo + off) = lo;
+    }
+    umma::fence_smem_to_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    if (tid == 0) {
+        const uint32_t idesc = umma::instr_desc_bf16(M, N);
+        for (int ks = 0; ks < K / 16; ++ks) {
+            const uint32_t ao = ks * 256, bo = ks * 2 * b_lbo;
+            const uint64_t dah = umma::smem_desc(umma::smem_u32(a_hi) + ao, 128, kch * 128);
+            const uint64_t dal = umma::smem_desc(umma::smem_u32(a_lo) + ao, 128, kch * 128);
+            const uint64_t dbh = umma::smem_desc(umma::smem_u32(b_hi) + bo, b_lbo, b_sbo);
+            const uint64_t dbl = umma::smem_desc(umma::smem_u32(b_lo) + bo, b_lbo, b_sbo);
+            umma::mma_f16(tmem + N, dal, dbh, idesc, ks > 0);
+            umma::mma_f16(tmem + N, dah, dbl, idesc, true);
+            umma::mma_f16(tmem, dah, dbh, idesc, ks > 0);
+        }
+        umma::commit(&bar);
+    }
+    umma::mbar_wait(&bar, 0);
+    umma::fence_after_sync();
+    const int row = (M == 128) ? tid : (lane < 16 ? warp * 16 + lane : -1);
+    for (int c0 = 0; c0 < N; c0 += 8) {
+        float v[8], u[8];
+        umma::tmem_ld8(umma::tmem_addr(tmem, warp * 32, c0), v);
+        umma::tmem_ld8(umma::tmem_addr(tmem, warp * 32, N + c0), u);
+        umma::tmem_ld_wait();
+        if (row >= 0 && row < M)
+            for (int j = 0; j < 8; ++j) C[(size_t)row * N + c0 + j] = v[j] + u[j];
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc<256>(tmem);
+}
+}  // namespace
+
+extern "C" int ebfi_selftest_gemm_bf16x3(void *stream, const float *A, const float *B, float *C, int M, int N,
+                                         int K, int b_lbo_bytes)
+{
+    EBFI_REQUIRE(A && B && C, "selftest_gemm_bf16: null pointer");
+    EBFI_REQUIRE(M == 128 || M == 64, "selftest_gemm_bf16: M must be 64 or 128");
+    EBFI_REQUIRE(N >= 8 && N <= 128 && N % (M == 128 ? 16 : 8) == 0, "selftest_gemm_bf16: bad N");
+    EBFI_REQUIRE(K > 0 && K % 16 == 0 && K <= 128, "selftest_gemm_bf16: K must be a multiple of 16, <= 128");
+    EBFI_REQUIRE(b_lbo_bytes >= 128 && b_lbo_bytes % 16 == 0 && b_lbo_bytes <= 256, "selftest_gemm_bf16: bad LBO");
+    const int smem = 2 * 128 * K * 2 + 2 * 16 * (K / 8) * b_lbo_bytes;
+    EBFI_CUDA_OK(cudaFuncSetAttribute(tc_gemm_bf16_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    tc_gemm_bf16_selftest_kernel<<<1, 128, smem, ebfi::as_stream(stream)>>>(A, B, C, M, N, K, b_lbo_bytes);
+    EBFI_LAUNCH_OK("tc_gemm_bf16_selftest_kernel");
+    return EBFI_OK;
+}
+
 // ---- layout probe -----------------------------------------------------------------------
 // Fills 64 KB of shared memory with "my own float index" (split into low 11 bits / high bits so
 // both halves are exact TF32 numbers) and multiplies it, as operand A (128 x 8) under the given

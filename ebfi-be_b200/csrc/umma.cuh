@@ -17,6 +17,7 @@
 // dropped lo*lo term and the truncation of lo to TF32 are both ~2^-22 relative.
 #pragma once
 #include <cstdint>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 namespace umma {
@@ -32,6 +33,18 @@ __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo)
 {
     hi = tf32_hi(x);
     lo = x - hi;
+}
+
+// ---- bf16 pair split ("bf16x3") -----------------------------------------------------
+// x ~= hi + lo with hi = bf16(x), lo = bf16(x - hi): 16 significand bits, products
+// lo_a*hi_b + hi_a*lo_b + hi_a*hi_b carry ~2^-16 relative error — used where the gate is 1e-4
+// (gradients) because the operands take half the shared memory of the TF32 pair.
+__device__ __forceinline__ void split_bf16(float x, unsigned short &hi, unsigned short &lo)
+{
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+    hi = __bfloat16_as_ushort(h);
+    lo = __bfloat16_as_ushort(l);
 }
 
 // ---- descriptors ------------------------------------------------------------------
@@ -56,6 +69,12 @@ __host__ __device__ constexpr uint32_t instr_desc_tf32(int M, int N, int a_mn_ma
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// kind::f16 with BF16 operands, fp32 accumulation: a/b_format = 1.
+__host__ __device__ constexpr uint32_t instr_desc_bf16(int M, int N)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // ---- MMA, commit, fences ------------------------------------------------------------
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread on behalf of the CTA.
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
@@ -66,6 +85,19 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint6
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+
+// Same for 16-bit operands (K = 16 elements = two 16-byte chunks per instruction).
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                        bool accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate)
         : "memory");
 }

@@ -179,6 +179,12 @@ int ebfi_events_to_stack(void *stream, void *xs, void *ys, const void *ts, const
 int ebfi_selftest_gemm_tf32x3(void *stream, const float *A, const float *B, float *C,
                               int M, int N, int K, int a_mn_major);
 
+/* Same GEMM with bf16 hi/lo pairs on kind::f16 (the DCN backward's operand format, ~2^-16
+ * relative accuracy). K multiple of 16, <= 128. b_lbo_bytes: byte distance between consecutive
+ * 16-byte K chunks of B (128 = dense, 144 = the padded layout the backward kernel uses). */
+int ebfi_selftest_gemm_bf16x3(void *stream, const float *A, const float *B, float *C,
+                              int M, int N, int K, int b_lbo_bytes);
+
 /* Layout probe: C[128][8] receives, for every element A(m, k) of a 128 x 8 TF32 operand described
  * by (lbo, sbo, major-ness), the float index inside shared memory that the tensor core fetched.
  * Documents how the hardware interprets the descriptor fields. */

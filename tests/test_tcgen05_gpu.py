@@ -28,6 +28,24 @@ def test_gemm_tf32x3_matches_fp64(M, N, K, a_mn):
     assert err < 2e-6, float(err)          # plain TF32 would sit near 1e-3
 
 
+@pytest.mark.parametrize("M,N,K,lbo", [(128, 80, 64, 128), (64, 80, 128, 144), (128, 16, 16, 128), (64, 72, 128, 144)])
+def test_gemm_bf16x3_matches_fp64(M, N, K, lbo):
+    """bf16 hi/lo pairs on kind::f16, dense and padded (LBO = 144 B) B operand."""
+    from ebfi_be_b200 import _lib as L
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A, B = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g)
+    want = A.double() @ B.double().t()
+    Ad, Bd = A.to(dev), B.to(dev)            # keep the device copies alive across the call
+    C = torch.full((M, N), float("nan"), device=dev)
+    L.check(L.load().ebfi_selftest_gemm_bf16x3(L.stream_ptr(dev), L.ptr(Ad), L.ptr(Bd), L.ptr(C), M, N, K, lbo),
+            "selftest_gemm_bf16")
+    torch.cuda.synchronize()
+    err = (C.double().cpu() - want).abs().max() / want.abs().max()
+    print(f"bf16x3 M={M} N={N} K={K} lbo={lbo}: rel err {float(err):.3e}")
+    assert err < 3e-5, float(err)
+
+
 def test_probe_documents_the_k_major_core_matrix_layout():
     """addr(row, k) = (row/8)*SBO + (k/4)*LBO + (row%8)*16 + (k%4)*4 bytes — read back from the hardware."""
     from ebfi_be_b200 import _lib as L
