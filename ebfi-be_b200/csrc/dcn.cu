@@ -32,9 +32,10 @@ int forward_tc(cudaStream_t st, const DcnDims &d, const float *input, const floa
 size_t forward_tc_workspace(const DcnDims &d);
 // tensor-core backward (dcn_bwd_tc.cu); splits == 0 when the shape is not eligible
 int backward_tc_splits(const DcnDims &d);
+size_t backward_tc_scratch_bytes(const DcnDims &d);
 int backward_tc(cudaStream_t st, const DcnDims &d, const float *input, const float *weight, const float *offset,
                 const float *mask, const float *gout, float *gin, float *goff, float *gmask, float *gw_part,
-                float *gb_part, int S);
+                float *gb_part, int S, void *scratch);
 }
 
 namespace {
@@ -388,7 +389,8 @@ size_t ebfi_dcnv2_backward_workspace_bytes(const ebfi_dcn_geom *q)
     DcnDims d{};
     if (fill_dims(q, d) != EBFI_OK) return 0;
     const size_t S = (size_t)std::max(bwd_splits(d), backward_tc_splits(d));
-    return S * ((size_t)d.Co * d.C * d.KK + d.Co) * sizeof(float) + 256;
+    return ebfi::round_up(S * ((size_t)d.Co * d.C * d.KK + d.Co) * sizeof(float), (size_t)256) +
+           backward_tc_scratch_bytes(d) + 256;
 }
 
 size_t ebfi_dcnv2_forward_workspace_bytes(const ebfi_dcn_geom *q)
@@ -436,18 +438,20 @@ int ebfi_dcnv2_backward(void *stream, const ebfi_dcn_geom *q, const float *input
     const int S_tc = (impl && impl[0] == 's') ? 0 : backward_tc_splits(d);
     const int S = S_tc > 0 ? S_tc : bwd_splits(d);
     const size_t n_w = (size_t)d.Co * d.C * d.KK, n_b = (size_t)d.Co;
-    const size_t need = (size_t)S * (n_w + n_b) * sizeof(float);
+    const size_t part_bytes = ebfi::round_up((size_t)S * (n_w + n_b) * sizeof(float), (size_t)256);
+    const size_t need = part_bytes + (S_tc > 0 ? backward_tc_scratch_bytes(d) : 0);
     if (!workspace || workspace_bytes < need)
         return ebfi::fail(EBFI_ERR_WORKSPACE, "dcn_backward: workspace %zu < %zu bytes", workspace_bytes, need);
+    EBFI_REQUIRE(ebfi::aligned16(workspace), "dcn_backward: workspace must be 16-byte aligned");
     float *gw_part = static_cast<float *>(workspace);
     float *gb_part = gw_part + (size_t)S * n_w;
-    EBFI_CUDA_OK(cudaMemsetAsync(grad_input, 0, (size_t)d.B * d.C * d.H * d.W * sizeof(float), st));
     if (S_tc > 0) {
         // tensor-core path (dcn_bwd_tc.cu): cpg == 8, Cout == 64
         if (int rc = backward_tc(st, d, input, weight, offset, mask, grad_output, grad_input, grad_offset, grad_mask,
-                                 gw_part, gb_part, S))
+                                 gw_part, gb_part, S, static_cast<char *>(workspace) + part_bytes))
             return rc;
     } else {
+        EBFI_CUDA_OK(cudaMemsetAsync(grad_input, 0, (size_t)d.B * d.C * d.H * d.W * sizeof(float), st));
         EBFI_CUDA_OK(cudaFuncSetAttribute(dcn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
         const int n_cot = ceil_div(d.Co, COT);
         // Chunks of one group accumulate into the same grad_offset / grad_mask elements; separate,

@@ -52,6 +52,12 @@ __device__ __forceinline__ void st_bf16(unsigned char *base, int off, unsigned s
     *reinterpret_cast<unsigned short *>(base + off) = v;
 }
 
+// 16-byte vector reduction into global memory (sm_90+): 4 fp32 adds, one L2 transaction
+__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float e)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(e) : "memory");
+}
+
 // eight bf16 values -> one 16-byte K chunk
 __device__ __forceinline__ void st_bf16x8(unsigned char *base, int off, const unsigned short (&v)[8])
 {
@@ -61,9 +67,9 @@ __device__ __forceinline__ void st_bf16x8(unsigned char *base, int off, const un
 }
 
 __global__ void __launch_bounds__(NTHR, 2)
-dcn_bwd_tc_kernel(const float *__restrict__ input, const float *__restrict__ weight,
+dcn_bwd_tc_kernel(const float *__restrict__ in_blk, const float *__restrict__ weight,
                   const float *__restrict__ offset, const float *__restrict__ mask,
-                  const float *__restrict__ gout, float *__restrict__ gin,
+                  const float *__restrict__ gout, float *__restrict__ gin_blk,
                   float *__restrict__ goff, float *__restrict__ gmask,
                   float *__restrict__ gw_part, float *__restrict__ gb_part, DcnDims d, BwdPlan pl)
 {
@@ -192,26 +198,36 @@ dcn_bwd_tc_kernel(const float *__restrict__ input, const float *__restrict__ wei
                 const float w1 = tp.hy * tp.hx, w2 = tp.hy * tp.lx, w3 = tp.ly * tp.hx, w4 = tp.ly * tp.lx;
                 const float q1 = tq.hy * tq.hx, q2 = tq.hy * tq.lx, q3 = tq.ly * tq.hx, q4 = tq.ly * tq.lx;
                 float s_m = 0.f, s_y = 0.f, s_x = 0.f;
-                const float *ip = input + ((size_t)b * d.C + c0) * in_plane;
-                float *gp = gin + ((size_t)b * d.C + c0) * in_plane;
+                // group-blocked layout [b][g][y][x][8 ch]: the 8 channels of a corner are 32 contiguous bytes
+                const float4 *ib = reinterpret_cast<const float4 *>(in_blk + ((size_t)b * d.dg + g) * in_plane * CS);
+                float *gb = gin_blk + ((size_t)b * d.dg + g) * in_plane * CS;
+                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int cc = 0; cc < CS; ++cc, ip += in_plane, gp += in_plane) {
-                    const float v1 = tp.c00 ? __ldg(ip + tp.i00) : 0.f;
-                    const float v2 = tp.c01 ? __ldg(ip + tp.i01) : 0.f;
-                    const float v3 = tp.c10 ? __ldg(ip + tp.i10) : 0.f;
-                    const float v4 = tp.c11 ? __ldg(ip + tp.i11) : 0.f;
-                    const float val = w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4;
-                    s_m += gc[cc] * val;                                            // grad_mask (im2col_cuda.cu:311)
-                    const float wy = -tp.hx * v1 - tp.lx * v2 + tp.hx * v3 + tp.lx * v4;   // coordinate weights (:99-120)
-                    const float wx = -tp.hy * v1 + tp.hy * v2 - tp.ly * v3 + tp.ly * v4;
-                    const float top = gc[cc] * m;
-                    s_y += wy * top;
-                    s_x += wx * top;
-                    if (tq.c00) atomicAdd(gp + tq.i00, q1 * top);                   // grad_input scatter (:236-251)
-                    if (tq.c01) atomicAdd(gp + tq.i01, q2 * top);
-                    if (tq.c10) atomicAdd(gp + tq.i10, q3 * top);
-                    if (tq.c11) atomicAdd(gp + tq.i11, q4 * top);
-                    colv[cc] = val * m;
+                for (int h = 0; h < 2; ++h) {                       // two halves of 4 channels
+                    const float4 a1 = tp.c00 ? __ldg(ib + (size_t)tp.i00 * 2 + h) : z4;
+                    const float4 a2 = tp.c01 ? __ldg(ib + (size_t)tp.i01 * 2 + h) : z4;
+                    const float4 a3 = tp.c10 ? __ldg(ib + (size_t)tp.i10 * 2 + h) : z4;
+                    const float4 a4 = tp.c11 ? __ldg(ib + (size_t)tp.i11 * 2 + h) : z4;
+                    const float v1[4] = {a1.x, a1.y, a1.z, a1.w}, v2[4] = {a2.x, a2.y, a2.z, a2.w};
+                    const float v3[4] = {a3.x, a3.y, a3.z, a3.w}, v4[4] = {a4.x, a4.y, a4.z, a4.w};
+                    float top[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int cc = 4 * h + j;
+                        const float val = w1 * v1[j] + w2 * v2[j] + w3 * v3[j] + w4 * v4[j];
+                        s_m += gc[cc] * val;                                            // grad_mask (im2col_cuda.cu:311)
+                        const float wy = -tp.hx * v1[j] - tp.lx * v2[j] + tp.hx * v3[j] + tp.lx * v4[j];   // (:99-120)
+                        const float wx = -tp.hy * v1[j] + tp.hy * v2[j] - tp.ly * v3[j] + tp.ly * v4[j];
+                        top[j] = gc[cc] * m;
+                        s_y += wy * top[j];
+                        s_x += wx * top[j];
+                        colv[cc] = val * m;
+                    }
+                    // grad_input scatter (:236-251): one 16-byte vector reduction per corner and half
+                    if (tq.c00) red_add_v4(gb + (size_t)tq.i00 * CS + 4 * h, q1 * top[0], q1 * top[1], q1 * top[2], q1 * top[3]);
+                    if (tq.c01) red_add_v4(gb + (size_t)tq.i01 * CS + 4 * h, q2 * top[0], q2 * top[1], q2 * top[2], q2 * top[3]);
+                    if (tq.c10) red_add_v4(gb + (size_t)tq.i10 * CS + 4 * h, q3 * top[0], q3 * top[1], q3 * top[2], q3 * top[3]);
+                    if (tq.c11) red_add_v4(gb + (size_t)tq.i11 * CS + 4 * h, q4 * top[0], q4 * top[1], q4 * top[2], q4 * top[3]);
                 }
                 float *gy = goff + (((size_t)b * d.dg + g) * 2 * d.KK + 2 * t) * plane + pix;
                 gy[0] = s_y; gy[plane] = s_x;
@@ -293,6 +309,36 @@ dcn_bwd_tc_kernel(const float *__restrict__ input, const float *__restrict__ wei
     if (warp == 0) umma::tmem_dealloc<TMEM_COLS>(tmem);
 }
 
+// NCHW (B, dg*8, H, W)  <->  group-blocked (B, dg, H, W, 8): one thread per (b, g, y, x); reads and
+// writes are both coalesced (8 plane reads of consecutive x, 32 contiguous bytes per thread).
+__global__ void nchw_to_blocked(const float *__restrict__ src, float *__restrict__ dst, int BG, int HW)
+{
+    const size_t n = (size_t)BG * HW;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t bg = i / HW, px = i - bg * HW;
+        const float *sp = src + bg * CS * HW + px;
+        float v[CS];
+#pragma unroll
+        for (int c = 0; c < CS; ++c) v[c] = __ldg(sp + (size_t)c * HW);
+        float4 *dp = reinterpret_cast<float4 *>(dst + i * CS);
+        dp[0] = make_float4(v[0], v[1], v[2], v[3]);
+        dp[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+}
+
+__global__ void blocked_to_nchw(const float *__restrict__ src, float *__restrict__ dst, int BG, int HW)
+{
+    const size_t n = (size_t)BG * HW;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t bg = i / HW, px = i - bg * HW;
+        const float4 *sp = reinterpret_cast<const float4 *>(src + i * CS);
+        const float4 a = sp[0], c = sp[1];
+        float *dp = dst + bg * CS * HW + px;
+        dp[0] = a.x; dp[(size_t)HW] = a.y; dp[(size_t)2 * HW] = a.z; dp[(size_t)3 * HW] = a.w;
+        dp[(size_t)4 * HW] = c.x; dp[(size_t)5 * HW] = c.y; dp[(size_t)6 * HW] = c.z; dp[(size_t)7 * HW] = c.w;
+    }
+}
+
 bool make_plan(const DcnDims &d, BwdPlan &pl)
 {
     if (d.cpg != CS || d.Co != 64) return false;          // other shapes: CUDA-core kernel in dcn.cu
@@ -323,18 +369,43 @@ int backward_tc_splits(const DcnDims &d)
     return std::max(1, std::min(tiles, ceil_div(2 * ebfi::sm_count(), d.dg)));
 }
 
-// Launches the tensor-core backward main kernel (grad_input must already be zero). Partials:
-// gw_part[S][Co][C*KK], gb_part[S][Co] with S = backward_tc_splits(d).
+int launch_nchw_to_blocked(cudaStream_t st, const float *src, float *dst, int BG, int HW)
+{
+    const unsigned tgrid = (unsigned)std::min<size_t>(ceil_div((size_t)BG * HW, (size_t)256), (size_t)ebfi::sm_count() * 16);
+    nchw_to_blocked<<<tgrid, 256, 0, st>>>(src, dst, BG, HW);
+    EBFI_LAUNCH_OK("nchw_to_blocked");
+    return EBFI_OK;
+}
+
+// Extra scratch of the tensor-core backward: group-blocked copies of input and grad_input.
+size_t backward_tc_scratch_bytes(const DcnDims &d)
+{
+    BwdPlan pl{};
+    if (!make_plan(d, pl)) return 0;
+    return 2 * (size_t)d.B * d.C * d.H * d.W * sizeof(float);
+}
+
+// Tensor-core backward: writes grad_input / grad_offset / grad_mask in full and the partials
+// gw_part[S][Co][C*KK], gb_part[S][Co] with S = backward_tc_splits(d). `scratch` holds
+// backward_tc_scratch_bytes(d) bytes, 16-byte aligned.
 int backward_tc(cudaStream_t st, const DcnDims &d, const float *input, const float *weight, const float *offset,
                 const float *mask, const float *gout, float *gin, float *goff, float *gmask, float *gw_part,
-                float *gb_part, int S)
+                float *gb_part, int S, void *scratch)
 {
     BwdPlan pl{};
     if (!make_plan(d, pl)) return EBFI_ERR_UNSUPPORTED;
+    const size_t n = (size_t)d.B * d.C * d.H * d.W;
+    float *in_blk = static_cast<float *>(scratch), *gin_blk = in_blk + n;
+    const int BG = d.B * d.dg, HW = d.H * d.W;
+    const unsigned tgrid = (unsigned)std::min<size_t>(ceil_div((size_t)BG * HW, (size_t)256), (size_t)ebfi::sm_count() * 16);
+    if (int rc = launch_nchw_to_blocked(st, input, in_blk, BG, HW)) return rc;
+    EBFI_CUDA_OK(cudaMemsetAsync(gin_blk, 0, n * sizeof(float), st));
     EBFI_CUDA_OK(cudaFuncSetAttribute(dcn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
     dim3 grid(S, d.dg);
-    dcn_bwd_tc_kernel<<<grid, NTHR, pl.smem, st>>>(input, weight, offset, mask, gout, gin, goff, gmask, gw_part, gb_part, d, pl);
+    dcn_bwd_tc_kernel<<<grid, NTHR, pl.smem, st>>>(in_blk, weight, offset, mask, gout, gin_blk, goff, gmask, gw_part, gb_part, d, pl);
     EBFI_LAUNCH_OK("dcn_bwd_tc_kernel");
+    blocked_to_nchw<<<tgrid, 256, 0, st>>>(gin_blk, gin, BG, HW);
+    EBFI_LAUNCH_OK("blocked_to_nchw");
     return EBFI_OK;
 }
 

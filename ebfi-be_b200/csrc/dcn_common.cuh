@@ -55,4 +55,7 @@ __device__ __forceinline__ void tap_coords(const DcnDims &d, const float *__rest
 }
 
 
+// NCHW (BG*8 planes of HW pixels) -> group-blocked (BG, HW, 8) copy (dcn_bwd_tc.cu)
+int launch_nchw_to_blocked(cudaStream_t st, const float *src, float *dst, int BG, int HW);
+
 }  // namespace ebfi_dcn
