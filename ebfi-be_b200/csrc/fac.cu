@@ -23,6 +23,7 @@
 // terms in the same order on every run (two-operand merge adds commute), so the result is
 // bit-reproducible without atomics on data.
 #include "common.cuh"
+#include "umma.cuh"      // mbarrier + 1-D bulk (TMA) copy helpers
 
 namespace {
 
@@ -53,6 +54,7 @@ struct FacDims {
     int seg_rows;      // rows per segment
     int nseg;          // segments per plane
     int nxb;           // thread blocks along x (forward only)
+    int nstage;        // ring stages of the backward (0 = register variant)
 };
 
 // ------------------------------------------------------------------ forward ---
@@ -109,7 +111,11 @@ fac_fwd_march(const float *__restrict__ in, const float *__restrict__ ker, float
 // ----------------------------------------------------------------- backward ---
 // Workspace layout: [planes * (nseg-1)] int arrival counters (zeroed by the launcher),
 // then [planes * (nseg-1)][K-1][Wi] fp32 overhang rows.
-template <int K, int PX>
+// RING = true (4 px/thread only): the K*K kernel rows and the grad_output row of each step arrive
+// through a ring of `d.nstage` shared-memory stages filled by 1-D bulk (TMA) copies that one thread
+// issues two rows ahead; bytes in flight then live in shared memory instead of registers (the
+// register variant keeps 25 float4 loads = 100 registers per thread in flight, 8 warps per SM).
+template <int K, int PX, bool RING>
 __global__ void __launch_bounds__(256)
 fac_bwd_march(const float *__restrict__ in, const float *__restrict__ ker,
               const float *__restrict__ gout, float *__restrict__ gin, float *__restrict__ gker,
@@ -119,8 +125,10 @@ fac_bwd_march(const float *__restrict__ in, const float *__restrict__ ker,
     constexpr int R = K - 1;                       // halo width
     constexpr int RS = R > 0 ? R : 1;
     constexpr int D = R > 0 ? (R + PX - 1) / PX : 0;   // how many left neighbours reach into my columns
-    extern __shared__ float xchg[];                // [2][blockDim.x][RS]
+    extern __shared__ __align__(128) float dyn_smem[];
+    float *xchg = dyn_smem;                        // [2][blockDim.x][RS]
     __shared__ int s_flag[2];
+    __shared__ __align__(8) uint64_t ring_bar[4];
 
     const int seg = blockIdx.x % d.nseg;
     const int plane = blockIdx.x / d.nseg;
@@ -148,6 +156,28 @@ fac_bwd_march(const float *__restrict__ in, const float *__restrict__ ker,
         for (int r = 1; r < K; ++r)
 #pragma unroll
             for (int j = 0; j < WIN; ++j) win[r][j] = __ldg(inp + (size_t)(y0 + r - 1) * Wi + j);
+    }
+
+    // ---- ring of (K*K + 1) x W floats per stage: rows k of `kernel`, then the grad_output row
+    float *ring = dyn_smem + ((2 * blockDim.x * RS + 31) & ~31);
+    const int stage_floats = (K * K + 1) * W;
+    auto issue_row = [&](int y) {                  // thread 0: bulk copies of row y into its stage
+        const int st = (y - y0) % d.nstage;
+        float *dst = ring + (size_t)st * stage_floats;
+        umma::mbar_expect_tx(&ring_bar[st], (uint32_t)(stage_floats * sizeof(float)));
+        const float *src = ker + (size_t)plane * K * K * H * W + (size_t)y * W;
+        for (int k = 0; k < K * K; ++k)
+            umma::bulk_g2s(dst + (size_t)k * W, src + (size_t)k * H * W, (uint32_t)(W * sizeof(float)), &ring_bar[st]);
+        umma::bulk_g2s(dst + (size_t)K * K * W, gout + (size_t)plane * H * W + (size_t)y * W,
+                       (uint32_t)(W * sizeof(float)), &ring_bar[st]);
+    };
+    if constexpr (RING) {
+        if (t == 0) {
+            for (int i = 0; i < d.nstage; ++i) umma::mbar_init(&ring_bar[i], 1);
+            umma::mbar_fence_init();
+            for (int y = y0; y < min(y1, y0 + d.nstage - 1); ++y) issue_row(y);
+        }
+        __syncthreads();
     }
 
     // Emits one finished (or segment-partial) grad_input row held in acc[0] after the
@@ -196,7 +226,37 @@ fac_bwd_march(const float *__restrict__ in, const float *__restrict__ ker,
 
     int parity = 0;
     for (int y = y0; y < y1; ++y) {
-        if (active) {
+        if constexpr (RING) {
+            // the stage that row y + nstage - 1 reuses was consumed in iteration y - 1 (emit_row's barrier)
+            if (t == 0 && y + d.nstage - 1 < y1) issue_row(y + d.nstage - 1);
+            const int st = (y - y0) % d.nstage;
+            umma::mbar_wait(&ring_bar[st], ((y - y0) / d.nstage) & 1);
+            if (active) {
+                const float *stg = ring + (size_t)st * stage_floats + x;
+                const float4 g4 = *reinterpret_cast<const float4 *>(stg + (size_t)K * K * W);
+                const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+                for (int r = 0; r < K - 1; ++r)
+#pragma unroll
+                    for (int j = 0; j < WIN; ++j) win[r][j] = win[r + 1][j];
+#pragma unroll
+                for (int j = 0; j < WIN; ++j) win[K - 1][j] = __ldg(inp + (size_t)(y + K - 1) * Wi + j);
+#pragma unroll
+                for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < K; ++kx) {
+                        const float4 k4 = *reinterpret_cast<const float4 *>(stg + (size_t)(ky * K + kx) * W);
+                        const float kvv[4] = {k4.x, k4.y, k4.z, k4.w};
+                        Vec<4> gk;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            gk.v[i] = win[ky][kx + i] * g[i];
+                            acc[ky][kx + i] += kvv[i] * g[i];
+                        }
+                        gk.store_stream(gkp + ((size_t)(ky * K + kx) * H + y) * W);
+                    }
+            }
+        } else if (active) {
             Vec<PX> kv[K * K];
 #pragma unroll
             for (int k = 0; k < K * K; ++k) kv[k] = Vec<PX>::load_stream(kp + ((size_t)k * H + y) * W);
@@ -359,9 +419,19 @@ FacPlan make_plan(const void *const *ptrs, int nptr, int planes, int H, int W, i
     p.d.seg_rows = seg;
     p.d.nseg = ceil_div(H, seg);
     const int cols = ceil_div(W, p.px);
+    p.d.nstage = 0;
     if (backward) {
         p.threads = ebfi::round_up(cols, 32);
         p.d.nxb = 1;
+        // ring variant: 2 stages (one row being consumed, one in flight). Measured on B200 at the
+        // benchmark shape: 2 stages = 4 CTAs/SM -> 0.600 ms (91 % of HBM peak); 3 or 4 stages = 2 CTAs/SM
+        // -> 0.763 ms; register variant 0.687 ms. Resident CTAs matter more than ring depth.
+        if (p.px == 4 && (K == 3 || K == 5) && env_int("EBFI_FAC_RING", 1)) {
+            const size_t stage = (size_t)(K * K + 1) * W * sizeof(float);
+            const int want = env_int("EBFI_FAC_STAGES", 0);
+            if (want >= 2 && want <= 4 && want * stage <= 200 * 1024) p.d.nstage = want;
+            else if (2 * stage <= 200 * 1024) p.d.nstage = 2;
+        }
     } else {
         p.threads = cols >= 128 ? 128 : ebfi::round_up(cols, 32);
         p.d.nxb = ceil_div(cols, p.threads);
@@ -392,15 +462,34 @@ int launch_bwd(cudaStream_t st, const FacPlan &p, const float *in, const float *
                int planes, int K)
 {
     const unsigned grid = (unsigned)((size_t)planes * p.d.nseg);
-    const size_t smem = (size_t)2 * p.threads * (K > 1 ? K - 1 : 1) * sizeof(float);
-    switch (K) {
-    case 1: fac_bwd_march<1, PX><<<grid, p.threads, smem, st>>>(in, ker, gout, gin, gker, counters, overhang, p.d); break;
-    case 3: fac_bwd_march<3, PX><<<grid, p.threads, smem, st>>>(in, ker, gout, gin, gker, counters, overhang, p.d); break;
-    case 5: fac_bwd_march<5, PX><<<grid, p.threads, smem, st>>>(in, ker, gout, gin, gker, counters, overhang, p.d); break;
-    case 7: if constexpr (PX == 1) { fac_bwd_march<7, 1><<<grid, p.threads, smem, st>>>(in, ker, gout, gin, gker, counters, overhang, p.d); break; }
-            return ebfi::fail(EBFI_ERR_INVALID, "fac: K=7 runs 1 px/thread only");
-    default: return ebfi::fail(EBFI_ERR_INVALID, "fac: unsupported K=%d in march path", K);
+    const int RS = K > 1 ? K - 1 : 1;
+    const size_t xch = (size_t)((2 * p.threads * RS + 31) & ~31) * sizeof(float);
+    const size_t smem = xch + (size_t)p.d.nstage * (K * K + 1) * p.d.W * sizeof(float);
+#define EBFI_FAC_BWD(KK, RING)                                                                              \
+    do {                                                                                                    \
+        auto kern = fac_bwd_march<KK, PX, RING>;                                                            \
+        EBFI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+        kern<<<grid, p.threads, smem, st>>>(in, ker, gout, gin, gker, counters, overhang, p.d);            \
+    } while (0)
+    if (p.d.nstage > 0) {
+        if constexpr (PX == 4) {
+            if (K == 5) EBFI_FAC_BWD(5, true);
+            else if (K == 3) EBFI_FAC_BWD(3, true);
+            else return ebfi::fail(EBFI_ERR_INVALID, "fac: ring variant handles K = 3, 5");
+        } else {
+            return ebfi::fail(EBFI_ERR_INVALID, "fac: ring variant needs 4 px/thread");
+        }
+    } else {
+        switch (K) {
+        case 1: EBFI_FAC_BWD(1, false); break;
+        case 3: EBFI_FAC_BWD(3, false); break;
+        case 5: EBFI_FAC_BWD(5, false); break;
+        case 7: if constexpr (PX == 1) { EBFI_FAC_BWD(7, false); break; }
+                return ebfi::fail(EBFI_ERR_INVALID, "fac: K=7 runs 1 px/thread only");
+        default: return ebfi::fail(EBFI_ERR_INVALID, "fac: unsupported K=%d in march path", K);
+        }
     }
+#undef EBFI_FAC_BWD
     EBFI_LAUNCH_OK("fac_bwd_march");
     return EBFI_OK;
 }
