@@ -49,8 +49,10 @@ FAC_OUT = B_FAC * C * H * W
 FAC_FWD_BYTES = _F * (FAC_IN + FAC_KER + FAC_OUT)
 FAC_BWD_BYTES = _F * (FAC_KER + FAC_OUT + FAC_IN + FAC_IN + FAC_KER)
 STEP_BYTES = DCN_FWD_BYTES + DCN_BWD_BYTES + FAC_FWD_BYTES + FAC_BWD_BYTES
-# kernels of ours per step: dcn_fwd, dcn_bwd, dcn_reduce_partials, fac_fwd_march, fac_bwd_march
-LAUNCHES_PER_STEP = 5
+# kernels of ours per step (profiles/r1b_launches.txt): DCN forward = dcn_prep_weights + nchw_to_blocked +
+# dcn_fwd_tc_kernel; DCN backward = nchw_to_blocked + dcn_bwd_tc_kernel + blocked_to_nchw +
+# dcn_reduce_partials; FAC = fac_fwd_march + fac_bwd_march
+LAUNCHES_PER_STEP = 9
 
 
 def peaks():
@@ -260,7 +262,7 @@ def run_ours(args):
                    "l2": "inputs larger than L2: each step streams 5.4 GB of FAC tensors (>> 126 MB L2) "
                          "between consecutive DCN calls; breakdown.cold_ms flushes L2 explicitly",
                    "collective": "NCCL all-reduce of DCN grad_weight+grad_bias" if world > 1 else "none"},
-        "roofline": {"bound": "hbm", "kernel": "fac_bwd_march<5,4> (FAC fused backward)",
+        "roofline": {"bound": "hbm", "kernel": "fac_bwd_march<5,4,ring> (FAC fused backward)",
                      "achieved": round(gbs(op_bytes[dom], op_ms[dom]), 1), "peak": peak, "unit": "GB/s",
                      "frac": round(gbs(op_bytes[dom], op_ms[dom]) / peak, 4), "traffic": traffic,
                      "algorithmic_bytes_per_launch": op_bytes[dom], "peak_source": peak_src,
