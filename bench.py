@@ -189,18 +189,22 @@ def run_ours(args):
     pin_out = {n: torch.empty_like(t).pin_memory() for n, t in zip(res_names, res_like)}
     h2d = sum(v.numel() * 4 for v in pin.values()); d2h = sum(v.numel() * 4 for v in pin_out.values())
 
+    from ebfi_be_b200.host_pipeline import HostPipeline
+    pipe = HostPipeline(dev)
+    dcn_res = {"out": pin_out["out_d"], "grad_input": pin_out["g_x"], "grad_offset": pin_out["g_off"],
+               "grad_mask": pin_out["g_msk"], "grad_weight": pin_out["g_w"], "grad_bias": pin_out["g_b"]}
+
     def e2e_step():
-        g = {k: v.to(dev, non_blocking=True) for k, v in pin.items()}
-        leaves = [g[k].requires_grad_() for k in ("x", "off", "msk", "w", "b")]
-        out = dcn_v2.dcn_v2_conv(*leaves, 1, 1, 1, DG)
-        out.backward(g["go_d"])
-        if world > 1:
-            dist.all_reduce(leaves[3].grad); dist.all_reduce(leaves[4].grad)
-        xi, ker = g["xi"].requires_grad_(), g["ker"].requires_grad_()
-        of = kernelconv2d.KernelConv2DFunction.apply(xi, ker, K_FAC)
-        of.backward(g["go_f"])
-        for n, t in zip(res_names, [out.detach()] + [l.grad for l in leaves] + [of.detach(), xi.grad, ker.grad]):
-            pin_out[n].copy_(t, non_blocking=True)
+        """Host buffers in, host buffers out, through the package's host-pipeline API: per-sample
+        H2D | autograd forward+backward | D2H on three streams."""
+        s_out, keep = pipe.dcn_forward_backward(pin["x"], pin["off"], pin["msk"], pin["w"], pin["b"], pin["go_d"],
+                                                1, 1, 1, DG, dcn_res)
+        if world > 1:   # weight-gradient all-reduce; the reduced values are what a trainer would read
+            gw, gb = keep[1][3].grad, keep[1][4].grad
+            dist.all_reduce(gw); dist.all_reduce(gb)
+        pipe.fac_forward_backward(pin["xi"], pin["ker"], pin["go_f"], K_FAC,
+                                  pin_out["out_f"], pin_out["g_xi"], pin_out["g_ker"])
+        s_out.synchronize()
         torch.cuda.current_stream().synchronize()      # the step's results are on the host
 
     e2e_steps = 1 if args.kernels_only else max(3, min(args.steps, 10))
@@ -275,7 +279,8 @@ def run_ours(args):
             "cfg2_fac_B4": round(B_FAC * H * W / 1e6 / ((op_ms["fac_fwd"] + op_ms["fac_bwd"]) * 1e-3), 2)},
         "e2e": {"value": round(world * MPIX_PER_STEP * e2e_steps / e2e_s, 3), "unit": "Mpix/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                "api": "dcn_v2_conv / KernelConv2DFunction.apply (autograd), pinned host in/out"},
+                "api": "ebfi_be_b200.host_pipeline (dcn_v2_conv / KernelConv2DFunction autograd, pinned host in/out, "
+                       "per-sample H2D | compute | D2H on three streams)"},
         "gpu_launches": LAUNCHES_PER_STEP * args.steps,
         "clocks": clk.summary(),
     }
@@ -399,6 +404,9 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
+        # torchrun exports OMP_NUM_THREADS=1; the reference arm uses all the host threads it can
+        for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+            os.environ[k] = str(os.cpu_count() or 1)
         run_reference(args)
     else:
         run_ours(args)
