@@ -242,6 +242,27 @@ def run_ours(args):
         "fac_bwd": timed(lambda: kc.backward(d["xi"], d["ker"], K_FAC, d["go_f"], gi_f, gk_f)),
     }
 
+    # ---- BASELINE configs[2]: event encoders, 10 M synthetic events at 1280x720 (reported beside the
+    # headline metric, not part of it). Events are device-resident; the grid memset is inside the call.
+    events = None
+    if rank == 0 and not args.kernels_only:
+        from ebfi_be_b200 import encodings
+        g = torch.Generator(device="cpu").manual_seed(7)
+        NEV, EH, EW = 10_000_000, 720, 1280
+        exs = torch.randint(0, EW, (NEV,), generator=g).float().to(dev)
+        eys = torch.randint(0, EH, (NEV,), generator=g).float().to(dev)
+        ets = torch.sort(torch.rand(NEV, generator=g, dtype=torch.float64))[0]
+        ets = ((ets - ets[0]) / (ets[-1] - ets[0] + 1e-6)).float().to(dev)
+        eps_ = (torch.randint(0, 2, (NEV,), generator=g) * 2 - 1).float().to(dev)
+        t_vox = timed(lambda: encodings.events_to_voxel(exs, eys, ets, eps_, 5, sensor_size=(EH, EW)), n=10)
+        t_stk = timed(lambda: encodings.events_to_stack(exs, eys, ets, eps_, 16, sensor_size=(EH, EW)), n=10)
+        events = {"workload": "10M events, 1280x720, fp32 coordinates, uniform pixels, sorted ts",
+                  "voxel_5bins": {"ms": round(t_vox, 4), "Mev_s": round(NEV / 1e6 / (t_vox * 1e-3), 1),
+                                  "algorithmic_GBps": round((16 * NEV + 4 * 5 * EH * EW) / (t_vox * 1e-3) / 1e9, 1)},
+                  "stack_16bins": {"ms": round(t_stk, 4), "Mev_s": round(NEV / 1e6 / (t_stk * 1e-3), 1),
+                                   "algorithmic_GBps": round((16 * NEV + 4 * 32 * EH * EW) / (t_stk * 1e-3) / 1e9, 1)}}
+        del exs, eys, ets, eps_
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -281,6 +302,7 @@ def run_ours(args):
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "api": "ebfi_be_b200.host_pipeline (dcn_v2_conv / KernelConv2DFunction autograd, pinned host in/out, "
                        "per-sample H2D | compute | D2H on three streams)"},
+        "events": events,
         "gpu_launches": LAUNCHES_PER_STEP * args.steps,
         "clocks": clk.summary(),
     }
@@ -344,7 +366,16 @@ def cpu_baseline(budget_s=20.0):
     rows = int(max(8, min(H, 8 * budget_s / max(td + tf, 1e-6))))
     td, tf = _cpu_step(torch, ref_dcn, oracle, rows, data)
     mpix = (B_DCN + B_FAC) * rows * W / 1e6
-    return {"value": round(mpix / (td + tf), 5), "unit": "Mpix/s", "cores": torch.get_num_threads(),
+    # encoders: the oracle's serial C port of dataloader/encodings.py on 2 M events (same distribution)
+    import numpy as np
+    rng = np.random.default_rng(7)
+    n_ev = 2_000_000
+    exs = rng.integers(0, 1280, n_ev).astype(np.float32); eys = rng.integers(0, 720, n_ev).astype(np.float32)
+    ets = np.sort(rng.random(n_ev)).astype(np.float32); eps_ = (rng.integers(0, 2, n_ev) * 2 - 1).astype(np.float32)
+    t0 = time.perf_counter(); oracle.events_to_voxel(exs, eys, ets, eps_, 5, (720, 1280)); t_v = time.perf_counter() - t0
+    t0 = time.perf_counter(); oracle.events_to_stack(exs, eys, ets, eps_, 16, (720, 1280)); t_s = time.perf_counter() - t0
+    return {"events_voxel_5bins_Mev_s": round(n_ev / 1e6 / t_v, 2), "events_stack_16bins_Mev_s": round(n_ev / 1e6 / t_s, 2),
+            "value": round(mpix / (td + tf), 5), "unit": "Mpix/s", "cores": torch.get_num_threads(),
             "kind": "reference" if ref_dcn is not None else "port",
             "sample": f"top {rows} of 256 rows of the same step (DCN B=1 + FAC B=4, fwd+bwd): "
                       f"DCN {td:.2f} s via " + ("the reference's CPU build oracle/_ref/dcn_cpu (serial loops + MKL GEMM)"
