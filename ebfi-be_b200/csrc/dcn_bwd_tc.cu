@@ -199,35 +199,31 @@ dcn_bwd_tc_kernel(const float *__restrict__ in_blk, const float *__restrict__ we
                 const float q1 = tq.hy * tq.hx, q2 = tq.hy * tq.lx, q3 = tq.ly * tq.hx, q4 = tq.ly * tq.lx;
                 float s_m = 0.f, s_y = 0.f, s_x = 0.f;
                 // group-blocked layout [b][g][y][x][8 ch]: the 8 channels of a corner are 32 contiguous bytes
-                const float4 *ib = reinterpret_cast<const float4 *>(in_blk + ((size_t)b * d.dg + g) * in_plane * CS);
+                const float *ib = in_blk + ((size_t)b * d.dg + g) * in_plane * CS;
                 float *gb = gin_blk + ((size_t)b * d.dg + g) * in_plane * CS;
-                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                const f8 a1 = ldg_f8(ib + (size_t)tp.i00 * CS, tp.c00), a2 = ldg_f8(ib + (size_t)tp.i01 * CS, tp.c01);
+                const f8 a3 = ldg_f8(ib + (size_t)tp.i10 * CS, tp.c10), a4 = ldg_f8(ib + (size_t)tp.i11 * CS, tp.c11);
+                float top[CS];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {                       // two halves of 4 channels
-                    const float4 a1 = tp.c00 ? __ldg(ib + (size_t)tp.i00 * 2 + h) : z4;
-                    const float4 a2 = tp.c01 ? __ldg(ib + (size_t)tp.i01 * 2 + h) : z4;
-                    const float4 a3 = tp.c10 ? __ldg(ib + (size_t)tp.i10 * 2 + h) : z4;
-                    const float4 a4 = tp.c11 ? __ldg(ib + (size_t)tp.i11 * 2 + h) : z4;
-                    const float v1[4] = {a1.x, a1.y, a1.z, a1.w}, v2[4] = {a2.x, a2.y, a2.z, a2.w};
-                    const float v3[4] = {a3.x, a3.y, a3.z, a3.w}, v4[4] = {a4.x, a4.y, a4.z, a4.w};
-                    float top[4];
+                for (int cc = 0; cc < CS; ++cc) {
+                    const float v1 = a1.v[cc], v2 = a2.v[cc], v3 = a3.v[cc], v4 = a4.v[cc];
+                    const float val = w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4;
+                    s_m += gc[cc] * val;                                            // grad_mask (im2col_cuda.cu:311)
+                    const float wy = -tp.hx * v1 - tp.lx * v2 + tp.hx * v3 + tp.lx * v4;   // coordinate weights (:99-120)
+                    const float wx = -tp.hy * v1 + tp.hy * v2 - tp.ly * v3 + tp.ly * v4;
+                    top[cc] = gc[cc] * m;
+                    s_y += wy * top[cc];
+                    s_x += wx * top[cc];
+                    colv[cc] = val * m;
+                }
+                // grad_input scatter (:236-251): 16-byte vector reductions, two per corner
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int cc = 4 * h + j;
-                        const float val = w1 * v1[j] + w2 * v2[j] + w3 * v3[j] + w4 * v4[j];
-                        s_m += gc[cc] * val;                                            // grad_mask (im2col_cuda.cu:311)
-                        const float wy = -tp.hx * v1[j] - tp.lx * v2[j] + tp.hx * v3[j] + tp.lx * v4[j];   // (:99-120)
-                        const float wx = -tp.hy * v1[j] + tp.hy * v2[j] - tp.ly * v3[j] + tp.ly * v4[j];
-                        top[j] = gc[cc] * m;
-                        s_y += wy * top[j];
-                        s_x += wx * top[j];
-                        colv[cc] = val * m;
-                    }
-                    // grad_input scatter (:236-251): one 16-byte vector reduction per corner and half
-                    if (tq.c00) red_add_v4(gb + (size_t)tq.i00 * CS + 4 * h, q1 * top[0], q1 * top[1], q1 * top[2], q1 * top[3]);
-                    if (tq.c01) red_add_v4(gb + (size_t)tq.i01 * CS + 4 * h, q2 * top[0], q2 * top[1], q2 * top[2], q2 * top[3]);
-                    if (tq.c10) red_add_v4(gb + (size_t)tq.i10 * CS + 4 * h, q3 * top[0], q3 * top[1], q3 * top[2], q3 * top[3]);
-                    if (tq.c11) red_add_v4(gb + (size_t)tq.i11 * CS + 4 * h, q4 * top[0], q4 * top[1], q4 * top[2], q4 * top[3]);
+                for (int h = 0; h < 2; ++h) {
+                    const float *tt = top + 4 * h;
+                    if (tq.c00) red_add_v4(gb + (size_t)tq.i00 * CS + 4 * h, q1 * tt[0], q1 * tt[1], q1 * tt[2], q1 * tt[3]);
+                    if (tq.c01) red_add_v4(gb + (size_t)tq.i01 * CS + 4 * h, q2 * tt[0], q2 * tt[1], q2 * tt[2], q2 * tt[3]);
+                    if (tq.c10) red_add_v4(gb + (size_t)tq.i10 * CS + 4 * h, q3 * tt[0], q3 * tt[1], q3 * tt[2], q3 * tt[3]);
+                    if (tq.c11) red_add_v4(gb + (size_t)tq.i11 * CS + 4 * h, q4 * tt[0], q4 * tt[1], q4 * tt[2], q4 * tt[3]);
                 }
                 float *gy = goff + (((size_t)b * d.dg + g) * 2 * d.KK + 2 * t) * plane + pix;
                 gy[0] = s_y; gy[plane] = s_x;

@@ -55,6 +55,23 @@ __device__ __forceinline__ void tap_coords(const DcnDims &d, const float *__rest
 }
 
 
+// 256-bit read-only global load (sm_100+: LDG.E.256): the 8 channels of one bilinear corner in the
+// group-blocked layout, one instruction and one L1 wavefront per lane instead of two.
+struct f8 { float v[8]; };
+__device__ __forceinline__ f8 ldg_f8(const float *p32B_aligned, bool ok)
+{
+    f8 r;
+    if (ok) {
+        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+                     : "l"(p32B_aligned));
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.v[i] = 0.f;
+    }
+    return r;
+}
+
 // NCHW (BG*8 planes of HW pixels) -> group-blocked (BG, HW, 8) copy (dcn_bwd_tc.cu)
 int launch_nchw_to_blocked(cudaStream_t st, const float *src, float *dst, int BG, int HW);
 

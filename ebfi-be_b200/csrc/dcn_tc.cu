@@ -49,10 +49,6 @@ struct FwdPlan {
     int a_bytes, b_bytes, smem;
 };
 
-__device__ __forceinline__ float4 ld_corner(const float4 *base, bool ok, int unit)
-{
-    return ok ? __ldg(base + unit) : make_float4(0.f, 0.f, 0.f, 0.f);
-}
 
 __global__ void __launch_bounds__(NTHR, 2)
 dcn_fwd_tc_kernel(const float *__restrict__ in_blk,
@@ -137,20 +133,19 @@ dcn_fwd_tc_kernel(const float *__restrict__ in_blk,
                     const float m = s == 0 ? sm[0] : s == 1 ? sm[1] : s == 2 ? sm[2] : sm[3];
                     const Tap tp = make_tap(y, x, d.H, d.W);
                     const float w1 = tp.hy * tp.hx, w2 = tp.hy * tp.lx, w3 = tp.ly * tp.hx, w4 = tp.ly * tp.lx;
-                    for (int q = 0; q < 2; ++q) {
-                        float v[4];
-                        const float4 a = ld_corner(ib, tp.c00, tp.i00 * 2 + q), bq = ld_corner(ib, tp.c01, tp.i01 * 2 + q);
-                        const float4 c = ld_corner(ib, tp.c10, tp.i10 * 2 + q), e4 = ld_corner(ib, tp.c11, tp.i11 * 2 + q);
-                        v[0] = (w1 * a.x + w2 * bq.x + w3 * c.x + w4 * e4.x) * m;
-                        v[1] = (w1 * a.y + w2 * bq.y + w3 * c.y + w4 * e4.y) * m;
-                        v[2] = (w1 * a.z + w2 * bq.z + w3 * c.z + w4 * e4.z) * m;
-                        v[3] = (w1 * a.w + w2 * bq.w + w3 * c.w + w4 * e4.w) * m;
-                        float hi[4], lo[4];
+                    {
+                        const float *ibf = reinterpret_cast<const float *>(ib);
+                        const f8 a = ldg_f8(ibf + (size_t)tp.i00 * 8, tp.c00), bq = ldg_f8(ibf + (size_t)tp.i01 * 8, tp.c01);
+                        const f8 c = ldg_f8(ibf + (size_t)tp.i10 * 8, tp.c10), e8 = ldg_f8(ibf + (size_t)tp.i11 * 8, tp.c11);
+                        float hi[8], lo[8];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) umma::split_tf32(v[j], hi[j], lo[j]);
-                        const int off = a_row + ((r * pl.cs + 4 * q) >> 2) * 32;
+                        for (int j = 0; j < 8; ++j)
+                            umma::split_tf32((w1 * a.v[j] + w2 * bq.v[j] + w3 * c.v[j] + w4 * e8.v[j]) * m, hi[j], lo[j]);
+                        const int off = a_row + ((r * pl.cs) >> 2) * 32;
                         *reinterpret_cast<float4 *>(a_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
                         *reinterpret_cast<float4 *>(a_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                        *reinterpret_cast<float4 *>(a_hi + off + 32) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+                        *reinterpret_cast<float4 *>(a_lo + off + 32) = make_float4(lo[4], lo[5], lo[6], lo[7]);
                     }
                     if (r == 0 && pl.Ksp > pl.Ks) {                        // zero the K padding of this row
                         const int off = a_row + (pl.Ks >> 2) * 32;
