@@ -430,7 +430,7 @@ FacPlan make_plan(const void *const *ptrs, int nptr, int planes, int H, int W, i
             const size_t stage = (size_t)(K * K + 1) * W * sizeof(float);
             const int want = env_int("EBFI_FAC_STAGES", 0);
             if (want >= 2 && want <= 4 && want * stage <= 200 * 1024) p.d.nstage = want;
-            else if (2 * stage <= 200 * 1024) p.d.nstage = 2;
+            else if (2 * stage <= 72 * 1024) p.d.nstage = 2;      // >= 3 CTAs per SM, else the register variant
         }
     } else {
         p.threads = cols >= 128 ? 128 : ebfi::round_up(cols, 32);
