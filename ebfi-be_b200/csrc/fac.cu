@@ -23,13 +23,25 @@
 // terms in the same order on every run (two-operand merge adds commute), so the result is
 // bit-reproducible without atomics on data.
 #include "common.cuh"
-#include "umma.cuh"      // mbarrier + 1-D bulk (TMA) copy helpers
+#include "umma.cuh"
+
+#include <algorithm>
+#include <cuda_bf16.h>      // mbarrier + 1-D bulk (TMA) copy helpers
 
 namespace {
 
 using ebfi::ceil_div;
 
-// PX-wide vectors of fp32 with streaming (evict-first) global access.
+// Element types: fp32 (the reference's) and bf16 (storage only; all arithmetic is fp32).
+using bf16 = __nv_bfloat16;
+__device__ __forceinline__ float ld_elt(const float *p) { return __ldg(p); }
+__device__ __forceinline__ float ld_elt(const bf16 *p) { return __bfloat162float(__ldg(p)); }
+__device__ __forceinline__ float ld_elt_cg(const float *p) { return __ldcg(p); }
+__device__ __forceinline__ float ld_elt_cg(const bf16 *p) { return __bfloat162float(__ldcg(p)); }
+__device__ __forceinline__ void st_elt(float *p, float v) { *p = v; }
+__device__ __forceinline__ void st_elt(bf16 *p, float v) { *p = __float2bfloat16_rn(v); }
+
+// PX-wide vectors (held as fp32) with streaming (evict-first) global access and shared-memory reads.
 template <int PX> struct Vec;
 template <> struct Vec<4> {
     float v[4];
@@ -38,15 +50,40 @@ template <> struct Vec<4> {
         float4 t = __ldcs(reinterpret_cast<const float4 *>(p));
         return Vec{{t.x, t.y, t.z, t.w}};
     }
+    __device__ __forceinline__ static Vec load_stream(const bf16 *p)
+    {
+        const uint2 t = __ldcs(reinterpret_cast<const uint2 *>(p));
+        return Vec{{__uint_as_float(t.x << 16), __uint_as_float(t.x & 0xFFFF0000u),
+                    __uint_as_float(t.y << 16), __uint_as_float(t.y & 0xFFFF0000u)}};
+    }
+    __device__ __forceinline__ static Vec load_smem(const float *p)
+    {
+        const float4 t = *reinterpret_cast<const float4 *>(p);
+        return Vec{{t.x, t.y, t.z, t.w}};
+    }
+    __device__ __forceinline__ static Vec load_smem(const bf16 *p)
+    {
+        const uint2 t = *reinterpret_cast<const uint2 *>(p);
+        return Vec{{__uint_as_float(t.x << 16), __uint_as_float(t.x & 0xFFFF0000u),
+                    __uint_as_float(t.y << 16), __uint_as_float(t.y & 0xFFFF0000u)}};
+    }
     __device__ __forceinline__ void store_stream(float *p) const
     {
         __stcs(reinterpret_cast<float4 *>(p), make_float4(v[0], v[1], v[2], v[3]));
+    }
+    __device__ __forceinline__ void store_stream(bf16 *p) const
+    {
+        const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+        __stcs(reinterpret_cast<uint2 *>(p), make_uint2(*reinterpret_cast<const uint32_t *>(&a),
+                                                         *reinterpret_cast<const uint32_t *>(&b)));
     }
 };
 template <> struct Vec<1> {
     float v[1];
     __device__ __forceinline__ static Vec load_stream(const float *p) { return Vec{{__ldcs(p)}}; }
+    __device__ __forceinline__ static Vec load_stream(const bf16 *p) { return Vec{{__bfloat162float(*p)}}; }
     __device__ __forceinline__ void store_stream(float *p) const { __stcs(p, v[0]); }
+    __device__ __forceinline__ void store_stream(bf16 *p) const { *p = __float2bfloat16_rn(v[0]); }
 };
 
 struct FacDims {
@@ -58,9 +95,9 @@ struct FacDims {
 };
 
 // ------------------------------------------------------------------ forward ---
-template <int K, int PX>
+template <int K, int PX, typename T>
 __global__ void __launch_bounds__(128)
-fac_fwd_march(const float *__restrict__ in, const float *__restrict__ ker, float *__restrict__ out,
+fac_fwd_march(const T *__restrict__ in, const T *__restrict__ ker, T *__restrict__ out,
               FacDims d)
 {
     constexpr int WIN = PX + K - 1;
@@ -73,15 +110,15 @@ fac_fwd_march(const float *__restrict__ in, const float *__restrict__ ker, float
 
     const int H = d.H, W = d.W, Wi = W + K - 1;
     const int y0 = seg * d.seg_rows, y1 = min(H, y0 + d.seg_rows);
-    const float *inp = in + (size_t)plane * (H + K - 1) * Wi + x;
-    const float *kp = ker + (size_t)plane * K * K * H * W + x;
-    float *op = out + (size_t)plane * H * W + x;
+    const T *inp = in + (size_t)plane * (H + K - 1) * Wi + x;
+    const T *kp = ker + (size_t)plane * K * K * H * W + x;
+    T *op = out + (size_t)plane * H * W + x;
 
     float win[K][WIN];
 #pragma unroll
     for (int r = 1; r < K; ++r)
 #pragma unroll
-        for (int j = 0; j < WIN; ++j) win[r][j] = __ldg(inp + (size_t)(y0 + r - 1) * Wi + j);
+        for (int j = 0; j < WIN; ++j) win[r][j] = ld_elt(inp + (size_t)(y0 + r - 1) * Wi + j);
 
     for (int y = y0; y < y1; ++y) {
         Vec<PX> kv[K * K];
@@ -92,7 +129,7 @@ fac_fwd_march(const float *__restrict__ in, const float *__restrict__ ker, float
 #pragma unroll
             for (int j = 0; j < WIN; ++j) win[r][j] = win[r + 1][j];
 #pragma unroll
-        for (int j = 0; j < WIN; ++j) win[K - 1][j] = __ldg(inp + (size_t)(y + K - 1) * Wi + j);
+        for (int j = 0; j < WIN; ++j) win[K - 1][j] = ld_elt(inp + (size_t)(y + K - 1) * Wi + j);
 
         Vec<PX> acc;
 #pragma unroll
@@ -115,10 +152,10 @@ fac_fwd_march(const float *__restrict__ in, const float *__restrict__ ker, float
 // through a ring of `d.nstage` shared-memory stages filled by 1-D bulk (TMA) copies that one thread
 // issues two rows ahead; bytes in flight then live in shared memory instead of registers (the
 // register variant keeps 25 float4 loads = 100 registers per thread in flight, 8 warps per SM).
-template <int K, int PX, bool RING>
+template <int K, int PX, bool RING, typename T>
 __global__ void __launch_bounds__(256)
-fac_bwd_march(const float *__restrict__ in, const float *__restrict__ ker,
-              const float *__restrict__ gout, float *__restrict__ gin, float *__restrict__ gker,
+fac_bwd_march(const T *__restrict__ in, const T *__restrict__ ker,
+              const T *__restrict__ gout, T *__restrict__ gin, T *__restrict__ gker,
               int *__restrict__ counters, float *__restrict__ overhang, FacDims d)
 {
     constexpr int WIN = PX + K - 1;
@@ -140,11 +177,11 @@ fac_bwd_march(const float *__restrict__ in, const float *__restrict__ ker,
     const int y0 = seg * d.seg_rows, y1 = min(H, y0 + d.seg_rows);
     const bool wi_vec = (PX == 4) && (Wi % 4 == 0);
 
-    const float *inp = in + (size_t)plane * (H + R) * Wi + x;
-    const float *kp = ker + (size_t)plane * K * K * H * W + x;
-    const float *gp = gout + (size_t)plane * H * W + x;
-    float *gkp = gker + (size_t)plane * K * K * H * W + x;
-    float *gip = gin + (size_t)plane * (H + R) * Wi;
+    const T *inp = in + (size_t)plane * (H + R) * Wi + x;
+    const T *kp = ker + (size_t)plane * K * K * H * W + x;
+    const T *gp = gout + (size_t)plane * H * W + x;
+    T *gkp = gker + (size_t)plane * K * K * H * W + x;
+    T *gip = gin + (size_t)plane * (H + R) * Wi;
 
     float win[K][WIN], acc[K][WIN];
 #pragma unroll
@@ -155,21 +192,21 @@ fac_bwd_march(const float *__restrict__ in, const float *__restrict__ ker,
 #pragma unroll
         for (int r = 1; r < K; ++r)
 #pragma unroll
-            for (int j = 0; j < WIN; ++j) win[r][j] = __ldg(inp + (size_t)(y0 + r - 1) * Wi + j);
+            for (int j = 0; j < WIN; ++j) win[r][j] = ld_elt(inp + (size_t)(y0 + r - 1) * Wi + j);
     }
 
-    // ---- ring of (K*K + 1) x W floats per stage: rows k of `kernel`, then the grad_output row
-    float *ring = dyn_smem + ((2 * blockDim.x * RS + 31) & ~31);
-    const int stage_floats = (K * K + 1) * W;
+    // ---- ring of (K*K + 1) x W elements per stage: rows k of `kernel`, then the grad_output row
+    T *ring = reinterpret_cast<T *>(dyn_smem + ((2 * blockDim.x * RS + 31) & ~31));
+    const int stage_elts = (K * K + 1) * W;
     auto issue_row = [&](int y) {                  // thread 0: bulk copies of row y into its stage
         const int st = (y - y0) % d.nstage;
-        float *dst = ring + (size_t)st * stage_floats;
-        umma::mbar_expect_tx(&ring_bar[st], (uint32_t)(stage_floats * sizeof(float)));
-        const float *src = ker + (size_t)plane * K * K * H * W + (size_t)y * W;
+        T *dst = ring + (size_t)st * stage_elts;
+        umma::mbar_expect_tx(&ring_bar[st], (uint32_t)(stage_elts * sizeof(T)));
+        const T *src = ker + (size_t)plane * K * K * H * W + (size_t)y * W;
         for (int k = 0; k < K * K; ++k)
-            umma::bulk_g2s(dst + (size_t)k * W, src + (size_t)k * H * W, (uint32_t)(W * sizeof(float)), &ring_bar[st]);
+            umma::bulk_g2s(dst + (size_t)k * W, src + (size_t)k * H * W, (uint32_t)(W * sizeof(T)), &ring_bar[st]);
         umma::bulk_g2s(dst + (size_t)K * K * W, gout + (size_t)plane * H * W + (size_t)y * W,
-                       (uint32_t)(W * sizeof(float)), &ring_bar[st]);
+                       (uint32_t)(W * sizeof(T)), &ring_bar[st]);
     };
     if constexpr (RING) {
         if (t == 0) {
@@ -182,7 +219,8 @@ fac_bwd_march(const float *__restrict__ in, const float *__restrict__ ker,
 
     // Emits one finished (or segment-partial) grad_input row held in acc[0] after the
     // neighbour exchange. `dst` is the row base (Wi floats) in gin or in the overhang buffer.
-    auto emit_row = [&](const float (&row)[WIN], float *dst, int parity) {
+    // `dst_t` (a grad_input row) or `dst_f` (an fp32 overhang row): exactly one is non-null.
+    auto emit_row = [&](const float (&row)[WIN], T *dst_t, float *dst_f, int parity) {
         float *xb = xchg + (size_t)parity * nthr * RS;
         if constexpr (R > 0) {
 #pragma unroll
@@ -203,11 +241,18 @@ fac_bwd_march(const float *__restrict__ in, const float *__restrict__ ker,
                     }
                 }
             }
-            if (wi_vec) {
-                *reinterpret_cast<float4 *>(dst + x) = make_float4(o[0], o[PX > 1 ? 1 : 0], o[PX > 2 ? 2 : 0], o[PX > 3 ? 3 : 0]);
+            if (dst_f) {
+                if (wi_vec) {
+                    *reinterpret_cast<float4 *>(dst_f + x) = make_float4(o[0], o[PX > 1 ? 1 : 0], o[PX > 2 ? 2 : 0], o[PX > 3 ? 3 : 0]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < PX; ++j) dst_f[x + j] = o[j];
+                }
+            } else if (wi_vec && sizeof(T) == 4) {
+                *reinterpret_cast<float4 *>(dst_t + x) = make_float4(o[0], o[PX > 1 ? 1 : 0], o[PX > 2 ? 2 : 0], o[PX > 3 ? 3 : 0]);
             } else {
 #pragma unroll
-                for (int j = 0; j < PX; ++j) dst[x + j] = o[j];
+                for (int j = 0; j < PX; ++j) st_elt(dst_t + x + j, o[j]);
             }
         }
         if constexpr (R > 0) {
@@ -219,7 +264,7 @@ fac_bwd_march(const float *__restrict__ in, const float *__restrict__ ker,
                     const int src = tv - dd, c = j + PX * dd;
                     if (src >= 0 && src < nact && c < WIN) o += xb[src * RS + (c - PX)];
                 }
-                dst[X] = o;
+                if (dst_f) dst_f[X] = o; else st_elt(dst_t + X, o);
             }
         }
     };
@@ -232,21 +277,21 @@ fac_bwd_march(const float *__restrict__ in, const float *__restrict__ ker,
             const int st = (y - y0) % d.nstage;
             umma::mbar_wait(&ring_bar[st], ((y - y0) / d.nstage) & 1);
             if (active) {
-                const float *stg = ring + (size_t)st * stage_floats + x;
-                const float4 g4 = *reinterpret_cast<const float4 *>(stg + (size_t)K * K * W);
-                const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+                const T *stg = ring + (size_t)st * stage_elts + x;
+                const Vec<4> gv = Vec<4>::load_smem(stg + (size_t)K * K * W);
+                const float *g = gv.v;
 #pragma unroll
                 for (int r = 0; r < K - 1; ++r)
 #pragma unroll
                     for (int j = 0; j < WIN; ++j) win[r][j] = win[r + 1][j];
 #pragma unroll
-                for (int j = 0; j < WIN; ++j) win[K - 1][j] = __ldg(inp + (size_t)(y + K - 1) * Wi + j);
+                for (int j = 0; j < WIN; ++j) win[K - 1][j] = ld_elt(inp + (size_t)(y + K - 1) * Wi + j);
 #pragma unroll
                 for (int ky = 0; ky < K; ++ky)
 #pragma unroll
                     for (int kx = 0; kx < K; ++kx) {
-                        const float4 k4 = *reinterpret_cast<const float4 *>(stg + (size_t)(ky * K + kx) * W);
-                        const float kvv[4] = {k4.x, k4.y, k4.z, k4.w};
+                        const Vec<4> kq = Vec<4>::load_smem(stg + (size_t)(ky * K + kx) * W);
+                        const float *kvv = kq.v;
                         Vec<4> gk;
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
@@ -266,7 +311,7 @@ fac_bwd_march(const float *__restrict__ in, const float *__restrict__ ker,
 #pragma unroll
                 for (int j = 0; j < WIN; ++j) win[r][j] = win[r + 1][j];
 #pragma unroll
-            for (int j = 0; j < WIN; ++j) win[K - 1][j] = __ldg(inp + (size_t)(y + K - 1) * Wi + j);
+            for (int j = 0; j < WIN; ++j) win[K - 1][j] = ld_elt(inp + (size_t)(y + K - 1) * Wi + j);
 #pragma unroll
             for (int ky = 0; ky < K; ++ky)
 #pragma unroll
@@ -280,7 +325,7 @@ fac_bwd_march(const float *__restrict__ in, const float *__restrict__ ker,
                     gk.store_stream(gkp + ((size_t)(ky * K + kx) * H + y) * W);
                 }
         }
-        emit_row(acc[0], gip + (size_t)y * Wi, parity);
+        emit_row(acc[0], gip + (size_t)y * Wi, nullptr, parity);
         parity ^= 1;
 #pragma unroll
         for (int r = 0; r < K - 1; ++r)
@@ -296,8 +341,8 @@ fac_bwd_march(const float *__restrict__ in, const float *__restrict__ ker,
         float *oh = last ? nullptr : overhang + ((size_t)plane * (d.nseg - 1) + seg) * R * Wi;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            float *dst = last ? gip + (size_t)(y1 + r) * Wi : oh + (size_t)r * Wi;
-            emit_row(acc[r], dst, parity);
+            if (last) emit_row(acc[r], gip + (size_t)(y1 + r) * Wi, nullptr, parity);
+            else emit_row(acc[r], nullptr, oh + (size_t)r * Wi, parity);
             parity ^= 1;
         }
         if (d.nseg == 1) return;
@@ -318,34 +363,36 @@ fac_bwd_march(const float *__restrict__ in, const float *__restrict__ ker,
             const int bseg = side == 0 ? seg - 1 : seg;             // upper segment of the boundary
             const int yb = (bseg + 1) * d.seg_rows;                 // first row of the lower segment
             const float *src = overhang + ((size_t)plane * (d.nseg - 1) + bseg) * R * Wi;
-            float *dst = gip + (size_t)yb * Wi;
-            for (int e = t; e < R * Wi; e += nthr) dst[e] = __ldcg(dst + e) + __ldcg(src + e);
+            T *dst = gip + (size_t)yb * Wi;
+            for (int e = t; e < R * Wi; e += nthr) st_elt(dst + e, ld_elt_cg(dst + e) + __ldcg(src + e));
         }
     }
 }
 
 // ------------------------------------------------- generic fallback kernels ---
 // Any K, any size: one thread per element, no data-dependent reductions.
-__global__ void fac_fwd_generic(const float *__restrict__ in, const float *__restrict__ ker,
-                                float *__restrict__ out, int planes, int H, int W, int K)
+template <typename T>
+__global__ void fac_fwd_generic(const T *__restrict__ in, const T *__restrict__ ker,
+                                T *__restrict__ out, int planes, int H, int W, int K)
 {
     const size_t n = (size_t)planes * H * W;
     const int Wi = W + K - 1, Hi = H + K - 1;
     for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
         const int x = e % W, y = (e / W) % H;
         const size_t plane = e / ((size_t)H * W);
-        const float *ip = in + (plane * Hi + y) * Wi + x;
-        const float *kp = ker + plane * K * K * H * W + (size_t)y * W + x;
+        const T *ip = in + (plane * Hi + y) * Wi + x;
+        const T *kp = ker + plane * K * K * H * W + (size_t)y * W + x;
         float s = 0.f;
         for (int ky = 0; ky < K; ++ky)
-            for (int kx = 0; kx < K; ++kx) s += ip[(size_t)ky * Wi + kx] * kp[(size_t)(ky * K + kx) * H * W];
-        out[e] = s;
+            for (int kx = 0; kx < K; ++kx) s += ld_elt(ip + (size_t)ky * Wi + kx) * ld_elt(kp + (size_t)(ky * K + kx) * H * W);
+        st_elt(out + e, s);
     }
 }
 
-__global__ void fac_bwd_generic(const float *__restrict__ in, const float *__restrict__ ker,
-                                const float *__restrict__ gout, float *__restrict__ gin,
-                                float *__restrict__ gker, int planes, int H, int W, int K)
+template <typename T>
+__global__ void fac_bwd_generic(const T *__restrict__ in, const T *__restrict__ ker,
+                                const T *__restrict__ gout, T *__restrict__ gin,
+                                T *__restrict__ gker, int planes, int H, int W, int K)
 {
     const int Wi = W + K - 1, Hi = H + K - 1;
     const size_t n_in = (size_t)planes * Hi * Wi, n_k = (size_t)planes * K * K * H * W;
@@ -353,20 +400,20 @@ __global__ void fac_bwd_generic(const float *__restrict__ in, const float *__res
     for (size_t e = tid; e < n_in; e += stride) {
         const int X = e % Wi, Y = (e / Wi) % Hi;
         const size_t plane = e / ((size_t)Hi * Wi);
-        const float *kp = ker + plane * K * K * H * W, *gp = gout + plane * H * W;
+        const T *kp = ker + plane * K * K * H * W, *gp = gout + plane * H * W;
         float s = 0.f;
         for (int ky = 0; ky < K; ++ky)
             for (int kx = 0; kx < K; ++kx) {
                 const int y = Y - ky, x = X - kx;
                 if (y >= 0 && y < H && x >= 0 && x < W)
-                    s += kp[((size_t)(ky * K + kx) * H + y) * W + x] * gp[(size_t)y * W + x];
+                    s += ld_elt(kp + ((size_t)(ky * K + kx) * H + y) * W + x) * ld_elt(gp + (size_t)y * W + x);
             }
-        gin[e] = s;
+        st_elt(gin + e, s);
     }
     for (size_t e = tid; e < n_k; e += stride) {
         const int x = e % W, y = (e / W) % H, k = (e / ((size_t)H * W)) % (K * K);
         const size_t plane = e / ((size_t)K * K * H * W);
-        gker[e] = in[(plane * Hi + y + k / K) * Wi + x + k % K] * gout[(plane * H + y) * W + x];
+        st_elt(gker + e, ld_elt(in + (plane * Hi + y + k / K) * Wi + x + k % K) * ld_elt(gout + (plane * H + y) * W + x));
     }
 }
 
@@ -397,7 +444,7 @@ int choose_seg(int planes, int H, int K)
     return seg;
 }
 
-FacPlan make_plan(const void *const *ptrs, int nptr, int planes, int H, int W, int K, bool backward)
+FacPlan make_plan(const void *const *ptrs, int nptr, int planes, int H, int W, int K, bool backward, int esize)
 {
     FacPlan p{};
     p.d.H = H; p.d.W = W;
@@ -427,9 +474,11 @@ FacPlan make_plan(const void *const *ptrs, int nptr, int planes, int H, int W, i
         // benchmark shape: 2 stages = 4 CTAs/SM -> 0.600 ms (91 % of HBM peak); 3 or 4 stages = 2 CTAs/SM
         // -> 0.763 ms; register variant 0.687 ms. Resident CTAs matter more than ring depth.
         if (p.px == 4 && (K == 3 || K == 5) && env_int("EBFI_FAC_RING", 1)) {
-            const size_t stage = (size_t)(K * K + 1) * W * sizeof(float);
+            const size_t stage = (size_t)(K * K + 1) * W * esize;
             const int want = env_int("EBFI_FAC_STAGES", 0);
-            if (want >= 2 && want <= 4 && want * stage <= 200 * 1024) p.d.nstage = want;
+            const bool rows16 = ((size_t)W * esize) % 16 == 0;     // bulk copies move multiples of 16 bytes
+            if (!rows16) p.d.nstage = 0;
+            else if (want >= 2 && want <= 4 && want * stage <= 200 * 1024) p.d.nstage = want;
             else if (2 * stage <= 72 * 1024) p.d.nstage = 2;      // >= 3 CTAs per SM, else the register variant
         }
     } else {
@@ -439,16 +488,16 @@ FacPlan make_plan(const void *const *ptrs, int nptr, int planes, int H, int W, i
     return p;
 }
 
-template <int PX>
-int launch_fwd(cudaStream_t st, const FacPlan &p, const float *in, const float *ker, float *out,
+template <int PX, typename T>
+int launch_fwd(cudaStream_t st, const FacPlan &p, const T *in, const T *ker, T *out,
                int planes, int K)
 {
     const unsigned grid = (unsigned)((size_t)planes * p.d.nseg * p.d.nxb);
     switch (K) {
-    case 1: fac_fwd_march<1, PX><<<grid, p.threads, 0, st>>>(in, ker, out, p.d); break;
-    case 3: fac_fwd_march<3, PX><<<grid, p.threads, 0, st>>>(in, ker, out, p.d); break;
-    case 5: fac_fwd_march<5, PX><<<grid, p.threads, 0, st>>>(in, ker, out, p.d); break;
-    case 7: if constexpr (PX == 1) { fac_fwd_march<7, 1><<<grid, p.threads, 0, st>>>(in, ker, out, p.d); break; }
+    case 1: fac_fwd_march<1, PX, T><<<grid, p.threads, 0, st>>>(in, ker, out, p.d); break;
+    case 3: fac_fwd_march<3, PX, T><<<grid, p.threads, 0, st>>>(in, ker, out, p.d); break;
+    case 5: fac_fwd_march<5, PX, T><<<grid, p.threads, 0, st>>>(in, ker, out, p.d); break;
+    case 7: if constexpr (PX == 1) { fac_fwd_march<7, 1, T><<<grid, p.threads, 0, st>>>(in, ker, out, p.d); break; }
             return ebfi::fail(EBFI_ERR_INVALID, "fac: K=7 runs 1 px/thread only");
     default: return ebfi::fail(EBFI_ERR_INVALID, "fac: unsupported K=%d in march path", K);
     }
@@ -456,18 +505,18 @@ int launch_fwd(cudaStream_t st, const FacPlan &p, const float *in, const float *
     return EBFI_OK;
 }
 
-template <int PX>
-int launch_bwd(cudaStream_t st, const FacPlan &p, const float *in, const float *ker,
-               const float *gout, float *gin, float *gker, int *counters, float *overhang,
+template <int PX, typename T>
+int launch_bwd(cudaStream_t st, const FacPlan &p, const T *in, const T *ker,
+               const T *gout, T *gin, T *gker, int *counters, float *overhang,
                int planes, int K)
 {
     const unsigned grid = (unsigned)((size_t)planes * p.d.nseg);
     const int RS = K > 1 ? K - 1 : 1;
     const size_t xch = (size_t)((2 * p.threads * RS + 31) & ~31) * sizeof(float);
-    const size_t smem = xch + (size_t)p.d.nstage * (K * K + 1) * p.d.W * sizeof(float);
+    const size_t smem = xch + (size_t)p.d.nstage * (K * K + 1) * p.d.W * sizeof(T);
 #define EBFI_FAC_BWD(KK, RING)                                                                              \
     do {                                                                                                    \
-        auto kern = fac_bwd_march<KK, PX, RING>;                                                            \
+        auto kern = fac_bwd_march<KK, PX, RING, T>;                                                            \
         EBFI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
         kern<<<grid, p.threads, smem, st>>>(in, ker, gout, gin, gker, counters, overhang, p.d);            \
     } while (0)
@@ -507,11 +556,8 @@ size_t ws_counter_bytes(int planes, int nseg)
     return ebfi::round_up((size_t)planes * (size_t)(nseg > 1 ? nseg - 1 : 1) * sizeof(int), (size_t)256);
 }
 
-}  // namespace
-
-extern "C" {
-
-int ebfi_fac_forward(void *stream, const float *input, const float *kernel, float *output,
+template <typename T>
+int fac_forward_impl(void *stream, const T *input, const T *kernel, T *output,
                      int batch, int channels, int height_out, int width_out, int kernel_size)
 {
     if (int rc = check_dims(batch, channels, height_out, width_out, kernel_size)) return rc;
@@ -519,14 +565,65 @@ int ebfi_fac_forward(void *stream, const float *input, const float *kernel, floa
     const int planes = batch * channels, H = height_out, W = width_out, K = kernel_size;
     cudaStream_t st = ebfi::as_stream(stream);
     const void *ptrs[] = {kernel, output};
-    const FacPlan p = make_plan(ptrs, 2, planes, H, W, K, false);
-    if (p.px == 4) return launch_fwd<4>(st, p, input, kernel, output, planes, K);
-    if (p.px == 1) return launch_fwd<1>(st, p, input, kernel, output, planes, K);
+    const FacPlan p = make_plan(ptrs, 2, planes, H, W, K, false, (int)sizeof(T));
+    if (p.px == 4) return launch_fwd<4, T>(st, p, input, kernel, output, planes, K);
+    if (p.px == 1) return launch_fwd<1, T>(st, p, input, kernel, output, planes, K);
     const size_t n = (size_t)planes * H * W;
-    const unsigned grid = (unsigned)min((size_t)ebfi::sm_count() * 16, ceil_div(n, (size_t)256));
-    fac_fwd_generic<<<grid, 256, 0, st>>>(input, kernel, output, planes, H, W, K);
+    const unsigned grid = (unsigned)std::min((size_t)ebfi::sm_count() * 16, ceil_div(n, (size_t)256));
+    fac_fwd_generic<T><<<grid, 256, 0, st>>>(input, kernel, output, planes, H, W, K);
     EBFI_LAUNCH_OK("fac_fwd_generic");
     return EBFI_OK;
+}
+
+template <typename T>
+int fac_backward_impl(void *stream, const T *input, const T *kernel, const T *grad_output, T *grad_input,
+                      T *grad_kernel, int batch, int channels, int height_out, int width_out, int kernel_size,
+                      void *workspace, size_t workspace_bytes)
+{
+    if (int rc = check_dims(batch, channels, height_out, width_out, kernel_size)) return rc;
+    EBFI_REQUIRE(input && kernel && grad_output && grad_input && grad_kernel, "fac_backward: null pointer");
+    const int planes = batch * channels, H = height_out, W = width_out, K = kernel_size;
+    cudaStream_t st = ebfi::as_stream(stream);
+    const void *ptrs[] = {kernel, grad_output, grad_kernel, grad_input};
+    const FacPlan p = make_plan(ptrs, 4, planes, H, W, K, true, (int)sizeof(T));
+    if (p.px == 0) {
+        const size_t n = (size_t)planes * K * K * H * W;
+        const unsigned grid = (unsigned)std::min((size_t)ebfi::sm_count() * 16, ceil_div(n, (size_t)256));
+        fac_bwd_generic<T><<<grid, 256, 0, st>>>(input, kernel, grad_output, grad_input, grad_kernel, planes, H, W, K);
+        EBFI_LAUNCH_OK("fac_bwd_generic");
+        return EBFI_OK;
+    }
+    int *counters = nullptr;
+    float *overhang = nullptr;
+    if (p.d.nseg > 1 && K > 1) {
+        const size_t cb = ws_counter_bytes(planes, p.d.nseg);
+        const size_t need = cb + (size_t)planes * (p.d.nseg - 1) * (K - 1) * (size_t)(W + K - 1) * sizeof(float);
+        if (!workspace || workspace_bytes < need)
+            return ebfi::fail(EBFI_ERR_WORKSPACE, "fac_backward: workspace %zu < %zu bytes", workspace_bytes, need);
+        EBFI_REQUIRE(ebfi::aligned16(workspace), "fac_backward: workspace must be 16-byte aligned");
+        counters = static_cast<int *>(workspace);
+        overhang = reinterpret_cast<float *>(static_cast<char *>(workspace) + cb);
+        EBFI_CUDA_OK(cudaMemsetAsync(counters, 0, (size_t)planes * (p.d.nseg - 1) * sizeof(int), st));
+    }
+    if (p.px == 4) return launch_bwd<4, T>(st, p, input, kernel, grad_output, grad_input, grad_kernel, counters, overhang, planes, K);
+    return launch_bwd<1, T>(st, p, input, kernel, grad_output, grad_input, grad_kernel, counters, overhang, planes, K);
+}
+
+}  // namespace
+
+extern "C" {
+
+int ebfi_fac_forward(void *stream, const float *input, const float *kernel, float *output,
+                     int batch, int channels, int height_out, int width_out, int kernel_size)
+{
+    return fac_forward_impl<float>(stream, input, kernel, output, batch, channels, height_out, width_out, kernel_size);
+}
+
+int ebfi_fac_forward_bf16(void *stream, const void *input, const void *kernel, void *output,
+                          int batch, int channels, int height_out, int width_out, int kernel_size)
+{
+    return fac_forward_impl<bf16>(stream, static_cast<const bf16 *>(input), static_cast<const bf16 *>(kernel),
+                                  static_cast<bf16 *>(output), batch, channels, height_out, width_out, kernel_size);
 }
 
 size_t ebfi_fac_backward_workspace_bytes(int batch, int channels, int height_out, int width_out,
@@ -545,33 +642,18 @@ int ebfi_fac_backward(void *stream, const float *input, const float *kernel,
                       int batch, int channels, int height_out, int width_out, int kernel_size,
                       void *workspace, size_t workspace_bytes)
 {
-    if (int rc = check_dims(batch, channels, height_out, width_out, kernel_size)) return rc;
-    EBFI_REQUIRE(input && kernel && grad_output && grad_input && grad_kernel, "fac_backward: null pointer");
-    const int planes = batch * channels, H = height_out, W = width_out, K = kernel_size;
-    cudaStream_t st = ebfi::as_stream(stream);
-    const void *ptrs[] = {kernel, grad_output, grad_kernel, grad_input};
-    const FacPlan p = make_plan(ptrs, 4, planes, H, W, K, true);
-    if (p.px == 0) {
-        const size_t n = (size_t)planes * K * K * H * W;
-        const unsigned grid = (unsigned)min((size_t)ebfi::sm_count() * 16, ceil_div(n, (size_t)256));
-        fac_bwd_generic<<<grid, 256, 0, st>>>(input, kernel, grad_output, grad_input, grad_kernel, planes, H, W, K);
-        EBFI_LAUNCH_OK("fac_bwd_generic");
-        return EBFI_OK;
-    }
-    int *counters = nullptr;
-    float *overhang = nullptr;
-    if (p.d.nseg > 1 && K > 1) {
-        const size_t cb = ws_counter_bytes(planes, p.d.nseg);
-        const size_t need = cb + (size_t)planes * (p.d.nseg - 1) * (K - 1) * (size_t)(W + K - 1) * sizeof(float);
-        if (!workspace || workspace_bytes < need)
-            return ebfi::fail(EBFI_ERR_WORKSPACE, "fac_backward: workspace %zu < %zu bytes", workspace_bytes, need);
-        EBFI_REQUIRE(ebfi::aligned16(workspace), "fac_backward: workspace must be 16-byte aligned");
-        counters = static_cast<int *>(workspace);
-        overhang = reinterpret_cast<float *>(static_cast<char *>(workspace) + cb);
-        EBFI_CUDA_OK(cudaMemsetAsync(counters, 0, (size_t)planes * (p.d.nseg - 1) * sizeof(int), st));
-    }
-    if (p.px == 4) return launch_bwd<4>(st, p, input, kernel, grad_output, grad_input, grad_kernel, counters, overhang, planes, K);
-    return launch_bwd<1>(st, p, input, kernel, grad_output, grad_input, grad_kernel, counters, overhang, planes, K);
+    return fac_backward_impl<float>(stream, input, kernel, grad_output, grad_input, grad_kernel, batch, channels,
+                                    height_out, width_out, kernel_size, workspace, workspace_bytes);
+}
+
+int ebfi_fac_backward_bf16(void *stream, const void *input, const void *kernel, const void *grad_output,
+                           void *grad_input, void *grad_kernel, int batch, int channels, int height_out,
+                           int width_out, int kernel_size, void *workspace, size_t workspace_bytes)
+{
+    return fac_backward_impl<bf16>(stream, static_cast<const bf16 *>(input), static_cast<const bf16 *>(kernel),
+                                   static_cast<const bf16 *>(grad_output), static_cast<bf16 *>(grad_input),
+                                   static_cast<bf16 *>(grad_kernel), batch, channels, height_out, width_out,
+                                   kernel_size, workspace, workspace_bytes);
 }
 
 }  // extern "C"

@@ -19,7 +19,9 @@ except ImportError:  # shims directory used stand-alone on sys.path
 
 def _dims(input, kernel, kernel_size, what):
     L.require_cuda(input, kernel)
-    L.require_f32(input=input, kernel=kernel)
+    if input.dtype not in (torch.float32, torch.bfloat16) or kernel.dtype != input.dtype:
+        raise RuntimeError(f"{what}: input and kernel must both be float32 (the reference's dtype) or both "
+                           f"bfloat16, got {input.dtype} / {kernel.dtype}")
     if input.dim() != 4 or kernel.dim() != 4:
         raise RuntimeError(f"{what}: input and kernel must be 4-D")
     B, C, Hi, Wi = input.shape
@@ -35,19 +37,22 @@ def _dims(input, kernel, kernel_size, what):
 
 def forward(input, kernel, kernel_size, output):
     B, C, H, W, K = _dims(input, kernel, kernel_size, "kernelconv2d_cuda.forward")
-    if tuple(output.shape) != (B, C, H, W) or not output.is_contiguous() or output.dtype != torch.float32:
-        raise RuntimeError("kernelconv2d_cuda.forward: output must be a contiguous float32 (B, C, H, W) tensor")
+    if tuple(output.shape) != (B, C, H, W) or not output.is_contiguous() or output.dtype != input.dtype:
+        raise RuntimeError("kernelconv2d_cuda.forward: output must be a contiguous (B, C, H, W) tensor of the input dtype")
+    lib = L.load()
+    fn = lib.ebfi_fac_forward if input.dtype == torch.float32 else lib.ebfi_fac_forward_bf16
     with torch.cuda.device(input.device):
-        L.check(L.load().ebfi_fac_forward(L.stream_ptr(input.device), L.ptr(input), L.ptr(kernel),
-                                          L.ptr(output), B, C, H, W, K), "CUDA call")
+        L.check(fn(L.stream_ptr(input.device), L.ptr(input), L.ptr(kernel), L.ptr(output), B, C, H, W, K), "CUDA call")
     return 1
 
 
 def backward(input, kernel, kernel_size, grad_output, grad_input, grad_kernel):
     B, C, H, W, K = _dims(input, kernel, kernel_size, "kernelconv2d_cuda.backward")
     L.require_cuda(grad_output, grad_input, grad_kernel)
-    if tuple(grad_output.shape) != (B, C, H, W) or not grad_output.is_contiguous():
-        raise RuntimeError("kernelconv2d_cuda.backward: grad_output must be contiguous (B, C, H, W)")
+    if tuple(grad_output.shape) != (B, C, H, W) or not grad_output.is_contiguous() or grad_output.dtype != input.dtype:
+        raise RuntimeError("kernelconv2d_cuda.backward: grad_output must be contiguous (B, C, H, W) of the input dtype")
+    if grad_input.dtype != input.dtype or grad_kernel.dtype != input.dtype:
+        raise RuntimeError("kernelconv2d_cuda.backward: gradients must have the input dtype")
     if grad_input.shape != input.shape or grad_kernel.shape != kernel.shape or \
             not grad_input.is_contiguous() or not grad_kernel.is_contiguous():
         raise RuntimeError("kernelconv2d_cuda.backward: grad_input / grad_kernel must match input / kernel")
@@ -55,7 +60,7 @@ def backward(input, kernel, kernel_size, grad_output, grad_input, grad_kernel):
     with torch.cuda.device(input.device):
         nbytes = lib.ebfi_fac_backward_workspace_bytes(B, C, H, W, K)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=input.device)
-        L.check(lib.ebfi_fac_backward(L.stream_ptr(input.device), L.ptr(input), L.ptr(kernel),
-                                      L.ptr(grad_output), L.ptr(grad_input), L.ptr(grad_kernel),
-                                      B, C, H, W, K, L.ptr(ws), nbytes), "CUDA call")
+        fn = lib.ebfi_fac_backward if input.dtype == torch.float32 else lib.ebfi_fac_backward_bf16
+        L.check(fn(L.stream_ptr(input.device), L.ptr(input), L.ptr(kernel), L.ptr(grad_output), L.ptr(grad_input),
+                   L.ptr(grad_kernel), B, C, H, W, K, L.ptr(ws), nbytes), "CUDA call")
     return 1

@@ -125,6 +125,16 @@ int ebfi_fac_backward(void *stream, const float *input, const float *kernel,
                       int batch, int channels, int height_out, int width_out, int kernel_size,
                       void *workspace, size_t workspace_bytes);
 
+/* bf16 storage variants (new; the reference is fp32-only, KernelConv2D_kernel.cu:68 `data<float>()`):
+ * every tensor is bfloat16, all arithmetic and the grad_input reduction are fp32, results are
+ * rounded once on store. Half the HBM bytes of the fp32 op. Pointers are `__nv_bfloat16*`. */
+int ebfi_fac_forward_bf16(void *stream, const void *input, const void *kernel, void *output,
+                          int batch, int channels, int height_out, int width_out, int kernel_size);
+int ebfi_fac_backward_bf16(void *stream, const void *input, const void *kernel, const void *grad_output,
+                           void *grad_input, void *grad_kernel,
+                           int batch, int channels, int height_out, int width_out, int kernel_size,
+                           void *workspace, size_t workspace_bytes);
+
 /* ---- event encoders --------------------------------------------------------- */
 
 /* Coordinate / timestamp arrays may be fp32 or fp64, like the tensors the

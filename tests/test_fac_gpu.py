@@ -136,3 +136,50 @@ def test_full_size_properties(fac):
     out.backward(go)
     a, b, c = dot(go, out), dot(xg.grad, x), dot(kg.grad, ker)
     assert abs(a - b) <= 1e-5 * abs(a) and abs(a - c) <= 1e-5 * abs(a)
+
+
+# bf16 storage variant (new capability; the reference is fp32-only). Stated tolerance: inputs are the
+# bf16-rounded tensors, arithmetic is fp32, so the only error is the final rounding of each result to
+# bf16: |err| <= 2^-8 * max|ref| per tensor (bf16 has 8 significand bits).
+BF16_TOL = 2.0 ** -8
+
+
+@pytest.mark.parametrize("shape", [(2, 4, 5, 40, 64), (1, 3, 5, 33, 20), (1, 2, 3, 37, 36), (1, 2, 5, 19, 23),
+                                   (1, 2, 1, 20, 16), (1, 1, 9, 12, 16)])
+def test_bf16_variant_against_oracle(fac, oracle, shape):
+    from gpu_util import dev
+    B, C, K, H, W = shape
+    g = torch.Generator().manual_seed(B * 100 + H)
+    x = torch.randn(B, C, H + K - 1, W + K - 1, generator=g).bfloat16()
+    ker = torch.randn(B, C * K * K, H, W, generator=g).bfloat16()
+    go = torch.randn(B, C, H, W, generator=g).bfloat16()
+    xg, kg = x.to(dev()).requires_grad_(), ker.to(dev()).requires_grad_()
+    out = fac.KernelConv2DFunction.apply(xg, kg, K)
+    assert out.dtype == torch.bfloat16
+    out.backward(go.to(dev()))
+    xf, kf, gf = x.float().numpy(), ker.float().numpy(), go.float().numpy()
+    assert rel_err(out.detach().float().cpu().numpy(), oracle.fac_forward(xf, kf, K)) < BF16_TOL
+    ogi, ogk = oracle.fac_backward(xf, kf, gf, K)
+    assert rel_err(xg.grad.float().cpu().numpy(), ogi) < BF16_TOL
+    assert rel_err(kg.grad.float().cpu().numpy(), ogk) < BF16_TOL
+
+
+def test_bf16_full_size_is_reproducible_and_close_to_fp32(fac):
+    from gpu_util import dev
+    torch.manual_seed(0)
+    B, C, K, H, W = 4, 64, 5, 256, 256
+    x = torch.randn(B, C, H + K - 1, W + K - 1, device=dev()).bfloat16()
+    ker = (0.1 * torch.randn(B, C * K * K, H, W, device=dev())).bfloat16()
+    go = torch.randn(B, C, H, W, device=dev()).bfloat16()
+    res = []
+    for _ in range(2):
+        xg, kg = x.clone().requires_grad_(), ker.clone().requires_grad_()
+        o = fac.KernelConv2DFunction.apply(xg, kg, K)
+        o.backward(go)
+        res.append((o.detach(), xg.grad, kg.grad))
+    assert all(torch.equal(a, b) for a, b in zip(*res))
+    xf, kf = x.float().requires_grad_(), ker.float().requires_grad_()
+    of = fac.KernelConv2DFunction.apply(xf, kf, K)
+    of.backward(go.float())
+    for got, want in zip(res[0], (of.detach(), xf.grad, kf.grad)):
+        assert float((got.float() - want).abs().max()) <= BF16_TOL * float(want.abs().max())
