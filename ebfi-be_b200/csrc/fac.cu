@@ -92,6 +92,8 @@ struct FacDims {
     int nseg;          // segments per plane
     int nxb;           // thread blocks along x (forward only)
     int nstage;        // ring stages of the backward (0 = register variant)
+    int xstride;       // backward: first column of block i is i * xstride (blocks overlap by `halo_thr` threads)
+    int halo_thr;      // backward: leading threads of blocks > 0 that only recompute the left neighbour's columns
 };
 
 // ------------------------------------------------------------------ forward ---
@@ -167,13 +169,21 @@ fac_bwd_march(const T *__restrict__ in, const T *__restrict__ ker,
     __shared__ int s_flag[2];
     __shared__ __align__(8) uint64_t ring_bar[4];
 
-    const int seg = blockIdx.x % d.nseg;
-    const int plane = blockIdx.x / d.nseg;
+    // Wide rows are cut into column blocks (one CTA each). Block i > 0 starts `halo_thr` threads to
+    // the left of the columns it owns: those threads re-read kernel / grad_output of the left
+    // neighbour's last columns so that every grad_input column a block owns gets all its terms
+    // (1.6 % extra reads at 252 owned columns); they store nothing.
+    const int xb = blockIdx.x % d.nxb;
+    const int seg = (blockIdx.x / d.nxb) % d.nseg;
+    const int plane = blockIdx.x / (d.nxb * d.nseg);
     const int H = d.H, W = d.W, Wi = W + R;
     const int t = threadIdx.x, nthr = blockDim.x;
-    const int x = t * PX;
+    const int xbase = xb * d.xstride;
+    const int x = xbase + t * PX;
     const bool active = x < W;
-    const int nact = ceil_div(W, PX);              // threads that own output columns
+    const bool own = active && (xb == 0 || t >= d.halo_thr);
+    const bool last_xb = (xb == d.nxb - 1);
+    const int nact = min(nthr, ceil_div(W - xbase, PX));   // threads of this block that hold output columns
     const int y0 = seg * d.seg_rows, y1 = min(H, y0 + d.seg_rows);
     const bool wi_vec = (PX == 4) && (Wi % 4 == 0);
 
@@ -197,16 +207,18 @@ fac_bwd_march(const T *__restrict__ in, const T *__restrict__ ker,
 
     // ---- ring of (K*K + 1) x W elements per stage: rows k of `kernel`, then the grad_output row
     T *ring = reinterpret_cast<T *>(dyn_smem + ((2 * blockDim.x * RS + 31) & ~31));
-    const int stage_elts = (K * K + 1) * W;
+    const int bw = nthr * PX;                      // row pitch of a stage = columns a block can hold
+    const int ncols = min(bw, W - xbase);          // columns of this block that exist
+    const int stage_elts = (K * K + 1) * bw;
     auto issue_row = [&](int y) {                  // thread 0: bulk copies of row y into its stage
         const int st = (y - y0) % d.nstage;
         T *dst = ring + (size_t)st * stage_elts;
-        umma::mbar_expect_tx(&ring_bar[st], (uint32_t)(stage_elts * sizeof(T)));
-        const T *src = ker + (size_t)plane * K * K * H * W + (size_t)y * W;
+        umma::mbar_expect_tx(&ring_bar[st], (uint32_t)((K * K + 1) * ncols * sizeof(T)));
+        const T *src = ker + (size_t)plane * K * K * H * W + (size_t)y * W + xbase;
         for (int k = 0; k < K * K; ++k)
-            umma::bulk_g2s(dst + (size_t)k * W, src + (size_t)k * H * W, (uint32_t)(W * sizeof(T)), &ring_bar[st]);
-        umma::bulk_g2s(dst + (size_t)K * K * W, gout + (size_t)plane * H * W + (size_t)y * W,
-                       (uint32_t)(W * sizeof(T)), &ring_bar[st]);
+            umma::bulk_g2s(dst + (size_t)k * bw, src + (size_t)k * H * W, (uint32_t)(ncols * sizeof(T)), &ring_bar[st]);
+        umma::bulk_g2s(dst + (size_t)K * K * bw, gout + (size_t)plane * H * W + (size_t)y * W + xbase,
+                       (uint32_t)(ncols * sizeof(T)), &ring_bar[st]);
     };
     if constexpr (RING) {
         if (t == 0) {
@@ -227,7 +239,7 @@ fac_bwd_march(const T *__restrict__ in, const T *__restrict__ ker,
             for (int j = 0; j < R; ++j) xb[t * RS + j] = row[PX + j];
         }
         __syncthreads();
-        if (active) {
+        if (own) {
             float o[PX];
 #pragma unroll
             for (int j = 0; j < PX; ++j) o[j] = row[j];
@@ -256,9 +268,10 @@ fac_bwd_march(const T *__restrict__ in, const T *__restrict__ ker,
             }
         }
         if constexpr (R > 0) {
-            // right halo columns W .. W+R-1 have no owner thread: the first R threads gather them
-            if (t < R) {
-                const int X = W + t, tv = X / PX, j = X % PX;
+            // right halo columns W .. W+R-1 have no owner thread: the first R threads of the last
+            // column block gather them
+            if (last_xb && t < R) {
+                const int X = W + t, tv = (X - xbase) / PX, j = (X - xbase) % PX;
                 float o = 0.f;
                 for (int dd = 1; dd <= D; ++dd) {
                     const int src = tv - dd, c = j + PX * dd;
@@ -277,8 +290,8 @@ fac_bwd_march(const T *__restrict__ in, const T *__restrict__ ker,
             const int st = (y - y0) % d.nstage;
             umma::mbar_wait(&ring_bar[st], ((y - y0) / d.nstage) & 1);
             if (active) {
-                const T *stg = ring + (size_t)st * stage_elts + x;
-                const Vec<4> gv = Vec<4>::load_smem(stg + (size_t)K * K * W);
+                const T *stg = ring + (size_t)st * stage_elts + t * PX;
+                const Vec<4> gv = Vec<4>::load_smem(stg + (size_t)K * K * bw);
                 const float *g = gv.v;
 #pragma unroll
                 for (int r = 0; r < K - 1; ++r)
@@ -290,7 +303,7 @@ fac_bwd_march(const T *__restrict__ in, const T *__restrict__ ker,
                 for (int ky = 0; ky < K; ++ky)
 #pragma unroll
                     for (int kx = 0; kx < K; ++kx) {
-                        const Vec<4> kq = Vec<4>::load_smem(stg + (size_t)(ky * K + kx) * W);
+                        const Vec<4> kq = Vec<4>::load_smem(stg + (size_t)(ky * K + kx) * bw);
                         const float *kvv = kq.v;
                         Vec<4> gk;
 #pragma unroll
@@ -298,7 +311,7 @@ fac_bwd_march(const T *__restrict__ in, const T *__restrict__ ker,
                             gk.v[i] = win[ky][kx + i] * g[i];
                             acc[ky][kx + i] += kvv[i] * g[i];
                         }
-                        gk.store_stream(gkp + ((size_t)(ky * K + kx) * H + y) * W);
+                        if (own) gk.store_stream(gkp + ((size_t)(ky * K + kx) * H + y) * W);
                     }
             }
         } else if (active) {
@@ -322,7 +335,7 @@ fac_bwd_march(const T *__restrict__ in, const T *__restrict__ ker,
                         gk.v[i] = win[ky][kx + i] * g.v[i];                 // grad_kernel (:149)
                         acc[ky][kx + i] += kv[ky * K + kx].v[i] * g.v[i];   // grad_input scatter (:117-120)
                     }
-                    gk.store_stream(gkp + ((size_t)(ky * K + kx) * H + y) * W);
+                    if (own) gk.store_stream(gkp + ((size_t)(ky * K + kx) * H + y) * W);
                 }
         }
         emit_row(acc[0], gip + (size_t)y * Wi, nullptr, parity);
@@ -347,8 +360,9 @@ fac_bwd_march(const T *__restrict__ in, const T *__restrict__ ker,
         }
         if (d.nseg == 1) return;
 
-        // Hand-off: each boundary between segments s|s+1 has two parties; the second one to
-        // arrive adds the upper segment's overhang rows onto the lower segment's partial rows.
+        // Hand-off: each boundary between segments s|s+1 has 2 * nxb parties (the column blocks above
+        // and below); the last one to arrive adds the upper segment's overhang rows onto the lower
+        // segment's partial rows (always `partial + overhang`, so the result does not depend on who merges).
         __threadfence();
         __syncthreads();
         if (t == 0) {
@@ -358,7 +372,7 @@ fac_bwd_march(const T *__restrict__ in, const T *__restrict__ ker,
         __syncthreads();
 #pragma unroll
         for (int side = 0; side < 2; ++side) {
-            if (s_flag[side] != 1) continue;
+            if (s_flag[side] != 2 * d.nxb - 1) continue;
             __threadfence();
             const int bseg = side == 0 ? seg - 1 : seg;             // upper segment of the boundary
             const int yb = (bseg + 1) * d.seg_rows;                 // first row of the lower segment
@@ -451,10 +465,9 @@ FacPlan make_plan(const void *const *ptrs, int nptr, int planes, int H, int W, i
     const bool k_ok = (K == 1 || K == 3 || K == 5 || K == 7);
     bool al = true;
     for (int i = 0; i < nptr; ++i) al = al && ebfi::aligned16(ptrs[i]);
-    const int max_thr = backward ? 256 : 128;
     // K = 7 at 4 px/thread needs more than 255 registers; it runs on the 1 px/thread variant.
-    if (k_ok && K <= 5 && W % 4 == 0 && al && (!backward || W / 4 <= max_thr)) p.px = 4;
-    else if (k_ok && (!backward || W <= max_thr)) p.px = 1;
+    if (k_ok && K <= 5 && W % 4 == 0 && al) p.px = 4;
+    else if (k_ok) p.px = 1;
     else p.px = 0;
     if (env_int("EBFI_FAC_FORCE_PX", -1) >= 0 && p.px != 0) {
         const int f = env_int("EBFI_FAC_FORCE_PX", -1);
@@ -467,16 +480,31 @@ FacPlan make_plan(const void *const *ptrs, int nptr, int planes, int H, int W, i
     p.d.nseg = ceil_div(H, seg);
     const int cols = ceil_div(W, p.px);
     p.d.nstage = 0;
+    p.d.xstride = 0; p.d.halo_thr = 0;
     if (backward) {
-        p.threads = ebfi::round_up(cols, 32);
-        p.d.nxb = 1;
+        // One CTA per row segment up to 64 threads (256 columns at 4 px/thread: the shape the kernel was
+        // tuned on); wider rows become overlapping column blocks of 64 threads. The overlap covers the
+        // K-1 halo columns, rounded up so that a block's first column stays 16-byte aligned.
+        const int blk_thr = env_int("EBFI_FAC_BLOCK_THREADS", 64);
+        if (cols <= blk_thr) {
+            p.threads = ebfi::round_up(cols, 32);
+            p.d.nxb = 1;
+        } else {
+            const int align_px = std::max(p.px, 16 / esize);                       // columns per 16 bytes
+            const int halo_cols = ebfi::round_up(std::max(K - 1, 1), align_px);
+            p.threads = blk_thr;
+            p.d.halo_thr = ceil_div(halo_cols, p.px);
+            p.d.xstride = blk_thr * p.px - p.d.halo_thr * p.px;
+            p.d.nxb = ceil_div(W - p.d.halo_thr * p.px, p.d.xstride);
+        }
         // ring variant: 2 stages (one row being consumed, one in flight). Measured on B200 at the
         // benchmark shape: 2 stages = 4 CTAs/SM -> 0.600 ms (91 % of HBM peak); 3 or 4 stages = 2 CTAs/SM
         // -> 0.763 ms; register variant 0.687 ms. Resident CTAs matter more than ring depth.
         if (p.px == 4 && (K == 3 || K == 5) && env_int("EBFI_FAC_RING", 1)) {
-            const size_t stage = (size_t)(K * K + 1) * W * esize;
+            const size_t stage = (size_t)(K * K + 1) * p.threads * p.px * esize;
             const int want = env_int("EBFI_FAC_STAGES", 0);
-            const bool rows16 = ((size_t)W * esize) % 16 == 0;     // bulk copies move multiples of 16 bytes
+            // bulk copies move multiples of 16 bytes from 16-byte aligned addresses
+            const bool rows16 = ((size_t)W * esize) % 16 == 0 && ((size_t)p.d.xstride * esize) % 16 == 0;
             if (!rows16) p.d.nstage = 0;
             else if (want >= 2 && want <= 4 && want * stage <= 200 * 1024) p.d.nstage = want;
             else if (2 * stage <= 72 * 1024) p.d.nstage = 2;      // >= 3 CTAs per SM, else the register variant
@@ -510,10 +538,10 @@ int launch_bwd(cudaStream_t st, const FacPlan &p, const T *in, const T *ker,
                const T *gout, T *gin, T *gker, int *counters, float *overhang,
                int planes, int K)
 {
-    const unsigned grid = (unsigned)((size_t)planes * p.d.nseg);
+    const unsigned grid = (unsigned)((size_t)planes * p.d.nseg * p.d.nxb);
     const int RS = K > 1 ? K - 1 : 1;
     const size_t xch = (size_t)((2 * p.threads * RS + 31) & ~31) * sizeof(float);
-    const size_t smem = xch + (size_t)p.d.nstage * (K * K + 1) * p.d.W * sizeof(T);
+    const size_t smem = xch + (size_t)p.d.nstage * (K * K + 1) * p.threads * PX * sizeof(T);
 #define EBFI_FAC_BWD(KK, RING)                                                                              \
     do {                                                                                                    \
         auto kern = fac_bwd_march<KK, PX, RING, T>;                                                            \

@@ -38,7 +38,8 @@ def test_golden_vectors(fac, case):
 # K = 7 and an even-free generic K = 9, one-pixel images, wide rows
 SHAPES = [(2, 3, 5, 40, 64), (1, 2, 5, 33, 20), (1, 2, 5, 50, 23), (2, 2, 3, 37, 36), (1, 3, 3, 9, 7),
           (1, 2, 1, 20, 16), (1, 1, 7, 35, 24), (1, 1, 7, 20, 13), (1, 2, 9, 12, 16), (1, 1, 5, 1, 1),
-          (1, 1, 5, 3, 4), (1, 1, 5, 17, 512), (1, 1, 5, 18, 1100), (1, 1, 3, 40, 300)]
+          (1, 1, 5, 3, 4), (1, 1, 5, 17, 512), (1, 1, 5, 18, 1100), (1, 1, 3, 40, 300),
+          (1, 2, 5, 24, 1280), (1, 1, 5, 20, 257), (1, 1, 3, 33, 70), (1, 1, 5, 36, 260)]   # column blocks + halo
 
 
 @pytest.mark.parametrize("shape", SHAPES)
@@ -145,7 +146,8 @@ BF16_TOL = 2.0 ** -8
 
 
 @pytest.mark.parametrize("shape", [(2, 4, 5, 40, 64), (1, 3, 5, 33, 20), (1, 2, 3, 37, 36), (1, 2, 5, 19, 23),
-                                   (1, 2, 1, 20, 16), (1, 1, 9, 12, 16)])
+                                   (1, 2, 1, 20, 16), (1, 1, 9, 12, 16), (1, 2, 5, 22, 640), (1, 1, 5, 20, 516),
+                                   (1, 1, 3, 18, 300)])
 def test_bf16_variant_against_oracle(fac, oracle, shape):
     from gpu_util import dev
     B, C, K, H, W = shape
