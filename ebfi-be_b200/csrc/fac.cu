@@ -155,7 +155,7 @@ fac_fwd_march(const T *__restrict__ in, const T *__restrict__ ker, T *__restrict
 // issues two rows ahead; bytes in flight then live in shared memory instead of registers (the
 // register variant keeps 25 float4 loads = 100 registers per thread in flight, 8 warps per SM).
 template <int K, int PX, bool RING, typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256)      // (a 128-register cap for more CTAs/SM spills and loses 25 %)
 fac_bwd_march(const T *__restrict__ in, const T *__restrict__ ker,
               const T *__restrict__ gout, T *__restrict__ gin, T *__restrict__ gker,
               int *__restrict__ counters, float *__restrict__ overhang, FacDims d)
