@@ -120,10 +120,12 @@ __global__ void events_voxel_kernel(T *__restrict__ xs, T *__restrict__ ys, cons
 
 // binary_search_torch_tensor (:77-99) for all 2*bins boundaries, one thread each.
 template <typename T>
-__global__ void stack_bounds_kernel(const T *__restrict__ ts, int64_t n, int bins, int64_t *__restrict__ bounds)
+__global__ void stack_bounds_kernel(const T *__restrict__ ts, int64_t n, int bins, int64_t *__restrict__ bounds,
+                                    const unsigned char *__restrict__ skip)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= 2 * bins) return;
+    if (skip && *skip) { bounds[e] = 0; return; }     // empty slices: the scatter kernel adds nothing
     const int bi = e >> 1, right = e & 1;
     // dt = ts[-1]-ts[0]+1e-6; delta = dt/B; tstart = ts[0]+delta*bi; tend = tstart+delta (:324-329),
     // every step rounded in the dtype of ts
@@ -252,8 +254,9 @@ int ebfi_events_to_voxel(void *stream, void *xs, void *ys, const void *ts, const
 
 int ebfi_events_to_stack(void *stream, void *xs, void *ys, const void *ts, const float *ps, int dtype,
                          int64_t n, int num_bins, int height, int width, float *stack, int64_t *bounds,
-                         int write_back)
+                         int write_back, const unsigned char *skip_flag)
 {
+    const unsigned char *skip = skip_flag;
     if (int rc = check_common(xs, ys, dtype, n, height, width)) return rc;
     EBFI_REQUIRE(num_bins > 0 && num_bins <= 2048, "events_to_stack: num_bins must be in [1, 2048]");
     EBFI_REQUIRE(stack && bounds && (n == 0 || (ts && ps)), "events_to_stack: null pointer");
@@ -262,10 +265,10 @@ int ebfi_events_to_stack(void *stream, void *xs, void *ys, const void *ts, const
     const int nb2 = 2 * num_bins;
     const size_t smem = (size_t)nb2 * sizeof(int64_t);
     if (dtype == EBFI_F32) {
-        stack_bounds_kernel<float><<<ceil_div(nb2, 64), 64, 0, st>>>((const float *)ts, n, num_bins, bounds);
+        stack_bounds_kernel<float><<<ceil_div(nb2, 64), 64, 0, st>>>((const float *)ts, n, num_bins, bounds, skip);
         events_stack_kernel<float><<<grid_for(n), 256, smem, st>>>((float *)xs, (float *)ys, ps, n, num_bins, height, width, bounds, stack, write_back);
     } else {
-        stack_bounds_kernel<double><<<ceil_div(nb2, 64), 64, 0, st>>>((const double *)ts, n, num_bins, bounds);
+        stack_bounds_kernel<double><<<ceil_div(nb2, 64), 64, 0, st>>>((const double *)ts, n, num_bins, bounds, skip);
         events_stack_kernel<double><<<grid_for(n), 256, smem, st>>>((double *)xs, (double *)ys, ps, n, num_bins, height, width, bounds, stack, write_back);
     }
     EBFI_LAUNCH_OK("events_stack kernels");

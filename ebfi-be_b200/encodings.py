@@ -94,16 +94,20 @@ def events_to_channels(xs, ys, ps, sensor_size=(180, 240)):
 def events_to_stack(xs, ys, ts, ps, B, sensor_size=(180, 240)):
     """(2, B, H, W) per-bin positive / negative counts (encodings.py:307-350)."""
     H, W = sensor_size
-    if len(ts) <= 3 or ts.sum() == 0:                  # encodings.py:319-320 (one host sync, like the reference)
+    L.require_cuda(ts)
+    if len(ts) <= 3:                                   # encodings.py:319-320
         return torch.zeros([2, B, H, W], device=ts.device)
     assert len(xs) == len(ys) and len(ys) == len(ts) and len(ts) == len(ps)
     dt, (x, y, t) = _prep(xs, ys, ts)
     p = _ps(ps)
     with torch.cuda.device(x.device):
+        # the other half of the reference's early-out, `ts.sum() == 0`, stays on the device: the
+        # kernels read the flag, the host never waits for it
+        skip = (t.sum() == 0).to(torch.uint8)
         stack = torch.zeros((2, B, H, W), dtype=torch.float32, device=x.device)
         bounds = torch.empty(2 * B, dtype=torch.int64, device=x.device)
         L.check(L.load().ebfi_events_to_stack(L.stream_ptr(x.device), L.ptr(x), L.ptr(y), L.ptr(t), L.ptr(p),
-                                              dt, x.numel(), B, H, W, L.ptr(stack), L.ptr(bounds), 1),
+                                              dt, x.numel(), B, H, W, L.ptr(stack), L.ptr(bounds), 1, L.ptr(skip)),
                 "events_to_stack")
     _sync_back(xs, x), _sync_back(ys, y)
     return stack

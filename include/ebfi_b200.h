@@ -174,10 +174,13 @@ int ebfi_events_to_voxel(void *stream, void *xs, void *ys, const void *ts, const
  * adjacent bins exactly like the reference does.
  * stack : (2, num_bins, H, W) fp32, accumulated into (caller zero-fills).
  * bounds : (2*num_bins) int64 scratch, receives [beg_0,end_0,beg_1,end_1,...].
- * The early-out `ts.sum()==0 or len<=3` (:319-320) is the host wrapper's job. */
+ * skip_flag : optional 1-byte DEVICE flag; non-zero makes the call a no-op. It carries the
+ *   reference's early-out `ts.sum() == 0` (:319-320) without a device->host synchronisation
+ *   (the `len <= 3` half is decided on the host). */
 int ebfi_events_to_stack(void *stream, void *xs, void *ys, const void *ts, const float *ps,
                          int dtype, int64_t n_events, int num_bins, int height, int width,
-                         float *stack, int64_t *bounds, int write_back);
+                         float *stack, int64_t *bounds, int write_back,
+                         const unsigned char *skip_flag);
 
 /* ---- self test --------------------------------------------------------------- */
 
