@@ -113,6 +113,8 @@ dcn_bwd_tc_kernel(const float *__restrict__ in_blk, const float *__restrict__ we
     const uint32_t idesc1 = umma::instr_desc_bf16(TM, pl.N1), idesc3 = umma::instr_desc_bf16(d.Co, pl.N3);
     const uint32_t lane_base = (uint32_t)(warp & 3) * 32u;
 
+    const unsigned uplane = (unsigned)plane;
+
     uint32_t ph1 = 0, ph3 = 0;
     int ntiles_done = 0;
     for (int tile = s; tile < d.B * ntile; tile += S, ++ntiles_done) {
@@ -184,6 +186,7 @@ dcn_bwd_tc_kernel(const float *__restrict__ in_blk, const float *__restrict__ we
         for (int sidx = 0; sidx < pl.TPR; ++sidx) {
             const int t = r * pl.TPR + sidx;
             if (t >= d.KK) break;
+            const int ti = t / d.kw, tj = t - ti * d.kw;
             float gc[8];
             umma::tmem_ld8(umma::tmem_addr(tmem, lane_base, t * 8), gc);     // colgrad[p][t*8 .. t*8+7]
             umma::tmem_ld_wait();
@@ -191,8 +194,11 @@ dcn_bwd_tc_kernel(const float *__restrict__ in_blk, const float *__restrict__ we
 #pragma unroll
             for (int j = 0; j < 8; ++j) colv[j] = 0.f;
             if (valid) {
-                float y, x, xq, m;
-                tap_coords(d, off_bg, mask_bg, t, pix, y, x, xq, m);
+                float dy, dx, m;
+                tap_read(off_bg, mask_bg, uplane, (unsigned)t, (unsigned)pix, dy, dx, m);
+                const float y = (float)(ho * d.sh - d.ph + ti * d.dh) + dy;
+                const float x = (float)(wo * d.sw - d.pw + tj * d.dw) + dx;
+                const float xq = (float)(wo * d.sw - d.ph + tj * d.dw) + dx;   // the scatter's x uses pad_h (im2col_cuda.cu:368)
                 const Tap tp = make_tap(y, x, d.H, d.W);
                 const Tap tq = (d.ph == d.pw) ? tp : make_tap(y, xq, d.H, d.W);
                 const float w1 = tp.hy * tp.hx, w2 = tp.hy * tp.lx, w3 = tp.ly * tp.hx, w4 = tp.ly * tp.lx;
@@ -338,6 +344,7 @@ __global__ void blocked_to_nchw(const float *__restrict__ src, float *__restrict
 bool make_plan(const DcnDims &d, BwdPlan &pl)
 {
     if (d.cpg != CS || d.Co != 64) return false;          // other shapes: CUDA-core kernel in dcn.cu
+    if ((long)2 * d.KK * d.Ho * d.Wo >= (1L << 31)) return false;   // 32-bit offsets inside one group
     pl.TPR = ceil_div(d.KK, NR);
     pl.Kc = CS * d.KK;
     pl.N1 = ebfi::round_up(pl.Kc, 16);

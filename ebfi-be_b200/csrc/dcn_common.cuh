@@ -55,6 +55,17 @@ __device__ __forceinline__ void tap_coords(const DcnDims &d, const float *__rest
 }
 
 
+// Division-free read of one tap's (dy, dx, mask) for kernels that already know the pixel index:
+// offset channel 2t = dy, 2t+1 = dx inside the group (im2col_cuda.cu:170-171); plane = Ho * Wo.
+__device__ __forceinline__ void tap_read(const float *__restrict__ off_bg, const float *__restrict__ mask_bg,
+                                         unsigned plane, unsigned t, unsigned pix, float &dy, float &dx, float &m)
+{
+    const unsigned o = 2u * t * plane + pix;
+    dy = __ldg(off_bg + o);
+    dx = __ldg(off_bg + o + plane);
+    m = __ldg(mask_bg + t * plane + pix);
+}
+
 // 256-bit read-only global load (sm_100+: LDG.E.256): the 8 channels of one bilinear corner in the
 // group-blocked layout, one instruction and one L1 wavefront per lane instead of two.
 struct f8 { float v[8]; };

@@ -37,7 +37,8 @@ using ebfi::ceil_div;
 constexpr int TM = 128;          // pixels per CTA tile
 constexpr int TH = 8, TW = 16;   // tile shape
 constexpr int NR = 3;            // thread rows: thread (p, r)
-constexpr int NTHR = TM * NR;    // 384
+constexpr int NSAMP = TM * NR;   // 384 sampler threads
+constexpr int NTHR = NSAMP + 32; // + one controller warp (weight prefetch, MMA issue)
 constexpr int TMEM_COLS = 256;
 
 struct FwdPlan {
@@ -57,145 +58,164 @@ dcn_fwd_tc_kernel(const float *__restrict__ in_blk,
                   const float *__restrict__ wimg, DcnDims d, FwdPlan pl)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char *opnd = smem_raw;                                        // [2 buffers][a_hi, a_lo, b_hi, b_lo]
-    const int buf_bytes = 2 * pl.a_bytes + 2 * pl.b_bytes;
-    __shared__ __align__(8) uint64_t bar[2];        // MMAs that read stage buffer i are complete
-    __shared__ __align__(8) uint64_t bar_w[2];      // weight image of stage buffer i has landed
+    unsigned char *opnd = smem_raw;                                        // [2 buffers][a_hi | a_lo]
+    unsigned char *wring = smem_raw + 4 * pl.a_bytes;                      // [4 slots][b_hi | b_lo], filled two stages ahead
+    __shared__ __align__(8) uint64_t bar_free[2];   // MMAs that read A buffer i are complete (tcgen05.commit)
+    __shared__ __align__(8) uint64_t bar_full[2];   // all 12 sampler warps have written A buffer i
+    __shared__ __align__(8) uint64_t bar_w[4];      // weight image in ring slot i has landed
     __shared__ uint32_t tmem_slot;
 
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int p = tid % TM, r = tid / TM;
-    int tile = blockIdx.x;
-    const int tx0 = (tile % pl.tiles_x) * TW; tile /= pl.tiles_x;
-    const int ty0 = (tile % pl.tiles_y) * TH;
-    const int b = tile / pl.tiles_y;
-    const int ho = ty0 + p / TW, wo = tx0 + p % TW;
-    const bool valid = ho < d.Ho && wo < d.Wo;
-    const int pix = ho * d.Wo + wo;
-    const size_t plane = (size_t)d.Ho * d.Wo, in_plane = (size_t)d.H * d.W;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int total_stages = d.dg * pl.ncs * pl.TPR;
     const uint32_t sbo = (uint32_t)pl.kch * 128u;
 
     if (warp == 0) umma::tmem_alloc<TMEM_COLS>(&tmem_slot);
     if (tid == 0) {
-        umma::mbar_init(&bar[0], 1); umma::mbar_init(&bar[1], 1);
-        umma::mbar_init(&bar_w[0], 1); umma::mbar_init(&bar_w[1], 1);
+        for (int i = 0; i < 2; ++i) { umma::mbar_init(&bar_free[i], 1); umma::mbar_init(&bar_full[i], NSAMP / 32); }
+        for (int i = 0; i < 4; ++i) umma::mbar_init(&bar_w[i], 1);
         umma::mbar_fence_init();
     }
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tmem = tmem_slot;
-    const uint32_t idesc = umma::instr_desc_tf32(TM, d.Co, 0, 0);
 
-    const int a_row = (p >> 3) * (pl.kch * 32) + (p & 7) * 4;             // floats, row of pixel p in an A image
-    uint32_t phase[2] = {0, 0}, phase_w[2] = {0, 0};
-    int nstage = 0;                                                        // stages issued so far (all threads)
-    int step = 0;                                                          // MMA k-steps issued (thread 0)
-
-    for (int g = 0; g < d.dg; ++g) {
-        const float *off_bg = offset + ((size_t)b * d.dg + g) * 2 * d.KK * plane;
-        const float *mask_bg = mask + ((size_t)b * d.dg + g) * d.KK * plane;
-        // ---- sampling positions of this thread's taps (offset / mask read once per (pixel, tap, group))
-        float sy[4], sx[4], sm[4];                                         // TPR <= 4 (see make_plan)
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            sy[s] = -2.f; sx[s] = -2.f; sm[s] = 0.f;                       // (-2,-2): outside the window
-            const int t = r * pl.TPR + s;
-            if (s < pl.TPR && valid && t < d.KK) {
-                float xq;
-                tap_coords(d, off_bg, mask_bg, t, pix, sy[s], sx[s], xq, sm[s]);
+    if (warp == NSAMP / 32) {
+        // ================= controller warp: weight prefetch + MMA issue, one elected lane =================
+        // Keeping this off the sampler warps takes the serial issue of 9 MMAs + descriptors per stage out
+        // of their critical path (with it on thread 0, a stage cost T_sample + T_issue; now max of the two).
+        if (lane == 0) {
+            const uint32_t idesc = umma::instr_desc_tf32(TM, d.Co, 0, 0);
+            const uint32_t wb = 2u * (uint32_t)pl.b_bytes;
+            int step = 0;
+            for (int n = 0; n < total_stages; ++n) {
+                const int bi = n & 1;
+                if (n == 0) {
+                    for (int ns = 0; ns < 3 && ns < total_stages; ++ns) {
+                        umma::mbar_expect_tx(&bar_w[ns & 3], wb);
+                        umma::bulk_g2s(wring + (ns & 3) * wb, wimg + (size_t)ns * (wb / 4), wb, &bar_w[ns & 3]);
+                    }
+                } else if (n + 2 < total_stages) {
+                    // ring slot (n+2) & 3 was read by stage n-2: wait for its MMAs, then refill it
+                    if (n >= 2) umma::mbar_wait(&bar_free[bi], (uint32_t)(((n - 2) >> 1) & 1));
+                    const int ns = n + 2;
+                    umma::mbar_expect_tx(&bar_w[ns & 3], wb);
+                    umma::bulk_g2s(wring + (ns & 3) * wb, wimg + (size_t)ns * (wb / 4), wb, &bar_w[ns & 3]);
+                }
+                umma::mbar_wait(&bar_w[n & 3], (uint32_t)((n >> 2) & 1));
+                umma::mbar_wait(&bar_full[bi], (uint32_t)((n >> 1) & 1));
+                umma::fence_after_sync();
+                const uint32_t ah = umma::smem_u32(opnd + bi * 2 * pl.a_bytes), al = ah + (uint32_t)pl.a_bytes;
+                const uint32_t bh = umma::smem_u32(wring + (n & 3) * wb), bl = bh + (uint32_t)pl.b_bytes;
+                for (int ks = 0; ks < pl.Ksp / 8; ++ks, ++step) {
+                    const uint32_t ko = (uint32_t)ks * 256u;
+                    const uint64_t dah = umma::smem_desc(ah + ko, 128, sbo), dal = umma::smem_desc(al + ko, 128, sbo);
+                    const uint64_t dbh = umma::smem_desc(bh + ko, 128, sbo), dbl = umma::smem_desc(bl + ko, 128, sbo);
+                    const uint32_t d_x = tmem + pl.nacc * d.Co, d_h = tmem + (step % pl.nacc) * d.Co;
+                    umma::mma_tf32(d_x, dal, dbh, idesc, step > 0);
+                    umma::mma_tf32(d_x, dah, dbl, idesc, true);
+                    umma::mma_tf32(d_h, dah, dbh, idesc, step >= pl.nacc);
+                }
+                umma::commit(&bar_free[bi]);
             }
         }
-        for (int ci = 0; ci < pl.ncs; ++ci) {
-            // blocked input of this chunk: [y][x][8 channels] as float4 pairs
-            const float4 *ib = reinterpret_cast<const float4 *>(in_blk + (((size_t)b * d.dg + g) * pl.ncs + ci) * in_plane * 8);
-            for (int s = 0; s < pl.TPR; ++s, ++nstage) {
-                const int bi = nstage & 1;
-                float *a_hi = reinterpret_cast<float *>(opnd + bi * buf_bytes);
-                float *a_lo = reinterpret_cast<float *>(opnd + bi * buf_bytes + pl.a_bytes);
-                float *b_hi = reinterpret_cast<float *>(opnd + bi * buf_bytes + 2 * pl.a_bytes);
-                float *b_lo = reinterpret_cast<float *>(opnd + bi * buf_bytes + 2 * pl.a_bytes + pl.b_bytes);
-                if (nstage >= 2) {                                         // MMAs that read this buffer are done
-                    umma::mbar_wait(&bar[bi], phase[bi]);
-                    phase[bi] ^= 1;
+    } else {
+        // ================= sampler warps: thread (pixel p, row r) =================
+        const int p = tid % TM, r = tid / TM;
+        int tile = blockIdx.x;
+        const int tx0 = (tile % pl.tiles_x) * TW; tile /= pl.tiles_x;
+        const int ty0 = (tile % pl.tiles_y) * TH;
+        const int b = tile / pl.tiles_y;
+        const int ho = ty0 + p / TW, wo = tx0 + p % TW;
+        const bool valid = ho < d.Ho && wo < d.Wo;
+        const int pix = ho * d.Wo + wo;
+        const size_t plane = (size_t)d.Ho * d.Wo, in_plane = (size_t)d.H * d.W;
+        const int a_row = (p >> 3) * (pl.kch * 32) + (p & 7) * 4;         // floats, row of pixel p in an A image
+        const unsigned uplane = (unsigned)plane, upix = (unsigned)pix;
+
+        // undeformed sampling positions of this thread's taps (group independent): no divisions in the loops
+        float by[4], bx[4];                                                // TPR <= 4 (see make_plan)
+        bool tv[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const int t = r * pl.TPR + s, i = t / d.kw, j = t - i * d.kw;
+            tv[s] = s < pl.TPR && valid && t < d.KK;
+            by[s] = (float)(ho * d.sh - d.ph + i * d.dh);
+            bx[s] = (float)(wo * d.sw - d.pw + j * d.dw);
+        }
+
+        int n = 0;
+        for (int g = 0; g < d.dg; ++g) {
+            const float *off_bg = offset + ((size_t)b * d.dg + g) * 2 * d.KK * plane;
+            const float *mask_bg = mask + ((size_t)b * d.dg + g) * d.KK * plane;
+            // sampling positions of this thread's taps (offset / mask read once per (pixel, tap, group))
+            float sy[4], sx[4], sm[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                sy[s] = -2.f; sx[s] = -2.f; sm[s] = 0.f;                   // (-2,-2): outside the window
+                if (tv[s]) {
+                    float dy, dx;
+                    tap_read(off_bg, mask_bg, uplane, (unsigned)(r * pl.TPR + s), upix, dy, dx, sm[s]);
+                    sy[s] = by[s] + dy; sx[s] = bx[s] + dx;
                 }
-                // ---- weights of the stage: one bulk (TMA) copy of the pre-split hi|lo image that
-                //      dcn_prep_weights wrote in exactly this shared-memory order
-                if (tid == 0) {
-                    const int img = ((g * pl.ncs + ci) * pl.TPR + s);
-                    umma::mbar_expect_tx(&bar_w[bi], 2u * (uint32_t)pl.b_bytes);
-                    umma::bulk_g2s(b_hi, wimg + (size_t)img * (2 * pl.b_bytes / 4), 2u * (uint32_t)pl.b_bytes, &bar_w[bi]);
-                }
-                // ---- this thread's tap of the stage -> cs values of row p, columns r*cs .. r*cs+cs-1
-                {
+            }
+            for (int ci = 0; ci < pl.ncs; ++ci) {
+                // blocked input of this chunk: [y][x][8 channels]
+                const float *ibf = in_blk + (((size_t)b * d.dg + g) * pl.ncs + ci) * in_plane * 8;
+                for (int s = 0; s < pl.TPR; ++s, ++n) {
+                    const int bi = n & 1;
+                    float *a_hi = reinterpret_cast<float *>(opnd + bi * 2 * pl.a_bytes);
+                    float *a_lo = reinterpret_cast<float *>(opnd + bi * 2 * pl.a_bytes + pl.a_bytes);
+                    // this thread's tap of the stage -> 8 values of row p, columns r*8 .. r*8+7
                     const float y = s == 0 ? sy[0] : s == 1 ? sy[1] : s == 2 ? sy[2] : sy[3];
                     const float x = s == 0 ? sx[0] : s == 1 ? sx[1] : s == 2 ? sx[2] : sx[3];
                     const float m = s == 0 ? sm[0] : s == 1 ? sm[1] : s == 2 ? sm[2] : sm[3];
                     const Tap tp = make_tap(y, x, d.H, d.W);
                     const float w1 = tp.hy * tp.hx, w2 = tp.hy * tp.lx, w3 = tp.ly * tp.hx, w4 = tp.ly * tp.lx;
-                    {
-                        const float *ibf = reinterpret_cast<const float *>(ib);
-                        const f8 a = ldg_f8(ibf + (size_t)tp.i00 * 8, tp.c00), bq = ldg_f8(ibf + (size_t)tp.i01 * 8, tp.c01);
-                        const f8 c = ldg_f8(ibf + (size_t)tp.i10 * 8, tp.c10), e8 = ldg_f8(ibf + (size_t)tp.i11 * 8, tp.c11);
-                        float hi[8], lo[8];
+                    const f8 a = ldg_f8(ibf + (size_t)tp.i00 * 8, tp.c00), bq = ldg_f8(ibf + (size_t)tp.i01 * 8, tp.c01);
+                    const f8 c = ldg_f8(ibf + (size_t)tp.i10 * 8, tp.c10), e8 = ldg_f8(ibf + (size_t)tp.i11 * 8, tp.c11);
+                    float hi[8], lo[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            umma::split_tf32((w1 * a.v[j] + w2 * bq.v[j] + w3 * c.v[j] + w4 * e8.v[j]) * m, hi[j], lo[j]);
-                        const int off = a_row + ((r * pl.cs) >> 2) * 32;
-                        *reinterpret_cast<float4 *>(a_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                        *reinterpret_cast<float4 *>(a_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                        *reinterpret_cast<float4 *>(a_hi + off + 32) = make_float4(hi[4], hi[5], hi[6], hi[7]);
-                        *reinterpret_cast<float4 *>(a_lo + off + 32) = make_float4(lo[4], lo[5], lo[6], lo[7]);
-                    }
+                    for (int j = 0; j < 8; ++j)
+                        umma::split_tf32((w1 * a.v[j] + w2 * bq.v[j] + w3 * c.v[j] + w4 * e8.v[j]) * m, hi[j], lo[j]);
+                    if (n >= 2) umma::mbar_wait(&bar_free[bi], (uint32_t)(((n - 2) >> 1) & 1));   // MMAs of stage n-2 done
+                    const int off = a_row + ((r * pl.cs) >> 2) * 32;
+                    *reinterpret_cast<float4 *>(a_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<float4 *>(a_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    *reinterpret_cast<float4 *>(a_hi + off + 32) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+                    *reinterpret_cast<float4 *>(a_lo + off + 32) = make_float4(lo[4], lo[5], lo[6], lo[7]);
                     if (r == 0 && pl.Ksp > pl.Ks) {                        // zero the K padding of this row
-                        const int off = a_row + (pl.Ks >> 2) * 32;
-                        *reinterpret_cast<float4 *>(a_hi + off) = make_float4(0.f, 0.f, 0.f, 0.f);
-                        *reinterpret_cast<float4 *>(a_lo + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+                        const int offp = a_row + (pl.Ks >> 2) * 32;
+                        *reinterpret_cast<float4 *>(a_hi + offp) = make_float4(0.f, 0.f, 0.f, 0.f);
+                        *reinterpret_cast<float4 *>(a_lo + offp) = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
-                }
-                umma::fence_smem_to_async();
-                __syncthreads();
-                if (tid == 0) {
-                    umma::mbar_wait(&bar_w[bi], phase_w[bi]);
-                    phase_w[bi] ^= 1;
-                    umma::fence_after_sync();
-                    const uint32_t ah = umma::smem_u32(a_hi), al = umma::smem_u32(a_lo);
-                    const uint32_t bh = umma::smem_u32(b_hi), bl = umma::smem_u32(b_lo);
-                    for (int ks = 0; ks < pl.Ksp / 8; ++ks, ++step) {
-                        const uint32_t ko = (uint32_t)ks * 256u;
-                        const uint64_t dah = umma::smem_desc(ah + ko, 128, sbo), dal = umma::smem_desc(al + ko, 128, sbo);
-                        const uint64_t dbh = umma::smem_desc(bh + ko, 128, sbo), dbl = umma::smem_desc(bl + ko, 128, sbo);
-                        const uint32_t d_x = tmem + pl.nacc * d.Co, d_h = tmem + (step % pl.nacc) * d.Co;
-                        umma::mma_tf32(d_x, dal, dbh, idesc, step > 0);
-                        umma::mma_tf32(d_x, dah, dbl, idesc, true);
-                        umma::mma_tf32(d_h, dah, dbh, idesc, step >= pl.nacc);
-                    }
-                    umma::commit(&bar[bi]);
+                    umma::fence_smem_to_async();
+                    __syncwarp();
+                    if (lane == 0) umma::mbar_arrive(&bar_full[bi]);
                 }
             }
         }
-    }
-    // ---- drain: the last commit on each buffer has not been waited for yet
-    if (nstage >= 2) umma::mbar_wait(&bar[nstage & 1], phase[nstage & 1]);
-    umma::mbar_wait(&bar[(nstage - 1) & 1], phase[(nstage - 1) & 1]);
-    umma::fence_after_sync();
+        // ---- all MMAs complete (commits complete in order: the last one covers everything)
+        umma::mbar_wait(&bar_free[(n - 1) & 1], (uint32_t)(((n - 1) >> 1) & 1));
+        umma::fence_after_sync();
 
-    // ---- epilogue: thread (p, r) takes every NR-th block of 8 output channels of pixel p
-    const int total_steps = nstage * (pl.Ksp / 8), nused = min(pl.nacc, total_steps);
-    const uint32_t lane_base = (uint32_t)(warp & 3) * 32u;
-    for (int cb = r * 8; cb < d.Co; cb += NR * 8) {
-        float v[8], u[8];
-        umma::tmem_ld8(umma::tmem_addr(tmem, lane_base, pl.nacc * d.Co + cb), v);
-        umma::tmem_ld_wait();
-        for (int j = 0; j < nused; ++j) {
-            umma::tmem_ld8(umma::tmem_addr(tmem, lane_base, j * d.Co + cb), u);
+        // ---- epilogue: thread (p, r) takes every NR-th block of 8 output channels of pixel p
+        const int total_steps = n * (pl.Ksp / 8), nused = min(pl.nacc, total_steps);
+        const uint32_t lane_base = (uint32_t)(warp & 3) * 32u;
+        for (int cb = r * 8; cb < d.Co; cb += NR * 8) {
+            float v[8], u[8];
+            umma::tmem_ld8(umma::tmem_addr(tmem, lane_base, pl.nacc * d.Co + cb), v);
             umma::tmem_ld_wait();
+            for (int j = 0; j < nused; ++j) {
+                umma::tmem_ld8(umma::tmem_addr(tmem, lane_base, j * d.Co + cb), u);
+                umma::tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] += u[i];
-        }
-        if (valid) {
+                for (int i = 0; i < 8; ++i) v[i] += u[i];
+            }
+            if (valid) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) output[((size_t)b * d.Co + cb + i) * plane + pix] = v[i] + __ldg(bias + cb + i);
+                for (int i = 0; i < 8; ++i) output[((size_t)b * d.Co + cb + i) * plane + pix] = v[i] + __ldg(bias + cb + i);
+            }
         }
     }
     umma::fence_before_sync();
@@ -230,6 +250,7 @@ __global__ void dcn_prep_weights(const float *__restrict__ weight, float *__rest
 bool make_plan(const DcnDims &d, FwdPlan &pl)
 {
     if (d.Co % 16 != 0 || d.Co > 128 || d.cpg % 8 != 0) return false;   // blocked layout: 8-channel chunks
+    if ((long)2 * d.KK * d.Ho * d.Wo >= (1L << 31)) return false;        // 32-bit offsets inside one group
     pl.nacc = std::min(3, TMEM_COLS / d.Co - 1);
     if (pl.nacc < 1) return false;
     pl.TPR = ceil_div(d.KK, NR);
@@ -243,7 +264,7 @@ bool make_plan(const DcnDims &d, FwdPlan &pl)
     pl.b_bytes = d.Co * pl.Ksp * 4;
     pl.tiles_x = ceil_div(d.Wo, TW);
     pl.tiles_y = ceil_div(d.Ho, TH);
-    pl.smem = 2 * (2 * pl.a_bytes + 2 * pl.b_bytes);
+    pl.smem = 4 * pl.a_bytes + 8 * pl.b_bytes;                // 2 A buffers (hi, lo) + 4 weight slots (hi | lo)
     return pl.smem <= 110 * 1024;
 }
 
