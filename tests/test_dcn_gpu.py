@@ -189,3 +189,23 @@ def test_full_size_properties(dcn):
     assert abs(a - dot(ts[3].grad, w)) <= 1e-4 * abs(a)
     assert abs(a - dot(ts[2].grad, msk)) <= 1e-4 * abs(a)          # linear in mask, too
     assert rel_err(ts[4].grad.cpu().numpy(), go.double().sum((0, 2, 3)).cpu().numpy()) < GRAD_TOL
+
+
+def test_reference_gradcheck_recipe(dcn):
+    """check_gradient_dconv of the reference (testcuda.py:69-97): torch.autograd.gradcheck on dcn_v2_conv in
+    fp32 with eps=1e-3, atol=1e-4, rtol=1e-2, N=2, C=2, 4x4, dg=1, input rand*0.01, offset ~ randn*2,
+    mask sigmoid(rand). Bilinear sampling is only piecewise differentiable, so (unlike the reference's
+    script, which just prints the verdict) the fractional parts of the offsets are kept in [0.2, 0.8]:
+    no sample sits within eps of a pixel boundary. grad_input uses fp32 reductions whose order is not
+    fixed -> nondet_tol."""
+    from gpu_util import dev
+    torch.manual_seed(0)
+    N, inC, outC, inH, inW, kH, kW, dg = 2, 2, 2, 4, 4, 3, 3, 1
+    input = (torch.rand(N, inC, inH, inW, device=dev()) * 0.01).requires_grad_()
+    offset = torch.randn(N, dg * 2 * kW * kH, inH, inW, device=dev()) * 2
+    offset = (offset.floor() + 0.2 + 0.6 * torch.rand_like(offset)).requires_grad_()
+    mask = torch.sigmoid(torch.rand(N, dg * kW * kH, inH, inW, device=dev())).detach().requires_grad_()
+    weight = torch.randn(outC, inC, kH, kW, device=dev()).requires_grad_()
+    bias = torch.rand(outC, device=dev()).requires_grad_()
+    assert torch.autograd.gradcheck(dcn.dcn_v2_conv, (input, offset, mask, weight, bias, 1, 1, 1, dg),
+                                    eps=1e-3, atol=1e-4, rtol=1e-2, nondet_tol=1e-5)

@@ -185,3 +185,20 @@ def test_bf16_full_size_is_reproducible_and_close_to_fp32(fac):
     of.backward(go.float())
     for got, want in zip(res[0], (of.detach(), xf.grad, kf.grad)):
         assert float((got.float() - want).abs().max()) <= BF16_TOL * float(want.abs().max())
+
+
+def test_reference_gradient_check_recipe(fac):
+    """gradient_check of the reference (KernelConv2D.py:61-74), re-expressed for the static Function API:
+    10 rounds, B in [1,4], C = 1..10, K in {1,3}, H, W in {8,10}; the op is bilinear, hence eps=1e-1,
+    atol=1e-5, rtol=1e-3."""
+    import random
+    from gpu_util import dev
+    random.seed(0)
+    torch.manual_seed(0)
+    for i in range(10):
+        B, C = random.randint(1, 4), i + 1
+        K, H, W = random.choice([1, 3]), random.choice([8, 10]), random.choice([8, 10])
+        input = torch.randn(B, C, H + K - 1, W + K - 1, device=dev(), dtype=torch.float32).requires_grad_()
+        kernel = torch.randn(B, C * K * K, H, W, device=dev(), dtype=torch.float32).requires_grad_()
+        fn = lambda a, b: fac.KernelConv2DFunction.apply(a, b, K)
+        assert torch.autograd.gradcheck(fn, (input, kernel), eps=1e-1, atol=1e-5, rtol=1e-3)
