@@ -44,7 +44,19 @@ def _check_cuda(**named):
     for k, t in named.items():
         if not t.is_cuda:
             raise RuntimeError(f"{k} must be a CUDA tensor")   # AT_ASSERTM, dcn_v2_cuda.cu:38-42
-    L.require_f32(**named)
+    dts = {t.dtype for t in named.values()}
+    if dts != {torch.float32} and dts != {torch.bfloat16}:
+        raise RuntimeError("dcn_v2: all tensors must be float32 (the reference's `using scalar_t = float`) or all "
+                           f"bfloat16, got {sorted(str(d) for d in dts)}")
+    return next(iter(dts))
+
+
+def _bf16_via_fp32(fn, tensors, ints):
+    """bfloat16 tensors (new; the reference is fp32-only): the DCN kernels compute in fp32 on the exactly
+    converted values, results are rounded once to bf16. The conversion happens at this boundary (extra
+    elementwise passes), unlike FAC, whose kernels read and write bf16 directly."""
+    out = fn(*(t.float() for t in tensors), *ints)
+    return out.bfloat16() if torch.is_tensor(out) else [o.bfloat16() for o in out]
 
 
 def _check_offset_mask(g, ho, wo, offset, mask):
@@ -59,7 +71,9 @@ def _check_offset_mask(g, ho, wo, offset, mask):
 def dcn_v2_forward(input, weight, bias, offset, mask, kernel_h, kernel_w, stride_h, stride_w,
                    pad_h, pad_w, dilation_h, dilation_w, deformable_group):
     """dcn_v2_cuda_forward (src/cuda/dcn_v2_cuda.cu:20-95). Returns a new (B, Cout, Ho, Wo) tensor."""
-    _check_cuda(input=input, weight=weight, bias=bias, offset=offset, mask=mask)
+    if _check_cuda(input=input, weight=weight, bias=bias, offset=offset, mask=mask) == torch.bfloat16:
+        return _bf16_via_fp32(dcn_v2_forward, (input, weight, bias, offset, mask),
+                              (kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w, deformable_group))
     g, ho, wo = _geom(input, weight, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w,
                       dilation_h, dilation_w, deformable_group)
     _check_offset_mask(g, ho, wo, offset, mask)
@@ -84,7 +98,10 @@ def dcn_v2_backward(input, weight, bias, offset, mask, grad_output, kernel_h, ke
         raise RuntimeError("input tensor has to be contiguous")
     if not weight.is_contiguous():
         raise RuntimeError("weight tensor has to be contiguous")
-    _check_cuda(input=input, weight=weight, bias=bias, offset=offset, mask=mask, grad_output=grad_output)
+    if _check_cuda(input=input, weight=weight, bias=bias, offset=offset, mask=mask,
+                   grad_output=grad_output) == torch.bfloat16:
+        return _bf16_via_fp32(dcn_v2_backward, (input, weight, bias, offset, mask, grad_output),
+                              (kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w, deformable_group))
     g, ho, wo = _geom(input, weight, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w,
                       dilation_h, dilation_w, deformable_group)
     _check_offset_mask(g, ho, wo, offset, mask)

@@ -209,3 +209,24 @@ def test_reference_gradcheck_recipe(dcn):
     bias = torch.rand(outC, device=dev()).requires_grad_()
     assert torch.autograd.gradcheck(dcn.dcn_v2_conv, (input, offset, mask, weight, bias, 1, 1, 1, dg),
                                     eps=1e-3, atol=1e-4, rtol=1e-2, nondet_tol=1e-5)
+
+
+def test_bf16_tensors_stated_tolerance(dcn, oracle):
+    """bf16 at the boundary (new capability): fp32 arithmetic on the exactly converted values, one rounding
+    to bf16 per result -> |err| <= 2^-8 * max|ref| per tensor against the oracle run on the same bf16 inputs."""
+    from gpu_util import dev
+    torch.manual_seed(3)
+    B, C, Co, H, W, dg = 1, 64, 64, 20, 24, 8
+    mk = lambda *s: torch.randn(*s).bfloat16()
+    x, off, msk = mk(B, C, H, W), (2 * torch.randn(B, 2 * dg * 9, H, W)).bfloat16(), torch.sigmoid(torch.randn(B, dg * 9, H, W)).bfloat16()
+    w, b, go = (torch.randn(Co, C, 3, 3) / 24).bfloat16(), mk(Co), mk(B, Co, H, W)
+    ts = [t.to(dev()).requires_grad_() for t in (x, off, msk, w, b)]
+    out = dcn.dcn_v2_conv(*ts, 1, 1, 1, dg)
+    assert out.dtype == torch.bfloat16
+    out.backward(go.to(dev()))
+    f = lambda t: t.float().numpy()
+    tol = 2.0 ** -8
+    assert rel_err(out.detach().float().cpu().numpy(), oracle.dcn_forward(f(x), f(off), f(msk), f(w), f(b), 1, 1, 1, dg)) < tol
+    want = oracle.dcn_backward(f(x), f(off), f(msk), f(w), f(b), f(go), 1, 1, 1, dg)
+    for name, t, r in zip(GRADS, ts, want):
+        assert rel_err(t.grad.float().cpu().numpy(), r) < tol, name
