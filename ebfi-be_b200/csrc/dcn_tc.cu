@@ -51,6 +51,7 @@ struct FwdPlan {
 };
 
 
+template <int TPR>
 __global__ void __launch_bounds__(NTHR, 2)
 dcn_fwd_tc_kernel(const float *__restrict__ in_blk,
                   const float *__restrict__ bias, const float *__restrict__ offset,
@@ -66,7 +67,7 @@ dcn_fwd_tc_kernel(const float *__restrict__ in_blk,
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int total_stages = d.dg * pl.ncs * pl.TPR;
+    const int total_stages = d.dg * pl.ncs * TPR;
     const uint32_t sbo = (uint32_t)pl.kch * 128u;
 
     if (warp == 0) umma::tmem_alloc<TMEM_COLS>(&tmem_slot);
@@ -133,43 +134,54 @@ dcn_fwd_tc_kernel(const float *__restrict__ in_blk,
         const int a_row = (p >> 3) * (pl.kch * 32) + (p & 7) * 4;         // floats, row of pixel p in an A image
         const unsigned uplane = (unsigned)plane, upix = (unsigned)pix;
 
-        // undeformed sampling positions of this thread's taps (group independent): no divisions in the loops
-        float by[4], bx[4];                                                // TPR <= 4 (see make_plan)
-        bool tv[4];
+        // undeformed sampling positions of this thread's TPR taps (group independent: no divisions in the loops)
+        float by[TPR], bx[TPR];
+        bool tv[TPR];
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            const int t = r * pl.TPR + s, i = t / d.kw, j = t - i * d.kw;
-            tv[s] = s < pl.TPR && valid && t < d.KK;
+        for (int s = 0; s < TPR; ++s) {
+            const int t = r * TPR + s, i = t / d.kw, j = t - i * d.kw;
+            tv[s] = valid && t < d.KK;
             by[s] = (float)(ho * d.sh - d.ph + i * d.dh);
             bx[s] = (float)(wo * d.sw - d.pw + j * d.dw);
         }
+        // Offsets / masks are read exactly once, i.e. every read misses to DRAM (~4 k cycles with the
+        // dependent corner loads behind it): they are fetched one deformable group AHEAD into registers.
+        float ndy[TPR], ndx[TPR], nm[TPR];
+        auto fetch_group = [&](int g) {
+            const float *off_bg = offset + ((size_t)b * d.dg + g) * 2 * d.KK * plane;
+            const float *mask_bg = mask + ((size_t)b * d.dg + g) * d.KK * plane;
+#pragma unroll
+            for (int s = 0; s < TPR; ++s) {
+                ndy[s] = 0.f; ndx[s] = 0.f; nm[s] = 0.f;
+                if (tv[s]) tap_read(off_bg, mask_bg, uplane, (unsigned)(r * TPR + s), upix, ndy[s], ndx[s], nm[s]);
+            }
+        };
+        fetch_group(0);
 
         int n = 0;
         for (int g = 0; g < d.dg; ++g) {
-            const float *off_bg = offset + ((size_t)b * d.dg + g) * 2 * d.KK * plane;
-            const float *mask_bg = mask + ((size_t)b * d.dg + g) * d.KK * plane;
-            // sampling positions of this thread's taps (offset / mask read once per (pixel, tap, group))
-            float sy[4], sx[4], sm[4];
+            // sampling positions of this group's taps; (-2,-2) = outside the window
+            float sy[TPR], sx[TPR], sm[TPR];
 #pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                sy[s] = -2.f; sx[s] = -2.f; sm[s] = 0.f;                   // (-2,-2): outside the window
-                if (tv[s]) {
-                    float dy, dx;
-                    tap_read(off_bg, mask_bg, uplane, (unsigned)(r * pl.TPR + s), upix, dy, dx, sm[s]);
-                    sy[s] = by[s] + dy; sx[s] = bx[s] + dx;
-                }
+            for (int s = 0; s < TPR; ++s) {
+                sy[s] = tv[s] ? by[s] + ndy[s] : -2.f;
+                sx[s] = tv[s] ? bx[s] + ndx[s] : -2.f;
+                sm[s] = nm[s];
             }
+            if (g + 1 < d.dg) fetch_group(g + 1);
             for (int ci = 0; ci < pl.ncs; ++ci) {
                 // blocked input of this chunk: [y][x][8 channels]
                 const float *ibf = in_blk + (((size_t)b * d.dg + g) * pl.ncs + ci) * in_plane * 8;
-                for (int s = 0; s < pl.TPR; ++s, ++n) {
+#pragma unroll 1
+                for (int s = 0; s < TPR; ++s, ++n) {
                     const int bi = n & 1;
                     float *a_hi = reinterpret_cast<float *>(opnd + bi * 2 * pl.a_bytes);
                     float *a_lo = reinterpret_cast<float *>(opnd + bi * 2 * pl.a_bytes + pl.a_bytes);
                     // this thread's tap of the stage -> 8 values of row p, columns r*8 .. r*8+7
-                    const float y = s == 0 ? sy[0] : s == 1 ? sy[1] : s == 2 ? sy[2] : sy[3];
-                    const float x = s == 0 ? sx[0] : s == 1 ? sx[1] : s == 2 ? sx[2] : sx[3];
-                    const float m = s == 0 ? sm[0] : s == 1 ? sm[1] : s == 2 ? sm[2] : sm[3];
+                    float y = sy[0], x = sx[0], m = sm[0];               // register select, no local-memory indexing
+#pragma unroll
+                    for (int q = 1; q < TPR; ++q)
+                        if (s == q) { y = sy[q]; x = sx[q]; m = sm[q]; }
                     const Tap tp = make_tap(y, x, d.H, d.W);
                     const float w1 = tp.hy * tp.hx, w2 = tp.hy * tp.lx, w3 = tp.ly * tp.hx, w4 = tp.ly * tp.lx;
                     const f8 a = ldg_f8(ibf + (size_t)tp.i00 * 8, tp.c00), bq = ldg_f8(ibf + (size_t)tp.i01 * 8, tp.c01);
@@ -291,9 +303,19 @@ int forward_tc(cudaStream_t st, const DcnDims &d, const float *input, const floa
     dcn_prep_weights<<<ceil_div((int)(wbytes / 8), 256), 256, 0, st>>>(weight, wimg, d, pl);
     EBFI_LAUNCH_OK("dcn_prep_weights");
     if (int rc = launch_nchw_to_blocked(st, input, in_blk, d.B * d.C / 8, d.H * d.W)) return rc;
-    EBFI_CUDA_OK(cudaFuncSetAttribute(dcn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
     const unsigned grid = (unsigned)(d.B * pl.tiles_x * pl.tiles_y);
-    dcn_fwd_tc_kernel<<<grid, NTHR, pl.smem, st>>>(in_blk, bias, offset, mask, output, wimg, d, pl);
+#define EBFI_FWD_TC(T)                                                                                        \
+    do {                                                                                                      \
+        EBFI_CUDA_OK(cudaFuncSetAttribute(dcn_fwd_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem)); \
+        dcn_fwd_tc_kernel<T><<<grid, NTHR, pl.smem, st>>>(in_blk, bias, offset, mask, output, wimg, d, pl);  \
+    } while (0)
+    switch (pl.TPR) {
+    case 1: EBFI_FWD_TC(1); break;
+    case 2: EBFI_FWD_TC(2); break;
+    case 3: EBFI_FWD_TC(3); break;
+    default: EBFI_FWD_TC(4); break;
+    }
+#undef EBFI_FWD_TC
     EBFI_LAUNCH_OK("dcn_fwd_tc_kernel");
     return EBFI_OK;
 }
