@@ -35,6 +35,8 @@ SIGNATURES = {
     "ebfi_dcnv2_forward_workspace_bytes": (c_size, [_GEOM_P]),
     "ebfi_dcnv2_forward": (c_int, [c_void, _GEOM_P] + [c_void] * 6 + [c_void, c_size]),
     "ebfi_dcnv2_backward": (c_int, [c_void, _GEOM_P] + [c_void] * 11 + [c_void, c_size]),
+    "ebfi_dcnv2_forward_packed": (c_int, [c_void, _GEOM_P] + [c_void] * 6 + [c_void, c_size]),
+    "ebfi_dcnv2_backward_packed": (c_int, [c_void, _GEOM_P] + [c_void] * 9 + [c_void, c_size]),
     "ebfi_fac_forward": (c_int, [c_void] * 4 + [c_int] * 5),
     "ebfi_fac_backward_workspace_bytes": (c_size, [c_int] * 5),
     "ebfi_fac_backward": (c_int, [c_void] * 6 + [c_int] * 5 + [c_void, c_size]),

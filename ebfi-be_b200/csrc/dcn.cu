@@ -74,10 +74,11 @@ dcn_fwd_kernel(const float *__restrict__ input, const float *__restrict__ weight
     for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+    float asum = 0.f;                            // sum |offset| over this thread's taps (packed entry only)
 
     for (int g = 0; g < d.dg; ++g) {
-        const float *off_bg = offset + ((size_t)b * d.dg + g) * 2 * d.KK * plane;
-        const float *mask_bg = mask + ((size_t)b * d.dg + g) * d.KK * plane;
+        const float *off_bg = off_ptr(d, offset, b, g, plane);
+        const float *mask_bg = mask_ptr(d, mask, b, g, plane);
         for (int ch = 0; ch < d.nchunk; ++ch) {
             const int c0 = g * d.cpg + ch * d.cch;
             const int nc = min(d.cch, d.cpg - ch * d.cch);
@@ -93,8 +94,9 @@ dcn_fwd_kernel(const float *__restrict__ input, const float *__restrict__ weight
             for (int it = tid; it < d.KK * TP; it += NT) {
                 const int p = it % TP, t = it / TP, pix = pix_base + p;
                 if (pix < npix) {
-                    float y, x, xq, m;
-                    tap_coords(d, off_bg, mask_bg, t, pix, y, x, xq, m);
+                    float y, x, xq, m, oy, ox;
+                    tap_coords(d, off_bg, mask_bg, t, pix, y, x, xq, m, oy, ox);
+                    if (ch == 0 && blockIdx.y == 0) asum += fabsf(oy) + fabsf(ox);
                     const Tap tp = make_tap(y, x, d.H, d.W);
                     const float w1 = tp.hy * tp.hx, w2 = tp.hy * tp.lx, w3 = tp.ly * tp.hx, w4 = tp.ly * tp.lx;
                     const float *ip = input + ((size_t)b * d.C + c0) * in_plane;
@@ -123,6 +125,7 @@ dcn_fwd_kernel(const float *__restrict__ input, const float *__restrict__ weight
             }
         }
     }
+    if (d.abs_sum && blockIdx.y == 0) warp_atomic_sum(d.abs_sum, asum);
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const int co = co_base + cq * 4 + r;
@@ -178,8 +181,8 @@ dcn_bwd_kernel(const float *__restrict__ input, const float *__restrict__ weight
 
     for (int tile = s; tile < d.B * d.ntile; tile += S) {
         const int b = tile / d.ntile, pix_base = (tile % d.ntile) * TP;
-        const float *off_bg = offset + ((size_t)b * d.dg + g) * 2 * d.KK * plane;
-        const float *mask_bg = mask + ((size_t)b * d.dg + g) * d.KK * plane;
+        const float *off_bg = off_ptr(d, offset, b, g, plane);
+        const float *mask_bg = mask_ptr(d, mask, b, g, plane);
         __syncthreads();
         // ---- (a) col-grad slab = W_chunk^T . gO_tile, accumulated over Cout tiles (lead only)
         if (lead) {
@@ -232,8 +235,8 @@ dcn_bwd_kernel(const float *__restrict__ input, const float *__restrict__ weight
                 for (int cc = 0; cc < nc; ++cc) slab[(cc * d.KK + t) * TPP + p] = 0.f;
                 continue;
             }
-            float y, x, xq, m;
-            tap_coords(d, off_bg, mask_bg, t, pix, y, x, xq, m);
+            float y, x, xq, m, oy, ox;
+            tap_coords(d, off_bg, mask_bg, t, pix, y, x, xq, m, oy, ox);
             const Tap tp = make_tap(y, x, d.H, d.W);
             const Tap tq = (d.ph == d.pw) ? tp : make_tap(y, xq, d.H, d.W);
             const float w1 = tp.hy * tp.hx, w2 = tp.hy * tp.lx, w3 = tp.ly * tp.hx, w4 = tp.ly * tp.lx;
@@ -266,8 +269,9 @@ dcn_bwd_kernel(const float *__restrict__ input, const float *__restrict__ weight
                 *cell = val * m;                                          // column for grad_weight
             }
             if (lead) {
-                float *gy = goff + (((size_t)b * d.dg + g) * 2 * d.KK + 2 * t) * plane + pix;
-                float *gm = gmask + (((size_t)b * d.dg + g) * d.KK + t) * plane + pix;
+                float *gy = goff + (size_t)b * d.off_bs + ((size_t)g * 2 * d.KK + 2 * t) * plane + pix;
+                float *gm = gmask + (size_t)b * d.mask_bs + ((size_t)g * d.KK + t) * plane + pix;
+                s_m *= mask_act_grad(d, m);
                 if (ch == 0) { gy[0] = s_y; gy[plane] = s_x; *gm = s_m; }
                 else { gy[0] += s_y; gy[plane] += s_x; *gm += s_m; }     // chunks are separate, ordered launches
             }
@@ -349,7 +353,16 @@ int fill_dims(const ebfi_dcn_geom *q, DcnDims &d)
     d.ntile = ceil_div(Ho * Wo, TP);
     EBFI_REQUIRE((long)d.H * d.W < (1L << 30) && (long)Ho * Wo < (1L << 30), "dcn: plane too large");
     EBFI_REQUIRE(d.B <= 65535 && ceil_div(d.Co, COT) <= 65535, "dcn: batch / Cout too large for the grid");
+    const long long taps = (long long)d.dg * d.KK * Ho * Wo;
+    d.off_bs = 2 * taps; d.mask_bs = taps; d.packed = 0; d.abs_sum = nullptr;
     return EBFI_OK;
+}
+
+// the raw (B, 3*dg*KK, Ho, Wo) output of conv_offset_mask as offset + mask-logit views
+void set_packed(DcnDims &d)
+{
+    d.off_bs = d.mask_bs = 3 * d.mask_bs;
+    d.packed = 1;
 }
 
 int bwd_splits(const DcnDims &d)
@@ -400,14 +413,13 @@ size_t ebfi_dcnv2_forward_workspace_bytes(const ebfi_dcn_geom *q)
     return forward_tc_workspace(d) + 256;
 }
 
-int ebfi_dcnv2_forward(void *stream, const ebfi_dcn_geom *q, const float *input, const float *weight,
+static int run_forward(void *stream, const DcnDims &d, const float *input, const float *weight,
                        const float *bias, const float *offset, const float *mask, float *output,
                        void *workspace, size_t workspace_bytes)
 {
-    DcnDims d{};
-    if (int rc = fill_dims(q, d)) return rc;
     EBFI_REQUIRE(input && weight && bias && offset && mask && output, "dcn_forward: null pointer");
     cudaStream_t st = ebfi::as_stream(stream);
+    if (d.abs_sum) EBFI_CUDA_OK(cudaMemsetAsync(d.abs_sum, 0, sizeof(float), st));
     // Tensor-core path (dcn_tc.cu) for the shapes it covers; EBFI_DCN_IMPL=simt forces the
     // CUDA-core kernel below, which handles every shape.
     const char *impl = getenv("EBFI_DCN_IMPL");
@@ -422,15 +434,12 @@ int ebfi_dcnv2_forward(void *stream, const ebfi_dcn_geom *q, const float *input,
     return EBFI_OK;
 }
 
-int ebfi_dcnv2_backward(void *stream, const ebfi_dcn_geom *q, const float *input, const float *weight,
-                        const float *bias, const float *offset, const float *mask,
+static int run_backward(void *stream, const DcnDims &d, const float *input, const float *weight,
+                        const float *offset, const float *mask,
                         const float *grad_output, float *grad_input, float *grad_offset,
                         float *grad_mask, float *grad_weight, float *grad_bias,
                         void *workspace, size_t workspace_bytes)
 {
-    (void)bias;
-    DcnDims d{};
-    if (int rc = fill_dims(q, d)) return rc;
     EBFI_REQUIRE(input && weight && offset && mask && grad_output && grad_input && grad_offset &&
                  grad_mask && grad_weight && grad_bias, "dcn_backward: null pointer");
     cudaStream_t st = ebfi::as_stream(stream);
@@ -468,6 +477,56 @@ int ebfi_dcnv2_backward(void *stream, const ebfi_dcn_geom *q, const float *input
     dcn_reduce_partials<<<ceil_div(n, 256), 256, 0, st>>>(gw_part, gb_part, grad_weight, grad_bias, S, (int)n_w, (int)n_b);
     EBFI_LAUNCH_OK("dcn_reduce_partials");
     return EBFI_OK;
+}
+
+int ebfi_dcnv2_forward(void *stream, const ebfi_dcn_geom *q, const float *input, const float *weight,
+                       const float *bias, const float *offset, const float *mask, float *output,
+                       void *workspace, size_t workspace_bytes)
+{
+    DcnDims d{};
+    if (int rc = fill_dims(q, d)) return rc;
+    return run_forward(stream, d, input, weight, bias, offset, mask, output, workspace, workspace_bytes);
+}
+
+int ebfi_dcnv2_backward(void *stream, const ebfi_dcn_geom *q, const float *input, const float *weight,
+                        const float *bias, const float *offset, const float *mask,
+                        const float *grad_output, float *grad_input, float *grad_offset,
+                        float *grad_mask, float *grad_weight, float *grad_bias,
+                        void *workspace, size_t workspace_bytes)
+{
+    (void)bias;
+    DcnDims d{};
+    if (int rc = fill_dims(q, d)) return rc;
+    return run_backward(stream, d, input, weight, offset, mask, grad_output, grad_input, grad_offset, grad_mask,
+                        grad_weight, grad_bias, workspace, workspace_bytes);
+}
+
+int ebfi_dcnv2_forward_packed(void *stream, const ebfi_dcn_geom *q, const float *input, const float *weight,
+                              const float *bias, const float *offset_mask, float *output,
+                              float *abs_offset_sum, void *workspace, size_t workspace_bytes)
+{
+    DcnDims d{};
+    if (int rc = fill_dims(q, d)) return rc;
+    EBFI_REQUIRE(offset_mask != nullptr, "dcn_forward_packed: null pointer");
+    const float *mask_logits = offset_mask + 2 * d.mask_bs;      // channels [2*dg*KK, 3*dg*KK) of sample 0
+    set_packed(d);
+    d.abs_sum = abs_offset_sum;
+    return run_forward(stream, d, input, weight, bias, offset_mask, mask_logits, output, workspace, workspace_bytes);
+}
+
+int ebfi_dcnv2_backward_packed(void *stream, const ebfi_dcn_geom *q, const float *input, const float *weight,
+                               const float *bias, const float *offset_mask, const float *grad_output,
+                               float *grad_input, float *grad_offset_mask, float *grad_weight, float *grad_bias,
+                               void *workspace, size_t workspace_bytes)
+{
+    (void)bias;
+    DcnDims d{};
+    if (int rc = fill_dims(q, d)) return rc;
+    EBFI_REQUIRE(offset_mask && grad_offset_mask, "dcn_backward_packed: null pointer");
+    const long long m0 = 2 * d.mask_bs;
+    set_packed(d);
+    return run_backward(stream, d, input, weight, offset_mask, offset_mask + m0, grad_output, grad_input,
+                        grad_offset_mask, grad_offset_mask + m0, grad_weight, grad_bias, workspace, workspace_bytes);
 }
 
 }  // extern "C"

@@ -178,8 +178,8 @@ dcn_bwd_tc_kernel(const float *__restrict__ in_blk, const float *__restrict__ we
             umma::commit(&bar1);
         }
         // ---- sampling positions of this thread's taps (overlaps GEMM1)
-        const float *off_bg = offset + ((size_t)b * d.dg + g) * 2 * d.KK * plane;
-        const float *mask_bg = mask + ((size_t)b * d.dg + g) * d.KK * plane;
+        const float *off_bg = off_ptr(d, offset, b, g, plane);
+        const float *mask_bg = mask_ptr(d, mask, b, g, plane);
         umma::mbar_wait(&bar1, ph1);                 // D1 complete; P is dead, its storage becomes `col`
         ph1 ^= 1;
         umma::fence_after_sync();
@@ -196,6 +196,7 @@ dcn_bwd_tc_kernel(const float *__restrict__ in_blk, const float *__restrict__ we
             if (valid) {
                 float dy, dx, m;
                 tap_read(off_bg, mask_bg, uplane, (unsigned)t, (unsigned)pix, dy, dx, m);
+                m = mask_act(d, m);
                 const float y = (float)(ho * d.sh - d.ph + ti * d.dh) + dy;
                 const float x = (float)(wo * d.sw - d.pw + tj * d.dw) + dx;
                 const float xq = (float)(wo * d.sw - d.ph + tj * d.dw) + dx;   // the scatter's x uses pad_h (im2col_cuda.cu:368)
@@ -231,9 +232,9 @@ dcn_bwd_tc_kernel(const float *__restrict__ in_blk, const float *__restrict__ we
                     if (tq.c10) red_add_v4(gb + (size_t)tq.i10 * CS + 4 * h, q3 * tt[0], q3 * tt[1], q3 * tt[2], q3 * tt[3]);
                     if (tq.c11) red_add_v4(gb + (size_t)tq.i11 * CS + 4 * h, q4 * tt[0], q4 * tt[1], q4 * tt[2], q4 * tt[3]);
                 }
-                float *gy = goff + (((size_t)b * d.dg + g) * 2 * d.KK + 2 * t) * plane + pix;
+                float *gy = goff + (size_t)b * d.off_bs + ((size_t)g * 2 * d.KK + 2 * t) * plane + pix;
                 gy[0] = s_y; gy[plane] = s_x;
-                gmask[(((size_t)b * d.dg + g) * d.KK + t) * plane + pix] = s_m;
+                gmask[(size_t)b * d.mask_bs + ((size_t)g * d.KK + t) * plane + pix] = s_m * mask_act_grad(d, m);
             }
             // column operand: col[k' = t*8+cc][px = p]; rows t*8..t*8+7 are one 8-row group
             const int off = t * pl.col_sbo + (p >> 3) * COL_LBO + (p & 7) * 2;

@@ -15,7 +15,33 @@ struct DcnDims {
     int nchunk;       // chunks per group
     int KK;           // kh*kw
     int ntile;        // pixel tiles per sample
+    // offset / mask addressing. Separate tensors (the reference's _ext interface): off_bs = dg*2*KK*plane,
+    // mask_bs = dg*KK*plane. Packed (ebfi_dcnv2_*_packed): both are views into the raw (B, 3*dg*KK, Ho, Wo)
+    // output of conv_offset_mask (dcn_v2.py:217-219: offset = channels [0, 2*dg*KK), mask logits = the last
+    // third), off_bs = mask_bs = 3*dg*KK*plane, and the mask is sigmoid(logit) (dcn_v2.py:225).
+    long long off_bs, mask_bs;
+    int packed;
+    float *abs_sum;   // packed forward only, nullable: += sum |offset| (DCN_sep's `offset_mean` warning, :221-223)
 };
+
+__device__ __forceinline__ const float *off_ptr(const DcnDims &d, const float *offset, int b, int g, size_t plane)
+{
+    return offset + (size_t)b * d.off_bs + (size_t)g * 2 * d.KK * plane;
+}
+__device__ __forceinline__ const float *mask_ptr(const DcnDims &d, const float *mask, int b, int g, size_t plane)
+{
+    return mask + (size_t)b * d.mask_bs + (size_t)g * d.KK * plane;
+}
+// modulation scalar from the stored value: identity, or the sigmoid the module applies (dcn_v2.py:225)
+__device__ __forceinline__ float mask_act(const DcnDims &d, float raw)
+{
+    return d.packed ? 1.f / (1.f + expf(-raw)) : raw;
+}
+// d(mask_act)/d(raw) given the activated value
+__device__ __forceinline__ float mask_act_grad(const DcnDims &d, float m)
+{
+    return d.packed ? m * (1.f - m) : 1.f;
+}
 
 // One bilinear tap: corner indices, validity and weights (im2col_cuda.cu:25-54, :180).
 struct Tap {
@@ -41,21 +67,29 @@ __device__ __forceinline__ Tap make_tap(float y, float x, int H, int W)
 
 __device__ __forceinline__ void tap_coords(const DcnDims &d, const float *__restrict__ off_bg,
                                            const float *__restrict__ mask_bg, int t, int pix,
-                                           float &y, float &x, float &xq, float &m)
+                                           float &y, float &x, float &xq, float &m, float &oy, float &ox)
 {
     const size_t plane = (size_t)d.Ho * d.Wo;
     const int ho = pix / d.Wo, wo = pix - ho * d.Wo;
     const int i = t / d.kw, j = t - i * d.kw;
-    const float oy = __ldg(off_bg + (size_t)(2 * t) * plane + pix);
-    const float ox = __ldg(off_bg + (size_t)(2 * t + 1) * plane + pix);
-    m = __ldg(mask_bg + (size_t)t * plane + pix);
+    oy = __ldg(off_bg + (size_t)(2 * t) * plane + pix);
+    ox = __ldg(off_bg + (size_t)(2 * t + 1) * plane + pix);
+    m = mask_act(d, __ldg(mask_bg + (size_t)t * plane + pix));
     y = (float)(ho * d.sh - d.ph + i * d.dh) + oy;
     x = (float)(wo * d.sw - d.pw + j * d.dw) + ox;
     xq = (float)(wo * d.sw - d.ph + j * d.dw) + ox;   // the scatter's x (pad_h quirk, :368)
 }
 
 
-// Division-free read of one tap's (dy, dx, mask) for kernels that already know the pixel index:
+// warp-sum of `v`, then one atomic per warp into *dst (order-dependent rounding: statistics only)
+__device__ __forceinline__ void warp_atomic_sum(float *dst, float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(dst, v);
+}
+
+// Division-free read of one tap's (dy, dx, raw mask value) for kernels that already know the pixel index:
 // offset channel 2t = dy, 2t+1 = dx inside the group (im2col_cuda.cu:170-171); plane = Ho * Wo.
 __device__ __forceinline__ void tap_read(const float *__restrict__ off_bg, const float *__restrict__ mask_bg,
                                          unsigned plane, unsigned t, unsigned pix, float &dy, float &dx, float &m)

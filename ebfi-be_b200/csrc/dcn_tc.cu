@@ -148,8 +148,8 @@ dcn_fwd_tc_kernel(const float *__restrict__ in_blk,
         // dependent corner loads behind it): they are fetched one deformable group AHEAD into registers.
         float ndy[TPR], ndx[TPR], nm[TPR];
         auto fetch_group = [&](int g) {
-            const float *off_bg = offset + ((size_t)b * d.dg + g) * 2 * d.KK * plane;
-            const float *mask_bg = mask + ((size_t)b * d.dg + g) * d.KK * plane;
+            const float *off_bg = off_ptr(d, offset, b, g, plane);
+            const float *mask_bg = mask_ptr(d, mask, b, g, plane);
 #pragma unroll
             for (int s = 0; s < TPR; ++s) {
                 ndy[s] = 0.f; ndx[s] = 0.f; nm[s] = 0.f;
@@ -157,6 +157,7 @@ dcn_fwd_tc_kernel(const float *__restrict__ in_blk,
             }
         };
         fetch_group(0);
+        float asum = 0.f;                          // sum |offset| of this thread's taps (packed entry)
 
         int n = 0;
         for (int g = 0; g < d.dg; ++g) {
@@ -166,7 +167,8 @@ dcn_fwd_tc_kernel(const float *__restrict__ in_blk,
             for (int s = 0; s < TPR; ++s) {
                 sy[s] = tv[s] ? by[s] + ndy[s] : -2.f;
                 sx[s] = tv[s] ? bx[s] + ndx[s] : -2.f;
-                sm[s] = nm[s];
+                sm[s] = mask_act(d, nm[s]);
+                asum += fabsf(ndy[s]) + fabsf(ndx[s]);       // invalid taps hold zeros
             }
             if (g + 1 < d.dg) fetch_group(g + 1);
             for (int ci = 0; ci < pl.ncs; ++ci) {
@@ -207,6 +209,7 @@ dcn_fwd_tc_kernel(const float *__restrict__ in_blk,
                 }
             }
         }
+        if (d.abs_sum) warp_atomic_sum(d.abs_sum, asum);
         // ---- all MMAs complete (commits complete in order: the last one covers everything)
         umma::mbar_wait(&bar_free[(n - 1) & 1], (uint32_t)(((n - 1) >> 1) & 1));
         umma::fence_after_sync();

@@ -47,6 +47,36 @@ class _DCNv2(Function):
 dcn_v2_conv = _DCNv2.apply
 
 
+class _DCNv2Packed(Function):
+    """dcn_v2_conv(input, cat(o1, o2), sigmoid(mask), ...) with (o1, o2, mask) = chunk(offset_mask, 3, 1)
+    (dcn_v2.py:217-227) as ONE op: the kernels read the raw conv output and apply the sigmoid themselves,
+    the backward returns one gradient of the same layout. `stat` (optional 1-element fp32 CUDA tensor)
+    receives sum |offset|."""
+
+    @staticmethod
+    def forward(ctx, input, offset_mask, weight, bias, stride, padding, dilation, deformable_groups, stat):
+        ctx.stride, ctx.padding, ctx.dilation = _pair(stride), _pair(padding), _pair(dilation)
+        ctx.kernel_size = _pair(weight.shape[2:4])
+        ctx.deformable_groups = deformable_groups
+        out = _backend.dcn_v2_forward_packed(input, weight, bias, offset_mask, *ctx.kernel_size, *ctx.stride,
+                                             *ctx.padding, *ctx.dilation, deformable_groups, stat)
+        ctx.save_for_backward(input, offset_mask, weight, bias)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        input, offset_mask, weight, bias = ctx.saved_tensors
+        g_in, g_om, g_w, g_b = _backend.dcn_v2_backward_packed(
+            input, weight, bias, offset_mask, grad_output, *ctx.kernel_size, *ctx.stride,
+            *ctx.padding, *ctx.dilation, ctx.deformable_groups)
+        return g_in, g_om, g_w, g_b, None, None, None, None, None
+
+
+def dcn_v2_conv_packed(input, offset_mask, weight, bias, stride, padding, dilation, deformable_groups, stat=None):
+    return _DCNv2Packed.apply(input, offset_mask, weight, bias, stride, padding, dilation, deformable_groups, stat)
+
+
 class DCNv2(nn.Module):
     """Parameters and init as dcn_v2.py:98-128: weight ~ U(-1/sqrt(C*kh*kw), +), bias = 0."""
 
@@ -98,16 +128,75 @@ class _DCNWithOffsetConv(DCNv2):
 
 
 class DCN(_DCNWithOffsetConv):
+    """`fused=True` (default) feeds the conv output straight to the packed kernels; `fused=False` runs
+    the reference's op sequence chunk -> cat -> sigmoid -> dcn_v2_conv (dcn_v2.py:179-187)."""
+    fused = True
+
     def forward(self, input):
+        if self.fused and input.is_cuda:
+            return dcn_v2_conv_packed(input, self.conv_offset_mask(input), self.weight, self.bias, self.stride,
+                                      self.padding, self.dilation, self.deformable_groups)
         offset, mask = self._offset_mask(input)
         return dcn_v2_conv(input, offset, torch.sigmoid(mask), self.weight, self.bias, self.stride,
                            self.padding, self.dilation, self.deformable_groups)
 
 
+class _OffsetWatch:
+    """The reference's `if offset_mean > 100: logger.warning(...)` (dcn_v2.py:221-223) forces a host
+    sync in every forward. Here the kernel accumulates sum |offset| on the device; the value is copied
+    to pinned memory asynchronously and examined when it has arrived (at the next forward of the module,
+    or on `flush()`), so the warning is the same but may be logged one call late."""
+
+    def __init__(self):
+        self._pending = []          # (event, pinned value, element count)
+        self._free = []             # pinned 1-float buffers, reused (cudaHostAlloc is slow)
+
+    def submit(self, stat, count):
+        host = self._free.pop() if self._free else torch.empty(1, dtype=torch.float32, pin_memory=True)
+        host.copy_(stat, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._pending.append((ev, host, count))
+
+    def poll(self, wait=False):
+        keep = []
+        for ev, host, count in self._pending:
+            if wait:
+                ev.synchronize()
+            if ev.query():
+                mean = float(host[0]) / count
+                if mean > 100:
+                    logger.warning("Offset mean is {}, larger than 100.".format(mean))
+                self._free.append(host)
+            else:
+                keep.append((ev, host, count))
+        self._pending = keep
+
+    def flush(self):
+        self.poll(wait=True)
+
+
 class DCN_sep(_DCNWithOffsetConv):
-    """Offsets and masks come from a second feature map `fea` (dcn_v2.py:197-227)."""
+    """Offsets and masks come from a second feature map `fea` (dcn_v2.py:197-227). `fused=False` runs
+    the reference's op sequence including its per-call host sync."""
+    fused = True
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self._watch = _OffsetWatch()
+
+    def flush_offset_warnings(self):
+        self._watch.flush()
 
     def forward(self, input, fea):
+        if self.fused and input.is_cuda:
+            om = self.conv_offset_mask(fea)
+            self._watch.poll()
+            stat = torch.empty(1, dtype=torch.float32, device=input.device)
+            out = dcn_v2_conv_packed(input, om, self.weight, self.bias, self.stride, self.padding,
+                                     self.dilation, self.deformable_groups, stat)
+            self._watch.submit(stat, om.numel() // 3 * 2)
+            return out
         offset, mask = self._offset_mask(fea)
         offset_mean = torch.mean(torch.abs(offset))
         if offset_mean > 100:                           # host sync, as in the reference (:221-223)

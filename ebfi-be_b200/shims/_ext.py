@@ -120,6 +120,73 @@ def dcn_v2_backward(input, weight, bias, offset, mask, grad_output, kernel_h, ke
     return grads
 
 
+def _check_packed(g, ho, wo, offset_mask):
+    want = (g.batch, 3 * g.deformable_group * g.kernel_h * g.kernel_w, ho, wo)
+    if tuple(offset_mask.shape) != want:
+        raise RuntimeError(f"dcn_v2: offset_mask shape {tuple(offset_mask.shape)} does not match the geometry "
+                           f"(expected {want})")
+
+
+def dcn_v2_forward_packed(input, weight, bias, offset_mask, kernel_h, kernel_w, stride_h, stride_w,
+                          pad_h, pad_w, dilation_h, dilation_w, deformable_group, abs_offset_sum=None):
+    """NEW (no reference counterpart in `_ext`): dcn_v2_forward fed with the raw `conv_offset_mask`
+    output, i.e. chunk / cat / sigmoid of DCN.forward / DCN_sep.forward (dcn_v2.py:179-187, :217-227)
+    folded into the kernel. `abs_offset_sum`: optional 1-element fp32 CUDA tensor that receives
+    sum |offset| (for the `offset_mean > 100` warning, :221-223)."""
+    if _check_cuda(input=input, weight=weight, bias=bias, offset_mask=offset_mask) == torch.bfloat16:
+        return dcn_v2_forward_packed(input.float(), weight.float(), bias.float(), offset_mask.float(), kernel_h,
+                                     kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w,
+                                     deformable_group, abs_offset_sum).bfloat16()
+    g, ho, wo = _geom(input, weight, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w,
+                      dilation_h, dilation_w, deformable_group)
+    _check_packed(g, ho, wo, offset_mask)
+    if abs_offset_sum is not None and not (abs_offset_sum.is_cuda and abs_offset_sum.dtype == torch.float32
+                                           and abs_offset_sum.numel() == 1):
+        raise RuntimeError("dcn_v2_forward_packed: abs_offset_sum must be a 1-element float32 CUDA tensor")
+    input, weight, bias, offset_mask = (t.contiguous() for t in (input, weight, bias, offset_mask))
+    with torch.cuda.device(input.device):
+        output = torch.empty((g.batch, g.channels_out, ho, wo), dtype=input.dtype, device=input.device)
+        lib = L.load()
+        nbytes = lib.ebfi_dcnv2_forward_workspace_bytes(g)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=input.device)
+        L.check(lib.ebfi_dcnv2_forward_packed(L.stream_ptr(input.device), g, L.ptr(input), L.ptr(weight),
+                                              L.ptr(bias), L.ptr(offset_mask), L.ptr(output),
+                                              L.ptr(abs_offset_sum) if abs_offset_sum is not None else None,
+                                              L.ptr(ws), nbytes),
+                "dcn_v2_forward_packed")
+    return output
+
+
+def dcn_v2_backward_packed(input, weight, bias, offset_mask, grad_output, kernel_h, kernel_w, stride_h,
+                           stride_w, pad_h, pad_w, dilation_h, dilation_w, deformable_group):
+    """Backward of dcn_v2_forward_packed. Returns [grad_input, grad_offset_mask, grad_weight, grad_bias];
+    grad_offset_mask has the layout of offset_mask, its last third already multiplied by sigmoid'."""
+    if not input.is_contiguous():
+        raise RuntimeError("input tensor has to be contiguous")
+    if not weight.is_contiguous():
+        raise RuntimeError("weight tensor has to be contiguous")
+    if _check_cuda(input=input, weight=weight, bias=bias, offset_mask=offset_mask,
+                   grad_output=grad_output) == torch.bfloat16:
+        return _bf16_via_fp32(dcn_v2_backward_packed, (input, weight, bias, offset_mask, grad_output),
+                              (kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w, deformable_group))
+    g, ho, wo = _geom(input, weight, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w,
+                      dilation_h, dilation_w, deformable_group)
+    _check_packed(g, ho, wo, offset_mask)
+    if tuple(grad_output.shape) != (g.batch, g.channels_out, ho, wo):
+        raise RuntimeError("dcn_v2_backward_packed: grad_output has the wrong shape")
+    bias, offset_mask, grad_output = (t.contiguous() for t in (bias, offset_mask, grad_output))
+    lib = L.load()
+    with torch.cuda.device(input.device):
+        grads = [torch.empty_like(t) for t in (input, offset_mask, weight, bias)]
+        nbytes = lib.ebfi_dcnv2_backward_workspace_bytes(g)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=input.device)
+        L.check(lib.ebfi_dcnv2_backward_packed(L.stream_ptr(input.device), g, L.ptr(input), L.ptr(weight),
+                                               L.ptr(bias), L.ptr(offset_mask), L.ptr(grad_output),
+                                               *(L.ptr(t) for t in grads), L.ptr(ws), nbytes),
+                "dcn_v2_backward_packed")
+    return grads
+
+
 def dcn_v2_psroi_pooling_forward(*args, **kwargs):
     raise NotImplementedError("deformable PS-ROI pooling is outside the EBFI-BE alignment hot path "
                               "(models/DCNv2/src/dcn_v2.h:94-145); not provided by ebfi_be_b200")

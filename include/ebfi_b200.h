@@ -100,6 +100,27 @@ int ebfi_dcnv2_backward(void *stream, const ebfi_dcn_geom *g,
                         float *grad_weight, float *grad_bias,
                         void *workspace, size_t workspace_bytes);
 
+/* Packed variants: the deformable conv fed directly with the raw output of the module's
+ * `conv_offset_mask` (models/DCNv2/dcn_v2.py:217-227, DCN.forward :179-187):
+ *   offset_mask : (B, 3*dg*kh*kw, Ho, Wo); channels [0, 2*dg*kh*kw) ARE cat(o1, o2) = the offsets,
+ *                 the last third are the mask logits; the kernels apply sigmoid() themselves.
+ * This folds torch.chunk / torch.cat / torch.sigmoid (and their backward passes) into the kernels:
+ * `grad_offset_mask` has the layout of `offset_mask` and already contains
+ * grad_mask * m * (1 - m) in its last third. `abs_offset_sum` (nullable, 1 float, device) receives
+ * sum |offset| so that the module's `offset_mean > 100` warning needs no separate pass over the
+ * offsets (it is a statistic: accumulated with atomics, not bit-reproducible).
+ * Workspace sizes are those of the unpacked calls. */
+int ebfi_dcnv2_forward_packed(void *stream, const ebfi_dcn_geom *g,
+                              const float *input, const float *weight, const float *bias,
+                              const float *offset_mask, float *output, float *abs_offset_sum,
+                              void *workspace, size_t workspace_bytes);
+int ebfi_dcnv2_backward_packed(void *stream, const ebfi_dcn_geom *g,
+                               const float *input, const float *weight, const float *bias,
+                               const float *offset_mask, const float *grad_output,
+                               float *grad_input, float *grad_offset_mask,
+                               float *grad_weight, float *grad_bias,
+                               void *workspace, size_t workspace_bytes);
+
 /* ---- FAC KernelConv2D ------------------------------------------------------- */
 
 /* input  : (B, C, H+K-1, W+K-1)   already padded by the caller (KernelConv2D.py:82-86)

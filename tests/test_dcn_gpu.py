@@ -230,3 +230,121 @@ def test_bf16_tensors_stated_tolerance(dcn, oracle):
     want = oracle.dcn_backward(f(x), f(off), f(msk), f(w), f(b), f(go), 1, 1, 1, dg)
     for name, t, r in zip(GRADS, ts, want):
         assert rel_err(t.grad.float().cpu().numpy(), r) < tol, name
+
+
+# ---- packed entry points: raw conv_offset_mask output in, chunk/cat/sigmoid folded into the kernels ----
+def _packed_case(rng, shape):
+    B, C, Co, H, W, k, s, p, d, dg, osc = shape
+    Ho = (H + 2 * p - (d * (k - 1) + 1)) // s + 1
+    Wo = (W + 2 * p - (d * (k - 1) + 1)) // s + 1
+    n_t = dg * k * k
+    x = rng.standard_normal((B, C, H, W), dtype=np.float32)
+    w = (rng.random((Co, C, k, k), dtype=np.float32) * 2 - 1) / np.sqrt(C * k * k)
+    b = rng.standard_normal(Co, dtype=np.float32)
+    om = rng.standard_normal((B, 3 * n_t, Ho, Wo)).astype(np.float32)
+    om[:, :2 * n_t] *= osc
+    om[:, 2 * n_t:] *= 2.0                         # logits in about (-6, 6)
+    go = rng.standard_normal((B, Co, Ho, Wo), dtype=np.float32)
+    return x, w, b, om, go, n_t
+
+
+def _packed_expected(oracle, x, w, b, om, go, n_t, s, p, d, dg):
+    """The reference's op sequence (dcn_v2.py:217-227) in float64 around the CPU oracle."""
+    off = np.ascontiguousarray(om[:, :2 * n_t])
+    m = 1.0 / (1.0 + np.exp(-om[:, 2 * n_t:].astype(np.float64)))
+    msk = m.astype(np.float32)
+    out = oracle.dcn_forward(x, off, msk, w, b, s, p, d, dg)
+    g_in, g_off, g_msk, g_w, g_b = oracle.dcn_backward(x, off, msk, w, b, go, s, p, d, dg)
+    g_om = np.concatenate([g_off, g_msk * m * (1.0 - m)], axis=1)
+    return out, [g_in, g_om, g_w, g_b], off
+
+
+@pytest.mark.parametrize("shape", [SHAPES[0], SHAPES[1], SHAPES[3], SHAPES[7]])
+def test_packed_offset_mask_against_oracle(dcn, oracle, shape):
+    from gpu_util import dev, n, t
+    rng = np.random.default_rng(7 + len(str(shape)))
+    s, p, d, dg = shape[6], shape[7], shape[8], shape[9]
+    x, w, b, om, go, n_t = _packed_case(rng, shape)
+    want_out, want_grads, off = _packed_expected(oracle, x, w, b, om, go, n_t, s, p, d, dg)
+    ts = [t(a).requires_grad_() for a in (x, om, w, b)]
+    stat = torch.full((1,), -1.0, device=dev())
+    out = dcn.dcn_v2_conv_packed(*ts, s, p, d, dg, stat)
+    out.backward(t(go))
+    assert rel_err(n(out), want_out) < FWD_TOL
+    for name, v, ref in zip(["grad_input", "grad_offset_mask", "grad_weight", "grad_bias"], ts, want_grads):
+        assert rel_err(n(v.grad), ref) < GRAD_TOL, name
+    # the statistic behind the `offset_mean > 100` warning (dcn_v2.py:221-223)
+    assert abs(float(stat) / off.size - np.abs(off.astype(np.float64)).mean()) < 1e-4 * np.abs(off).mean()
+
+
+def test_packed_equals_unpacked_sequence(dcn):
+    """Same kernels, two addressings: packed == chunk -> cat -> sigmoid -> dcn_v2_conv through autograd, to
+    rounding of the sigmoid (torch's vs the in-kernel one)."""
+    from gpu_util import dev
+    torch.manual_seed(3)
+    B, C, H, W, dg = 2, 64, 40, 56, 8
+    x = torch.randn(B, C, H, W, device=dev(), requires_grad=True)
+    om = (torch.randn(B, 3 * dg * 9, H, W, device=dev()) * 2).requires_grad_()
+    w = (torch.randn(C, C, 3, 3, device=dev()) / 24).requires_grad_()
+    b = torch.randn(C, device=dev(), requires_grad=True)
+    go = torch.randn(B, C, H, W, device=dev())
+    o1, o2, mask = torch.chunk(om, 3, dim=1)
+    ref = dcn.dcn_v2_conv(x, torch.cat((o1, o2), 1), torch.sigmoid(mask), w, b, 1, 1, 1, dg)
+    ref.backward(go)
+    want = [v.grad.clone() for v in (x, om, w, b)]
+    for v in (x, om, w, b):
+        v.grad = None
+    got = dcn.dcn_v2_conv_packed(x, om, w, b, 1, 1, 1, dg)
+    got.backward(go)
+    assert rel_err(got.detach().cpu().numpy(), ref.detach().cpu().numpy()) < FWD_TOL
+    for name, v, r in zip(["grad_input", "grad_offset_mask", "grad_weight", "grad_bias"], (x, om, w, b), want):
+        assert rel_err(v.grad.cpu().numpy(), r.cpu().numpy()) < GRAD_TOL, name
+
+
+def test_fused_modules_match_reference_sequence(dcn, caplog):
+    """DCN / DCN_sep with fused=True (packed kernels, deferred warning) vs fused=False (the reference's op
+    sequence with its host sync), same parameters."""
+    import logging
+    from gpu_util import dev
+    torch.manual_seed(5)
+    x = torch.randn(1, 64, 48, 64, device=dev())
+    fea = torch.randn_like(x)
+    for cls, args in ((dcn.DCN, (x,)), (dcn.DCN_sep, (x, fea))):
+        m = cls(64, 64, 3, stride=1, padding=1, deformable_groups=8).to(dev())
+        with torch.no_grad():
+            m.conv_offset_mask.weight.normal_(0, 0.05)
+            m.conv_offset_mask.bias.normal_(0, 0.5)
+        outs, grads = [], []
+        for fused in (True, False):
+            m.fused = fused
+            m.zero_grad()
+            out = m(*args)
+            out.square().sum().backward()
+            outs.append(out.detach().cpu().numpy())
+            grads.append({k: v.grad.cpu().numpy().copy() for k, v in m.named_parameters()})
+        assert rel_err(outs[0], outs[1]) < FWD_TOL
+        for k in grads[0]:
+            assert rel_err(grads[0][k], grads[1][k]) < GRAD_TOL, k
+    # the warning: offsets with mean |.| > 100 are reported (late, at the latest on flush)
+    sep = dcn.DCN_sep(64, 64, 3, stride=1, padding=1, deformable_groups=8).to(dev())
+    with torch.no_grad():
+        sep.conv_offset_mask.bias[:144] = 500.0
+    with caplog.at_level(logging.WARNING, logger="base"):
+        sep(x, fea)
+        sep.flush_offset_warnings()
+    assert any("larger than 100" in r.getMessage() for r in caplog.records)
+    caplog.clear()
+    with torch.no_grad():
+        sep.conv_offset_mask.bias.zero_()
+    with caplog.at_level(logging.WARNING, logger="base"):
+        sep(x, fea)
+        sep.flush_offset_warnings()
+    assert not caplog.records
+
+
+def test_packed_rejects_wrong_channel_count(dcn):
+    from gpu_util import dev
+    x = torch.randn(1, 16, 8, 8, device=dev())
+    w = torch.randn(16, 16, 3, 3, device=dev())
+    with pytest.raises(RuntimeError, match="offset_mask shape"):
+        dcn.dcn_v2_conv_packed(x, torch.randn(1, 2 * 2 * 9, 8, 8, device=dev()), w, torch.zeros(16, device=dev()), 1, 1, 1, 2)
