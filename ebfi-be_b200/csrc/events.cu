@@ -31,6 +31,11 @@ template <typename T> __device__ __forceinline__ bool out_of_range(T x, T y, int
     return (x >= (T)W) || (x < (T)0) || (y >= (T)H) || (y < (T)0);
 }
 
+__device__ __forceinline__ bool out_of_range(int16_t x, int16_t y, int H, int W)
+{
+    return ((int)x >= W) || (x < 0) || ((int)y >= H) || (y < 0);
+}
+
 __device__ __forceinline__ void red_add(float *p, float v)
 {
     if (v != 0.f) atomicAdd(p, v);     // result unused -> RED.ADD.F32; adding +-0 is a no-op
@@ -118,14 +123,23 @@ __global__ void events_voxel_kernel(T *__restrict__ xs, T *__restrict__ ys, cons
     }
 }
 
-// binary_search_torch_tensor (:77-99) for all 2*bins boundaries, one thread each.
-template <typename T>
-__global__ void stack_bounds_kernel(const T *__restrict__ ts, int64_t n, int bins, int64_t *__restrict__ bounds,
-                                    const unsigned char *__restrict__ skip)
+// Timestamps as the datasets hand them to events_to_stack: GetEventsIndex (dataloader/h5dataset.py:327-336)
+// normalises the on-disk float64 seconds with `ts = (ts - ts[0]) / (ts[-1] - ts[0] + 1e-6)` in float64.
+// The same two IEEE operations are evaluated on access, so the raw array never has to be rewritten.
+struct NormalizedTs {
+    const double *raw;
+    double t0, den;
+    __device__ __forceinline__ double operator[](int64_t i) const { return __ddiv_rn(__dsub_rn(raw[i], t0), den); }
+};
+__device__ __forceinline__ NormalizedTs normalized(const double *raw, int64_t n)
 {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= 2 * bins) return;
-    if (skip && *skip) { bounds[e] = 0; return; }     // empty slices: the scatter kernel adds nothing
+    return NormalizedTs{raw, raw[0], __dadd_rn(__dsub_rn(raw[n - 1], raw[0]), 1e-6)};
+}
+
+// binary_search_torch_tensor (:77-99) for all 2*bins boundaries, one thread each.
+template <typename T, typename TS>
+__device__ void stack_bounds(const TS &ts, int64_t n, int bins, int64_t *__restrict__ bounds, int e)
+{
     const int bi = e >> 1, right = e & 1;
     // dt = ts[-1]-ts[0]+1e-6; delta = dt/B; tstart = ts[0]+delta*bi; tend = tstart+delta (:324-329),
     // every step rounded in the dtype of ts
@@ -155,27 +169,50 @@ __global__ void stack_bounds_kernel(const T *__restrict__ ts, int64_t n, int bin
 }
 
 template <typename T>
-__global__ void events_stack_kernel(T *__restrict__ xs, T *__restrict__ ys, const float *__restrict__ ps,
+__global__ void stack_bounds_kernel(const T *__restrict__ ts, int64_t n, int bins, int64_t *__restrict__ bounds,
+                                    const unsigned char *__restrict__ skip)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 2 * bins) return;
+    if (skip && *skip) { bounds[e] = 0; return; }     // empty slices: the scatter kernel adds nothing
+    stack_bounds<T>(ts, n, bins, bounds, e);
+}
+
+// Raw (on-disk) timestamps. The early-out `ts.sum() == 0 or len(ts) <= 3` (encodings.py:319-320) on the
+// normalised, non-decreasing timestamps is `ts[-1] == ts[0]` (every term is >= 0).
+__global__ void stack_bounds_raw_kernel(const double *__restrict__ ts, int64_t n, int bins, int64_t *__restrict__ bounds)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 2 * bins) return;
+    if (n <= 3 || ts[n - 1] == ts[0]) { bounds[e] = 0; return; }
+    stack_bounds<double>(normalized(ts, n), n, bins, bounds, e);
+}
+
+// T: coordinate type (float / double tensors, or the on-disk int16, never written back); P: polarity type
+// (float, or the on-disk int8 -> `.float()`, h5dataset.py:349). pol_stride / bin_stride: element strides of
+// the two leading output dimensions, (bins*plane, plane) for the reference's (2, B, H, W) and
+// (plane, 2*plane) for the (B, 2, H, W) the datasets transpose it to.
+template <typename T, typename P>
+__global__ void events_stack_kernel(T *__restrict__ xs, T *__restrict__ ys, const P *__restrict__ ps,
                                     int64_t n, int bins, int H, int W, const int64_t *__restrict__ bounds,
-                                    float *__restrict__ stack, int write_back)
+                                    float *__restrict__ stack, int write_back, int64_t pol_stride, int64_t bin_stride)
 {
     extern __shared__ int64_t s_bounds[];
     for (int e = threadIdx.x; e < 2 * bins; e += blockDim.x) s_bounds[e] = bounds[e];
     __syncthreads();
-    const int64_t plane = (int64_t)H * W;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const T x = xs[i], y = ys[i];
         const bool oob = out_of_range(x, y, H, W);
         const int64_t pix = oob ? 0 : (int64_t)y * W + (int64_t)x;
-        const float p = ps[i];
+        const float p = (float)ps[i];
         const float vpos = p * (p < 0.f ? 0.f : p);    // ps * mask_pos, :333-336
         const float vneg = p * (p > 0.f ? 0.f : p);    // ps * mask_neg
         bool seen = false;
         for (int b = 0; b < bins; ++b) {
             if (i < s_bounds[2 * b] || i >= s_bounds[2 * b + 1]) continue;
             // first slice that holds an out-of-range event: its positive pass sees value 0
-            if (!(oob && !seen)) red_add(stack + (int64_t)b * plane + pix, vpos);
-            red_add(stack + ((int64_t)bins + b) * plane + pix, vneg);
+            if (!(oob && !seen)) red_add(stack + b * bin_stride + pix, vpos);
+            red_add(stack + pol_stride + b * bin_stride + pix, vneg);
             seen = true;
         }
         if (oob && seen && write_back) { xs[i] = (T)0; ys[i] = (T)0; }
@@ -264,14 +301,35 @@ int ebfi_events_to_stack(void *stream, void *xs, void *ys, const void *ts, const
     cudaStream_t st = ebfi::as_stream(stream);
     const int nb2 = 2 * num_bins;
     const size_t smem = (size_t)nb2 * sizeof(int64_t);
+    const int64_t plane = (int64_t)height * width;
     if (dtype == EBFI_F32) {
         stack_bounds_kernel<float><<<ceil_div(nb2, 64), 64, 0, st>>>((const float *)ts, n, num_bins, bounds, skip);
-        events_stack_kernel<float><<<grid_for(n), 256, smem, st>>>((float *)xs, (float *)ys, ps, n, num_bins, height, width, bounds, stack, write_back);
+        events_stack_kernel<float, float><<<grid_for(n), 256, smem, st>>>((float *)xs, (float *)ys, ps, n, num_bins, height, width, bounds, stack, write_back, num_bins * plane, plane);
     } else {
         stack_bounds_kernel<double><<<ceil_div(nb2, 64), 64, 0, st>>>((const double *)ts, n, num_bins, bounds, skip);
-        events_stack_kernel<double><<<grid_for(n), 256, smem, st>>>((double *)xs, (double *)ys, ps, n, num_bins, height, width, bounds, stack, write_back);
+        events_stack_kernel<double, float><<<grid_for(n), 256, smem, st>>>((double *)xs, (double *)ys, ps, n, num_bins, height, width, bounds, stack, write_back, num_bins * plane, plane);
     }
     EBFI_LAUNCH_OK("events_stack kernels");
+    return EBFI_OK;
+}
+
+int ebfi_events_raw_to_stack(void *stream, const int16_t *xs, const int16_t *ys, const double *ts, const int8_t *ps,
+                             int64_t n, int num_bins, int height, int width, float *stack, int64_t *bounds,
+                             int bins_major)
+{
+    EBFI_REQUIRE(n >= 0 && height > 0 && width > 0, "events_raw_to_stack: bad sizes n=%lld H=%d W=%d", (long long)n, height, width);
+    EBFI_REQUIRE(num_bins > 0 && num_bins <= 2048, "events_raw_to_stack: num_bins must be in [1, 2048]");
+    EBFI_REQUIRE(stack && bounds && (n == 0 || (xs && ys && ts && ps)), "events_raw_to_stack: null pointer");
+    if (n <= 3) return EBFI_OK;                        // encodings.py:319-320 (and h5dataset.py:332-333 for n == 0)
+    cudaStream_t st = ebfi::as_stream(stream);
+    const int nb2 = 2 * num_bins;
+    const int64_t plane = (int64_t)height * width;
+    stack_bounds_raw_kernel<<<ceil_div(nb2, 64), 64, 0, st>>>(ts, n, num_bins, bounds);
+    // the raw arrays are read-only: the in-place zeroing of out-of-range events is reproduced in the output only
+    events_stack_kernel<int16_t, int8_t><<<grid_for(n), 256, (size_t)nb2 * sizeof(int64_t), st>>>(
+        const_cast<int16_t *>(xs), const_cast<int16_t *>(ys), ps, n, num_bins, height, width, bounds, stack, 0,
+        bins_major ? plane : num_bins * plane, bins_major ? 2 * plane : plane);
+    EBFI_LAUNCH_OK("events_raw_to_stack kernels");
     return EBFI_OK;
 }
 

@@ -203,6 +203,23 @@ int ebfi_events_to_stack(void *stream, void *xs, void *ys, const void *ts, const
                          float *stack, int64_t *bounds, int write_back,
                          const unsigned char *skip_flag);
 
+/* The datasets' whole event path in one call: GetEventsIndex + events_to_stack
+ * (dataloader/h5dataset.py:327-349) on the ON-DISK dtypes of the HDF5 files
+ * (generate_dataset/tools/event_packagers.py:128-131): xs, ys int16; ts float64
+ * seconds, non-decreasing; ps int8. The normalisation
+ * `ts = (ts - ts[0]) / (ts[-1] - ts[0] + 1e-6)` (h5dataset.py:335) is evaluated in
+ * float64 on access, `ps.float()` (:349) in registers; nothing is converted or
+ * written back, 13 bytes are read per event instead of 32 (4 x float64).
+ * n_events <= 3 (which includes the reference's empty-slice substitute, :332-333) and
+ * all-equal timestamps leave `stack` untouched = the zeros early-out (encodings.py:319-320).
+ * stack : fp32, accumulated into (caller zero-fills); (2, num_bins, H, W) like the
+ *   reference, or (num_bins, 2, H, W) — what the datasets' `.transpose(0, 1)` yields —
+ *   when bins_major != 0.
+ * bounds : (2*num_bins) int64 scratch. */
+int ebfi_events_raw_to_stack(void *stream, const int16_t *xs, const int16_t *ys, const double *ts,
+                             const int8_t *ps, int64_t n_events, int num_bins, int height, int width,
+                             float *stack, int64_t *bounds, int bins_major);
+
 /* ---- self test --------------------------------------------------------------- */
 
 /* One-CTA GEMM on the tcgen05 tensor-core path with the 3xTF32 split the DCN kernels use:

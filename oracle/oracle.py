@@ -163,3 +163,16 @@ def events_to_stack(xs, ys, ts, ps, B, sensor_size):
     lib().oracle_events_to_stack(_p(xs), _p(ys), _p(ts), _p(ps), dt, ctypes.c_int64(len(xs)),
                                  B, H, W, _p(stack), _p(bounds))
     return stack, xs, ys, bounds
+
+
+def dataset_event_stack(xs, ys, ts, ps, B, sensor_size):
+    """H5Dataset.GetEvents (dataloader/h5dataset.py:327-349) for one slice in the on-disk dtypes (int16,
+    int16, float64 seconds, int8; generate_dataset/tools/event_packagers.py:128-131): empty-slice
+    substitute (:332-333), float64 normalisation (:335), everything promoted to float64 by the concatenate
+    (:336), `ps.float()` and events_to_stack, `.transpose(0, 1)` (:349). Returns (B, 2, H, W)."""
+    xs, ys, ts, ps = (np.asarray(a) for a in (xs, ys, ts, ps))
+    if len(xs) == 0 or len(ys) == 0 or len(ts) == 0 or len(ps) == 0:
+        xs = ys = ts = ps = np.array([0.])
+    ts = (ts.astype(np.float64) - ts[0]) / (ts[-1] - ts[0] + 1e-6)
+    stack, *_ = events_to_stack(xs.astype(np.float64), ys.astype(np.float64), ts, ps.astype(np.float32), B, sensor_size)
+    return np.ascontiguousarray(stack.transpose(1, 0, 2, 3))

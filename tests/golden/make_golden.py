@@ -137,6 +137,60 @@ def events_cases():
                                         torch.tensor([0., .5, 1]), torch.ones(3), 3, sensor_size=(4, 4)))
 
 
+def raw_event_slice(seed, n, H, W, oob=0, quant=None, ps01=False):
+    """An HDF5 event slice in the on-disk dtypes (generate_dataset/tools/event_packagers.py:128-131)."""
+    g = np.random.default_rng(seed)
+    xs = g.integers(0, W, n).astype(np.int16)
+    ys = g.integers(0, H, n).astype(np.int16)
+    ts = np.sort(g.random(n))
+    if quant:                                   # repeated timestamps, some exactly on bin boundaries
+        ts = np.round(ts * quant) / quant
+    ts = (1234.5 + 0.25 * ts).astype(np.float64)    # seconds since the start of the recording
+    ps = (g.integers(0, 2, n) if ps01 else g.integers(0, 2, n) * 2 - 1).astype(np.int8)
+    for j in range(oob):
+        i = int(g.integers(0, n))
+        if j % 4 == 0: xs[i] = W + j
+        elif j % 4 == 1: ys[i] = -1 - j
+        elif j % 4 == 2: xs[i] = -1
+        else: ys[i] = H
+    return xs, ys, ts, ps
+
+
+def dataset_event_stack(xs, ys, ts, ps, bins, sensor):
+    """H5Dataset.GetEvents (dataloader/h5dataset.py:327-349) on one slice. h5dataset.py itself needs h5py
+    (absent here), so its five array lines are restated; the encoder is the reference's own."""
+    if len(xs) == 0 or len(ys) == 0 or len(ts) == 0 or len(ps) == 0:          # :332-333
+        xs = ys = ts = ps = np.array([0.])
+    ts = (ts - ts[0]) / (ts[-1] - ts[0] + 1e-6)                                  # :335
+    ev = torch.from_numpy(np.concatenate((xs[np.newaxis, ...], ys[np.newaxis, ...], ts[np.newaxis, ...],
+                                          ps[np.newaxis, ...]), axis=0))        # :336, 4xN float64
+    return enc.events_to_stack(xs=ev[0], ys=ev[1], ts=ev[2], ps=ev[3].float(), B=bins,
+                               sensor_size=sensor).transpose(0, 1)              # :349, TBx2xHxW
+
+
+def events_raw_cases():
+    H, W = 12, 16
+    out = {"sensor": np.array([H, W])}
+    for name, kw in [("plain", dict(seed=31, n=700)),
+                     ("dupts_oob", dict(seed=32, n=600, oob=24, quant=64)),
+                     ("ps01", dict(seed=33, n=300, oob=4, quant=16, ps01=True)),
+                     ("len3", dict(seed=34, n=3)),
+                     ("len4", dict(seed=35, n=4)),
+                     ("empty", dict(seed=36, n=0))]:
+        xs, ys, ts, ps = raw_event_slice(H=H, W=W, **kw)
+        for k, v in zip(("xs", "ys", "ts", "ps"), (xs, ys, ts, ps)):
+            out[f"{name}_{k}"] = v
+        for nb in (4, 16):
+            out[f"{name}_stack{nb}"] = dataset_event_stack(xs, ys, ts, ps, nb, (H, W)).contiguous()
+    xs, ys, ts, ps = raw_event_slice(seed=37, n=50, H=H, W=W)
+    ts[:] = 99.0                                                                 # one instant: ts.sum() == 0
+    for k, v in zip(("xs", "ys", "ts", "ps"), (xs, ys, ts, ps)):
+        out[f"same_ts_{k}"] = v
+    out["same_ts_stack4"] = dataset_event_stack(xs, ys, ts, ps, 4, (H, W)).contiguous()
+    out["same_ts_stack16"] = dataset_event_stack(xs, ys, ts, ps, 16, (H, W)).contiguous()
+    save("events_raw", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     dcn_zero_offset()
@@ -153,3 +207,4 @@ if __name__ == "__main__":
     fac_case("fac_k1", 23, 1, 5, 1, 10, 8)
     fac_case("fac_k5_odd", 24, 1, 2, 5, 7, 13)
     events_cases()
+    events_raw_cases()

@@ -101,3 +101,95 @@ def test_full_size_properties(enc):
     assert float(st[0].sum()) == float((ps > 0).sum()) and float(st[1].sum()) == float((ps < 0).sum())
     ch = enc.events_to_channels(xs, ys, ps, sensor_size=(H, W))
     assert torch.equal(ch, st.sum(1))
+
+
+# ---- the datasets' event path on the on-disk dtypes (h5dataset.py:327-349) ----
+RAW_CASES = ["plain", "dupts_oob", "ps01", "len3", "len4", "empty", "same_ts"]
+
+
+def _raw(g, name):
+    from gpu_util import dev
+    return [torch.from_numpy(np.ascontiguousarray(g[f"{name}_{k}"])).to(dev()) for k in ("xs", "ys", "ts", "ps")]
+
+
+@pytest.mark.parametrize("name", RAW_CASES)
+def test_raw_slices_golden(enc, name):
+    from gpu_util import n
+    g = load_golden("events_raw")
+    H, W = (int(v) for v in g["sensor"])
+    for nb in (4, 16):
+        got = enc.events_raw_to_stack(*_raw(g, name), nb, (H, W))
+        assert np.array_equal(n(got), g[f"{name}_stack{nb}"]), (name, nb)
+        ref_layout = enc.events_raw_to_stack(*_raw(g, name), nb, (H, W), bins_major=False)
+        assert np.array_equal(n(ref_layout), g[f"{name}_stack{nb}"].transpose(1, 0, 2, 3))
+
+
+def _raw_cloud(rng, N, H, W, oob=True):
+    xs = rng.integers(-2 if oob else 0, W + (2 if oob else 0), N).astype(np.int16)
+    ys = rng.integers(-1 if oob else 0, H + (1 if oob else 0), N).astype(np.int16)
+    ts = 17.0 + np.round(np.sort(rng.random(N)) * 4e5) / 1e6        # microsecond stamps over 0.4 s: duplicates
+    ps = (rng.integers(0, 2, N) * 2 - 1).astype(np.int8)
+    return xs, ys, ts.astype(np.float64), ps
+
+
+def test_raw_against_oracle_300k_events(enc, oracle):
+    from gpu_util import dev, n
+    rng = np.random.default_rng(11)
+    H, W = 72, 128
+    arrs = _raw_cloud(rng, 300_000, H, W)
+    got = enc.events_raw_to_stack(*(torch.from_numpy(a).to(dev()) for a in arrs), 16, (H, W))
+    assert np.array_equal(n(got), oracle.dataset_event_stack(*arrs, 16, (H, W)))
+
+
+def test_raw_equals_float64_path(enc):
+    """Same result as doing what the dataset does (float64 normalisation, concatenate, ps.float()) and
+    calling events_to_stack on the converted tensors."""
+    from gpu_util import dev, n
+    rng = np.random.default_rng(12)
+    H, W = 180, 240
+    xs, ys, ts, ps = _raw_cloud(rng, 500_000, H, W)
+    tn = (ts - ts[0]) / (ts[-1] - ts[0] + 1e-6)
+    d = dev()
+    want = enc.events_to_stack(torch.from_numpy(xs.astype(np.float64)).to(d), torch.from_numpy(ys.astype(np.float64)).to(d),
+                               torch.from_numpy(tn).to(d), torch.from_numpy(ps.astype(np.float32)).to(d), 16, (H, W))
+    got = enc.events_raw_to_stack(*(torch.from_numpy(a).to(d) for a in (xs, ys, ts, ps)), 16, (H, W))
+    assert np.array_equal(n(got), n(want.transpose(0, 1)))
+
+
+def test_event_slice_feeder_batches(enc, oracle):
+    from gpu_util import dev, n
+    rng = np.random.default_rng(13)
+    H, W, B = 40, 56, 16
+    feeder = enc.EventSliceFeeder(dev(), B, (H, W), max_events=1000)          # forces a staging regrow
+    for rep in range(3):                                                      # staging sets are reused
+        slices = [_raw_cloud(rng, int(k), H, W) for k in (5000, 0, 3, 12345)]
+        out = feeder.encode(slices)
+        assert out.shape == (4, B, 2, H, W)
+        for i, s in enumerate(slices):
+            assert np.array_equal(n(out[i]), oracle.dataset_event_stack(*s, B, (H, W))), (rep, i)
+
+
+def test_raw_full_size_counts(enc):
+    """10 M events on 1280x720 (BASELINE config 3 size): every in-range event is counted once per containing
+    bin; with distinct bin interiors the grand total is N + (events shared by two bins)."""
+    from gpu_util import dev
+    torch.manual_seed(0)
+    N, H, W, B = 10_000_000, 720, 1280, 16
+    d = dev()
+    xs = torch.randint(0, W, (N,), device=d, dtype=torch.int16)
+    ys = torch.randint(0, H, (N,), device=d, dtype=torch.int16)
+    ts = torch.sort(torch.rand(N, device=d, dtype=torch.float64))[0] + 5.0
+    ps = (torch.randint(0, 2, (N,), device=d, dtype=torch.int8) * 2 - 1)
+    st = enc.events_raw_to_stack(xs, ys, ts, ps, B, (H, W))
+    total = float(st.double().sum())
+    assert N <= total <= N + B                       # random float64 stamps: at most one shared event per boundary
+    assert float(st[:, 0].double().sum()) + float(st[:, 1].double().sum()) == total
+    pos = float((ps > 0).sum())
+    assert abs(float(st[:, 0].double().sum()) - pos) <= B
+
+
+def test_raw_rejects_wrong_dtypes(enc):
+    from gpu_util import dev
+    z = torch.zeros(8, device=dev())
+    with pytest.raises(RuntimeError, match="int16"):
+        enc.events_raw_to_stack(z, z, z.double(), z.to(torch.int8), 4, (4, 4))

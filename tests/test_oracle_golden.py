@@ -87,3 +87,18 @@ def test_event_stack_degenerate(oracle):
     a = np.array([1, 2, 3], np.float32)
     st, *_ = oracle.events_to_stack(a, a, np.array([0, .5, 1], np.float32), np.ones(3, np.float32), 3, (4, 4))
     assert np.array_equal(st, g["stack_len3"])
+
+
+RAW_CASES = ["plain", "dupts_oob", "ps01", "len3", "len4", "empty", "same_ts"]
+
+
+@pytest.mark.parametrize("name", RAW_CASES)
+def test_dataset_event_path_on_disk_dtypes(oracle, name):
+    """GetEvents (h5dataset.py:327-349) restated around the oracle's events_to_stack vs the reference
+    encoder run on the same int16 / int16 / float64 / int8 slices (tests/golden/make_golden.py)."""
+    g = load_golden("events_raw")
+    H, W = (int(v) for v in g["sensor"])
+    for nb in (4, 16):
+        got = oracle.dataset_event_stack(g[f"{name}_xs"], g[f"{name}_ys"], g[f"{name}_ts"], g[f"{name}_ps"], nb, (H, W))
+        assert got.shape == (nb, 2, H, W)
+        assert np.array_equal(got, g[f"{name}_stack{nb}"]), (name, nb)
