@@ -64,30 +64,63 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """SM clock and clock-event (throttle) reasons sampled DURING the timed region: NVML (the library
+    behind nvidia-smi) polled every 5 ms from a thread of this process, so that even a 100 ms region gets
+    samples; `nvidia-smi -lms` as the fallback when the NVML binding is missing."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+    def __init__(self, index, uuid=None):
+        self.rows, self.proc, self.index, self.uuid = [], None, index, uuid
+        self.nvml, self.handle, self.stop, self.source = None, None, threading.Event(), None
 
     def __enter__(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = (pynvml.nvmlDeviceGetHandleByUUID(self.uuid) if self.uuid
+                           else pynvml.nvmlDeviceGetHandleByIndex(self.index))
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml, self.source = pynvml, "nvml"
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return self
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             self.th = threading.Thread(target=self._pump, daemon=True)
             self.th.start()
         except OSError:
             self.proc = None
         return self
 
+    def _poll(self):
+        n = self.nvml
+        bits = [n.nvmlClocksEventReasonHwSlowdown, n.nvmlClocksEventReasonHwThermalSlowdown,
+                n.nvmlClocksEventReasonSwThermalSlowdown, n.nvmlClocksEventReasonSwPowerCap]
+        while not self.stop.is_set():
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                self.rows.append([str(mhz), str(self.max_mhz)] + ["Active" if r & b else "Not Active" for b in bits])
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def __exit__(self, *a):
-        if self.proc:
+        if self.nvml:
+            self.stop.set()
+            self.th.join(timeout=2)
+        elif self.proc:
             time.sleep(0.25)
             self.proc.terminate()
             self.th.join(timeout=2)
@@ -95,12 +128,18 @@ class ClockSampler:
     def summary(self):
         sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples (NVML and nvidia-smi unavailable)"]}
         mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i] == "Active" for r in self.rows)]
+        reasons = [n for i, n in enumerate(self.NAMES) if any(len(r) >= 6 and r[2 + i] == "Active" for r in self.rows)]
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "source": self.source}
+
+
+def _gpu_uuid(torch, dev):
+    try:
+        return "GPU-" + str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        return None
 
 
 def make_inputs(torch, dev, seed):
@@ -162,7 +201,7 @@ def run_ours(args):
         dist.barrier()
     torch.cuda.synchronize()
     marks, t0, t1 = [], ev(), ev()
-    with ClockSampler(local) as clk:
+    with ClockSampler(local, _gpu_uuid(torch, dev)) as clk:
         t0.record()
         for _ in range(args.steps):
             step(marks)
@@ -261,7 +300,27 @@ def run_ours(args):
                                   "algorithmic_GBps": round((16 * NEV + 4 * 5 * EH * EW) / (t_vox * 1e-3) / 1e9, 1)},
                   "stack_16bins": {"ms": round(t_stk, 4), "Mev_s": round(NEV / 1e6 / (t_stk * 1e-3), 1),
                                    "algorithmic_GBps": round((16 * NEV + 4 * 32 * EH * EW) / (t_stk * 1e-3) / 1e9, 1)}}
-        del exs, eys, ets, eps_
+        # the datasets' path on the on-disk dtypes (int16, int16, float64, int8): device-resident, and end to end
+        # from pageable numpy arrays (what h5py returns) through the pinned staging of EventSliceFeeder
+        rxs, rys = exs.to(torch.int16), eys.to(torch.int16)
+        rts = torch.sort(torch.rand(NEV, generator=g, dtype=torch.float64))[0].to(dev) * 0.5 + 100.0
+        rps = eps_.to(torch.int8)
+        t_raw = timed(lambda: encodings.events_raw_to_stack(rxs, rys, rts, rps, 16, (EH, EW)), n=10)
+        feeder = encodings.EventSliceFeeder(dev, 16, (EH, EW), max_events=NEV)
+        host_slice = tuple(t.cpu().numpy() for t in (rxs, rys, rts, rps))
+        for _ in range(2):
+            feeder.encode([host_slice]); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            feeder.encode([host_slice])
+        torch.cuda.synchronize()
+        t_feed = (time.perf_counter() - t0) / 3 * 1e3
+        events["raw_stack_16bins"] = {"ms": round(t_raw, 4), "Mev_s": round(NEV / 1e6 / (t_raw * 1e-3), 1),
+                                      "algorithmic_GBps": round((13 * NEV + 4 * 32 * EH * EW) / (t_raw * 1e-3) / 1e9, 1),
+                                      "host_numpy_to_stack_ms": round(t_feed, 2),
+                                      "host_numpy_to_stack_Mev_s": round(NEV / 1e6 / (t_feed * 1e-3), 1),
+                                      "h2d_bytes": 13 * NEV}
+        del exs, eys, ets, eps_, rxs, rys, rts, rps, feeder
 
     if rank != 0:
         if world > 1:
@@ -308,9 +367,59 @@ def run_ours(args):
     }
     if world == 1 and not (args.no_cpu_baseline or args.kernels_only):
         line["cpu_baseline"] = cpu_baseline(budget_s=20.0)
+        ref_gpu = reference_cuda_kernels(torch, d, timed)
+        if ref_gpu:
+            line["cpu_baseline"]["reference_cuda_kernels_sm100a"] = ref_gpu
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _load_ref_ext(subdir, name):
+    import importlib.util
+    d = os.path.join(ROOT, "oracle", "_ref", subdir)
+    for f in (os.listdir(d) if os.path.isdir(d) else []):
+        if f.startswith(name + ".") and f.endswith(".so"):
+            spec = importlib.util.spec_from_file_location(name, os.path.join(d, f))
+            mod = importlib.util.module_from_spec(spec)
+            try:
+                spec.loader.exec_module(mod)
+                return mod
+            except ImportError:
+                return None
+    return None
+
+
+def reference_cuda_kernels(torch, d, timed):
+    """the reference's OWN CUDA kernels (dcn_v2_im2col_cuda.cu, KernelConv2D_kernel.cu),
+    compiled unmodified for sm_100a by oracle/build_ref.py, on the same device-resident inputs as the step:
+    the GPU-side baseline reported beside the CPU one. Not part of any product path."""
+    ref_d, ref_f = _load_ref_ext("dcn_cuda", "_ext_cuda_ref"), _load_ref_ext("fac_cuda", "kernelconv2d_cuda")
+    if ref_d is None or ref_f is None:
+        return None
+    geom = (3, 3, 1, 1, 1, 1, 1, 1, DG)
+    allow = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False          # the reference's SGEMMs are fp32
+    try:
+        t = {"dcn_fwd": timed(lambda: ref_d.dcn_v2_forward(d["x"], d["w"], d["b"], d["off"], d["msk"], *geom), n=5),
+             "dcn_bwd": timed(lambda: ref_d.dcn_v2_backward(d["x"], d["w"], d["b"], d["off"], d["msk"], d["go_d"], *geom), n=5)}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = allow
+
+    def fac_fwd():                                         # KernelConv2D.py:35-37: zeroed output, then the kernel
+        out = torch.zeros(B_FAC, C, H, W, device=d["xi"].device)
+        ref_f.forward(d["xi"], d["ker"], K_FAC, out)
+
+    def fac_bwd():                                         # KernelConv2D.py:50-53
+        gi, gk = torch.zeros_like(d["xi"]), torch.zeros_like(d["ker"])
+        ref_f.backward(d["xi"], d["ker"], K_FAC, d["go_f"], gi, gk)
+
+    t["fac_fwd"], t["fac_bwd"] = timed(fac_fwd, n=5), timed(fac_bwd, n=5)
+    total = sum(t.values())
+    return {"ms": {k: round(v, 4) for k, v in t.items()}, "ms_per_step": round(total, 4),
+            "value": round(MPIX_PER_STEP / (total * 1e-3), 2), "unit": "Mpix/s",
+            "note": "reference .cu files compiled for sm_100a + its host sequence (cuBLAS fp32 GEMMs, column buffer, "
+                    "zero-filled FAC outputs); L2 flushed before each call"}
 
 
 # ---------------------------------------------------------------- CPU arms ---
@@ -374,7 +483,12 @@ def cpu_baseline(budget_s=20.0):
     ets = np.sort(rng.random(n_ev)).astype(np.float32); eps_ = (rng.integers(0, 2, n_ev) * 2 - 1).astype(np.float32)
     t0 = time.perf_counter(); oracle.events_to_voxel(exs, eys, ets, eps_, 5, (720, 1280)); t_v = time.perf_counter() - t0
     t0 = time.perf_counter(); oracle.events_to_stack(exs, eys, ets, eps_, 16, (720, 1280)); t_s = time.perf_counter() - t0
+    rts = 100.0 + 0.5 * np.sort(rng.random(n_ev))
+    t0 = time.perf_counter()
+    oracle.dataset_event_stack(exs.astype(np.int16), eys.astype(np.int16), rts, eps_.astype(np.int8), 16, (720, 1280))
+    t_r = time.perf_counter() - t0
     return {"events_voxel_5bins_Mev_s": round(n_ev / 1e6 / t_v, 2), "events_stack_16bins_Mev_s": round(n_ev / 1e6 / t_s, 2),
+            "events_dataset_path_16bins_Mev_s": round(n_ev / 1e6 / t_r, 2),
             "value": round(mpix / (td + tf), 5), "unit": "Mpix/s", "cores": torch.get_num_threads(),
             "kind": "reference" if ref_dcn is not None else "port",
             "sample": f"top {rows} of 256 rows of the same step (DCN B=1 + FAC B=4, fwd+bwd): "

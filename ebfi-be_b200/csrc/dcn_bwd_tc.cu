@@ -66,6 +66,7 @@ __device__ __forceinline__ void st_bf16x8(unsigned char *base, int off, const un
     *reinterpret_cast<uint4 *>(base + off) = make_uint4(a, b, c, e);
 }
 
+template <bool PACKED>
 __global__ void __launch_bounds__(NTHR, 2)
 dcn_bwd_tc_kernel(const float *__restrict__ in_blk, const float *__restrict__ weight,
                   const float *__restrict__ offset, const float *__restrict__ mask,
@@ -178,8 +179,9 @@ dcn_bwd_tc_kernel(const float *__restrict__ in_blk, const float *__restrict__ we
             umma::commit(&bar1);
         }
         // ---- sampling positions of this thread's taps (overlaps GEMM1)
-        const float *off_bg = off_ptr(d, offset, b, g, plane);
-        const float *mask_bg = mask_ptr(d, mask, b, g, plane);
+        // element offsets of this (sample, group) inside offset / mask AND inside their gradients (same layout)
+        const size_t off_e = (size_t)b * d.off_bs + (size_t)g * 2 * d.KK * plane;
+        const size_t mask_e = (size_t)b * d.mask_bs + (size_t)g * d.KK * plane;
         umma::mbar_wait(&bar1, ph1);                 // D1 complete; P is dead, its storage becomes `col`
         ph1 ^= 1;
         umma::fence_after_sync();
@@ -195,8 +197,8 @@ dcn_bwd_tc_kernel(const float *__restrict__ in_blk, const float *__restrict__ we
             for (int j = 0; j < 8; ++j) colv[j] = 0.f;
             if (valid) {
                 float dy, dx, m;
-                tap_read(off_bg, mask_bg, uplane, (unsigned)t, (unsigned)pix, dy, dx, m);
-                m = mask_act(d, m);
+                tap_read(offset + off_e, mask + mask_e, uplane, (unsigned)t, (unsigned)pix, dy, dx, m);
+                m = mask_act_t<PACKED>(m);
                 const float y = (float)(ho * d.sh - d.ph + ti * d.dh) + dy;
                 const float x = (float)(wo * d.sw - d.pw + tj * d.dw) + dx;
                 const float xq = (float)(wo * d.sw - d.ph + tj * d.dw) + dx;   // the scatter's x uses pad_h (im2col_cuda.cu:368)
@@ -232,9 +234,9 @@ dcn_bwd_tc_kernel(const float *__restrict__ in_blk, const float *__restrict__ we
                     if (tq.c10) red_add_v4(gb + (size_t)tq.i10 * CS + 4 * h, q3 * tt[0], q3 * tt[1], q3 * tt[2], q3 * tt[3]);
                     if (tq.c11) red_add_v4(gb + (size_t)tq.i11 * CS + 4 * h, q4 * tt[0], q4 * tt[1], q4 * tt[2], q4 * tt[3]);
                 }
-                float *gy = goff + (size_t)b * d.off_bs + ((size_t)g * 2 * d.KK + 2 * t) * plane + pix;
-                gy[0] = s_y; gy[plane] = s_x;
-                gmask[(size_t)b * d.mask_bs + ((size_t)g * d.KK + t) * plane + pix] = s_m * mask_act_grad(d, m);
+                float *gy = goff + off_e + (2u * t * uplane + (unsigned)pix);
+                gy[0] = s_y; gy[uplane] = s_x;
+                gmask[mask_e + ((unsigned)t * uplane + (unsigned)pix)] = s_m * mask_act_grad_t<PACKED>(m);
             }
             // column operand: col[k' = t*8+cc][px = p]; rows t*8..t*8+7 are one 8-row group
             const int off = t * pl.col_sbo + (p >> 3) * COL_LBO + (p & 7) * 2;
@@ -404,9 +406,14 @@ int backward_tc(cudaStream_t st, const DcnDims &d, const float *input, const flo
     const unsigned tgrid = (unsigned)std::min<size_t>(ceil_div((size_t)BG * HW, (size_t)256), (size_t)ebfi::sm_count() * 16);
     if (int rc = launch_nchw_to_blocked(st, input, in_blk, BG, HW)) return rc;
     EBFI_CUDA_OK(cudaMemsetAsync(gin_blk, 0, n * sizeof(float), st));
-    EBFI_CUDA_OK(cudaFuncSetAttribute(dcn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
     dim3 grid(S, d.dg);
-    dcn_bwd_tc_kernel<<<grid, NTHR, pl.smem, st>>>(in_blk, weight, offset, mask, gout, gin_blk, goff, gmask, gw_part, gb_part, d, pl);
+    if (d.packed) {
+        EBFI_CUDA_OK(cudaFuncSetAttribute(dcn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
+        dcn_bwd_tc_kernel<true><<<grid, NTHR, pl.smem, st>>>(in_blk, weight, offset, mask, gout, gin_blk, goff, gmask, gw_part, gb_part, d, pl);
+    } else {
+        EBFI_CUDA_OK(cudaFuncSetAttribute(dcn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
+        dcn_bwd_tc_kernel<false><<<grid, NTHR, pl.smem, st>>>(in_blk, weight, offset, mask, gout, gin_blk, goff, gmask, gw_part, gb_part, d, pl);
+    }
     EBFI_LAUNCH_OK("dcn_bwd_tc_kernel");
     blocked_to_nchw<<<tgrid, 256, 0, st>>>(gin_blk, gin, BG, HW);
     EBFI_LAUNCH_OK("blocked_to_nchw");

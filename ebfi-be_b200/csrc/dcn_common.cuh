@@ -37,6 +37,15 @@ __device__ __forceinline__ float mask_act(const DcnDims &d, float raw)
 {
     return d.packed ? 1.f / (1.f + expf(-raw)) : raw;
 }
+// compile-time variants for the tensor-core kernels (no branch / flag register in their inner loops)
+template <bool PACKED> __device__ __forceinline__ float mask_act_t(float raw)
+{
+    return PACKED ? 1.f / (1.f + expf(-raw)) : raw;
+}
+template <bool PACKED> __device__ __forceinline__ float mask_act_grad_t(float m)
+{
+    return PACKED ? m * (1.f - m) : 1.f;
+}
 // d(mask_act)/d(raw) given the activated value
 __device__ __forceinline__ float mask_act_grad(const DcnDims &d, float m)
 {

@@ -51,7 +51,7 @@ struct FwdPlan {
 };
 
 
-template <int TPR>
+template <int TPR, bool PACKED>
 __global__ void __launch_bounds__(NTHR, 2)
 dcn_fwd_tc_kernel(const float *__restrict__ in_blk,
                   const float *__restrict__ bias, const float *__restrict__ offset,
@@ -167,8 +167,8 @@ dcn_fwd_tc_kernel(const float *__restrict__ in_blk,
             for (int s = 0; s < TPR; ++s) {
                 sy[s] = tv[s] ? by[s] + ndy[s] : -2.f;
                 sx[s] = tv[s] ? bx[s] + ndx[s] : -2.f;
-                sm[s] = mask_act(d, nm[s]);
-                asum += fabsf(ndy[s]) + fabsf(ndx[s]);       // invalid taps hold zeros
+                sm[s] = mask_act_t<PACKED>(nm[s]);
+                if (PACKED) asum += fabsf(ndy[s]) + fabsf(ndx[s]);       // invalid taps hold zeros
             }
             if (g + 1 < d.dg) fetch_group(g + 1);
             for (int ci = 0; ci < pl.ncs; ++ci) {
@@ -209,7 +209,7 @@ dcn_fwd_tc_kernel(const float *__restrict__ in_blk,
                 }
             }
         }
-        if (d.abs_sum) warp_atomic_sum(d.abs_sum, asum);
+        if (PACKED && d.abs_sum) warp_atomic_sum(d.abs_sum, asum);
         // ---- all MMAs complete (commits complete in order: the last one covers everything)
         umma::mbar_wait(&bar_free[(n - 1) & 1], (uint32_t)(((n - 1) >> 1) & 1));
         umma::fence_after_sync();
@@ -309,8 +309,13 @@ int forward_tc(cudaStream_t st, const DcnDims &d, const float *input, const floa
     const unsigned grid = (unsigned)(d.B * pl.tiles_x * pl.tiles_y);
 #define EBFI_FWD_TC(T)                                                                                        \
     do {                                                                                                      \
-        EBFI_CUDA_OK(cudaFuncSetAttribute(dcn_fwd_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem)); \
-        dcn_fwd_tc_kernel<T><<<grid, NTHR, pl.smem, st>>>(in_blk, bias, offset, mask, output, wimg, d, pl);  \
+        if (d.packed) {                                                                                       \
+            EBFI_CUDA_OK(cudaFuncSetAttribute(dcn_fwd_tc_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem)); \
+            dcn_fwd_tc_kernel<T, true><<<grid, NTHR, pl.smem, st>>>(in_blk, bias, offset, mask, output, wimg, d, pl); \
+        } else {                                                                                              \
+            EBFI_CUDA_OK(cudaFuncSetAttribute(dcn_fwd_tc_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem)); \
+            dcn_fwd_tc_kernel<T, false><<<grid, NTHR, pl.smem, st>>>(in_blk, bias, offset, mask, output, wimg, d, pl); \
+        }                                                                                                     \
     } while (0)
     switch (pl.TPR) {
     case 1: EBFI_FWD_TC(1); break;
