@@ -21,8 +21,10 @@ class DcnGeom(ctypes.Structure):
     """`ebfi_dcn_geom`."""
     _fields_ = [(n, c_int) for n in (
         "batch", "channels", "height", "width", "channels_out", "kernel_h", "kernel_w",
-        "stride_h", "stride_w", "pad_h", "pad_w", "dilation_h", "dilation_w", "deformable_group")]
+        "stride_h", "stride_w", "pad_h", "pad_w", "dilation_h", "dilation_w", "deformable_group", "flags")]
 
+
+EBFI_DCN_DETERMINISTIC = 1
 
 # name -> (restype, argtypes); must list every symbol include/ebfi_b200.h declares
 _GEOM_P = ctypes.POINTER(DcnGeom)
@@ -66,7 +68,7 @@ def load():
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)      # AttributeError here = header/library mismatch
         fn.restype, fn.argtypes = res, args
-    if lib.ebfi_abi_version() != 1:
+    if lib.ebfi_abi_version() != 2:
         raise RuntimeError("libebfi_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -147,6 +147,7 @@ dcn_fwd_kernel(const float *__restrict__ input, const float *__restrict__ weight
 // grad_mask, grad_input for its chunk; every ct accumulates its [COT x KC] grad_weight
 // partial in registers across all its tiles and writes it once at the end.
 // Partials: gw_part[S][Co][Kdim], gb_part[S][Co] -> dcn_reduce_partials (fixed order).
+template <bool DET>
 __global__ void __launch_bounds__(NT)
 dcn_bwd_kernel(const float *__restrict__ input, const float *__restrict__ weight,
                const float *__restrict__ offset, const float *__restrict__ mask,
@@ -171,6 +172,7 @@ dcn_bwd_kernel(const float *__restrict__ input, const float *__restrict__ weight
     const size_t plane = (size_t)npix, in_plane = (size_t)d.H * d.W;
     const int n_cot = gridDim.z;
 
+    const float det_scale = DET ? ldexpf(1.f, det_scale_exp(d)) : 0.f;   // DET: `gin` is the int64 fixed-point copy
     const int kq = tid % 16, cq = tid / 16;      // grad_weight: rows kq+16i, 4 co per thread
     float gw_acc[4][KC_MAX / 16];
 #pragma unroll
@@ -261,10 +263,18 @@ dcn_bwd_kernel(const float *__restrict__ input, const float *__restrict__ weight
                     s_y += wy * top;
                     s_x += wx * top;
                     // grad_input scatter (:236-251), x position with pad_h
-                    if (tq.c00) atomicAdd(gp + tq.i00, q1 * top);
-                    if (tq.c01) atomicAdd(gp + tq.i01, q2 * top);
-                    if (tq.c10) atomicAdd(gp + tq.i10, q3 * top);
-                    if (tq.c11) atomicAdd(gp + tq.i11, q4 * top);
+                    if (DET) {
+                        long long *gp64 = reinterpret_cast<long long *>(gin) + ((size_t)b * d.C + c0 + cc) * in_plane;
+                        if (tq.c00) det_add(gp64 + tq.i00, q1 * top, det_scale);
+                        if (tq.c01) det_add(gp64 + tq.i01, q2 * top, det_scale);
+                        if (tq.c10) det_add(gp64 + tq.i10, q3 * top, det_scale);
+                        if (tq.c11) det_add(gp64 + tq.i11, q4 * top, det_scale);
+                    } else {
+                        if (tq.c00) atomicAdd(gp + tq.i00, q1 * top);
+                        if (tq.c01) atomicAdd(gp + tq.i01, q2 * top);
+                        if (tq.c10) atomicAdd(gp + tq.i10, q3 * top);
+                        if (tq.c11) atomicAdd(gp + tq.i11, q4 * top);
+                    }
                 }
                 *cell = val * m;                                          // column for grad_weight
             }
@@ -334,6 +344,42 @@ __global__ void dcn_reduce_partials(const float *__restrict__ gw_part, const flo
     }
 }
 
+// ---- deterministic mode (EBFI_DCN_DETERMINISTIC): bound of a single grad_input contribution ----
+__device__ __forceinline__ void atomic_max_nonneg(float *dst, float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int *>(dst), __float_as_int(v));   // v >= 0: int order == float order
+}
+
+__global__ void dcn_det_bound(const float *__restrict__ gout, const float *__restrict__ weight,
+                              const float *__restrict__ mask, float *__restrict__ bound, DcnDims d)
+{
+    const size_t plane = (size_t)d.Ho * d.Wo, tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t nthr = (size_t)gridDim.x * blockDim.x;
+    float m0 = 0.f, m1 = 0.f, m2 = d.packed ? 1.f : 0.f;           // sigmoid(logit) <= 1
+    for (size_t i = tid; i < (size_t)d.B * plane; i += nthr) {      // max over pixels of sum_co |gO|
+        const size_t b = i / plane, pix = i - b * plane;
+        float a = 0.f;
+        for (int co = 0; co < d.Co; ++co) a += fabsf(__ldg(gout + (b * d.Co + co) * plane + pix));
+        m0 = fmaxf(m0, a);
+    }
+    for (size_t i = tid; i < (size_t)d.Co * d.C * d.KK; i += nthr) m1 = fmaxf(m1, fabsf(__ldg(weight + i)));
+    if (!d.packed)
+        for (size_t i = tid; i < (size_t)d.B * d.mask_bs; i += nthr) m2 = fmaxf(m2, fabsf(__ldg(mask + i)));
+    atomic_max_nonneg(bound + 0, m0);
+    atomic_max_nonneg(bound + 1, m1);
+    atomic_max_nonneg(bound + 2, m2);
+}
+
+// int64 fixed point -> fp32, one rounding per element (CUDA-core path: NCHW in, NCHW out)
+__global__ void dcn_i64_to_f32(const long long *__restrict__ src, float *__restrict__ dst, size_t n, DcnDims d)
+{
+    const float inv = ldexpf(1.f, -det_scale_exp(d));
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = __ll2float_rn(src[i]) * inv;
+}
+
 int fill_dims(const ebfi_dcn_geom *q, DcnDims &d)
 {
     EBFI_REQUIRE(q != nullptr, "dcn: null geometry");
@@ -355,6 +401,13 @@ int fill_dims(const ebfi_dcn_geom *q, DcnDims &d)
     EBFI_REQUIRE(d.B <= 65535 && ceil_div(d.Co, COT) <= 65535, "dcn: batch / Cout too large for the grid");
     const long long taps = (long long)d.dg * d.KK * Ho * Wo;
     d.off_bs = 2 * taps; d.mask_bs = taps; d.packed = 0; d.abs_sum = nullptr;
+    EBFI_REQUIRE((q->flags & ~EBFI_DCN_DETERMINISTIC) == 0, "dcn: unknown flags 0x%x", q->flags);
+    d.det = (q->flags & EBFI_DCN_DETERMINISTIC) ? 1 : 0;
+    d.det_bound = nullptr;
+    // an element of grad_input receives at most one contribution per (output pixel, tap) of its sample
+    int bits = 1;
+    while (((long long)1 << bits) < (long long)Ho * Wo * d.KK) ++bits;
+    d.det_head = 61 - bits;
     return EBFI_OK;
 }
 
@@ -402,8 +455,9 @@ size_t ebfi_dcnv2_backward_workspace_bytes(const ebfi_dcn_geom *q)
     DcnDims d{};
     if (fill_dims(q, d) != EBFI_OK) return 0;
     const size_t S = (size_t)std::max(bwd_splits(d), backward_tc_splits(d));
+    const size_t det = d.det ? 256 + (size_t)d.B * d.C * d.H * d.W * sizeof(long long) : 0;   // bound + CUDA-core int64 copy
     return ebfi::round_up(S * ((size_t)d.Co * d.C * d.KK + d.Co) * sizeof(float), (size_t)256) +
-           backward_tc_scratch_bytes(d) + 256;
+           std::max(backward_tc_scratch_bytes(d), det) + 512;
 }
 
 size_t ebfi_dcnv2_forward_workspace_bytes(const ebfi_dcn_geom *q)
@@ -434,7 +488,7 @@ static int run_forward(void *stream, const DcnDims &d, const float *input, const
     return EBFI_OK;
 }
 
-static int run_backward(void *stream, const DcnDims &d, const float *input, const float *weight,
+static int run_backward(void *stream, const DcnDims &d_in, const float *input, const float *weight,
                         const float *offset, const float *mask,
                         const float *grad_output, float *grad_input, float *grad_offset,
                         float *grad_mask, float *grad_weight, float *grad_bias,
@@ -443,34 +497,58 @@ static int run_backward(void *stream, const DcnDims &d, const float *input, cons
     EBFI_REQUIRE(input && weight && offset && mask && grad_output && grad_input && grad_offset &&
                  grad_mask && grad_weight && grad_bias, "dcn_backward: null pointer");
     cudaStream_t st = ebfi::as_stream(stream);
+    DcnDims d = d_in;
     const char *impl = getenv("EBFI_DCN_IMPL");
     const int S_tc = (impl && impl[0] == 's') ? 0 : backward_tc_splits(d);
     const int S = S_tc > 0 ? S_tc : bwd_splits(d);
     const size_t n_w = (size_t)d.Co * d.C * d.KK, n_b = (size_t)d.Co;
+    const size_t n_in = (size_t)d.B * d.C * d.H * d.W;
+    // workspace: [grad_weight / grad_bias partials][scratch][deterministic mode: 3-float bound]
     const size_t part_bytes = ebfi::round_up((size_t)S * (n_w + n_b) * sizeof(float), (size_t)256);
-    const size_t need = part_bytes + (S_tc > 0 ? backward_tc_scratch_bytes(d) : 0);
+    const size_t scratch_bytes = ebfi::round_up(
+        S_tc > 0 ? backward_tc_scratch_bytes(d) : (d.det ? n_in * sizeof(long long) : 0), (size_t)256);
+    const size_t need = part_bytes + scratch_bytes + (d.det ? 256 : 0);
     if (!workspace || workspace_bytes < need)
         return ebfi::fail(EBFI_ERR_WORKSPACE, "dcn_backward: workspace %zu < %zu bytes", workspace_bytes, need);
     EBFI_REQUIRE(ebfi::aligned16(workspace), "dcn_backward: workspace must be 16-byte aligned");
     float *gw_part = static_cast<float *>(workspace);
     float *gb_part = gw_part + (size_t)S * n_w;
+    char *scratch = static_cast<char *>(workspace) + part_bytes;
+    if (d.det) {
+        float *bound = reinterpret_cast<float *>(scratch + scratch_bytes);
+        EBFI_CUDA_OK(cudaMemsetAsync(bound, 0, 3 * sizeof(float), st));
+        dcn_det_bound<<<ebfi::sm_count() * 4, 256, 0, st>>>(grad_output, weight, mask, bound, d);
+        EBFI_LAUNCH_OK("dcn_det_bound");
+        d.det_bound = bound;
+    }
     if (S_tc > 0) {
         // tensor-core path (dcn_bwd_tc.cu): cpg == 8, Cout == 64
         if (int rc = backward_tc(st, d, input, weight, offset, mask, grad_output, grad_input, grad_offset, grad_mask,
-                                 gw_part, gb_part, S, static_cast<char *>(workspace) + part_bytes))
+                                 gw_part, gb_part, S, scratch))
             return rc;
     } else {
-        EBFI_CUDA_OK(cudaMemsetAsync(grad_input, 0, (size_t)d.B * d.C * d.H * d.W * sizeof(float), st));
-        EBFI_CUDA_OK(cudaFuncSetAttribute(dcn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
+        // deterministic mode accumulates into an int64 NCHW copy in the scratch and converts at the end
+        float *gin_acc = d.det ? reinterpret_cast<float *>(scratch) : grad_input;
+        EBFI_CUDA_OK(cudaMemsetAsync(gin_acc, 0, n_in * (d.det ? sizeof(long long) : sizeof(float)), st));
+        EBFI_CUDA_OK(cudaFuncSetAttribute(dcn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
+        EBFI_CUDA_OK(cudaFuncSetAttribute(dcn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
         const int n_cot = ceil_div(d.Co, COT);
         // Chunks of one group accumulate into the same grad_offset / grad_mask elements; separate,
         // stream-ordered launches keep that read-modify-write race-free. nchunk is 1 unless
         // channels-per-group * taps exceeds the KC_MAX-row slab.
         for (int ch = 0; ch < d.nchunk; ++ch) {
             dim3 grid(S, d.dg, n_cot);
-            dcn_bwd_kernel<<<grid, NT, kBwdSmem, st>>>(input, weight, offset, mask, grad_output, grad_input,
-                                                       grad_offset, grad_mask, gw_part, gb_part, d, ch);
+            if (d.det)
+                dcn_bwd_kernel<true><<<grid, NT, kBwdSmem, st>>>(input, weight, offset, mask, grad_output, gin_acc,
+                                                                 grad_offset, grad_mask, gw_part, gb_part, d, ch);
+            else
+                dcn_bwd_kernel<false><<<grid, NT, kBwdSmem, st>>>(input, weight, offset, mask, grad_output, gin_acc,
+                                                                  grad_offset, grad_mask, gw_part, gb_part, d, ch);
             EBFI_LAUNCH_OK("dcn_bwd_kernel");
+        }
+        if (d.det) {
+            dcn_i64_to_f32<<<ebfi::sm_count() * 8, 256, 0, st>>>(reinterpret_cast<const long long *>(gin_acc), grad_input, n_in, d);
+            EBFI_LAUNCH_OK("dcn_i64_to_f32");
         }
     }
     const int n = (int)(n_w + n_b);

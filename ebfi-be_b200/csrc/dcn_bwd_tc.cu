@@ -66,7 +66,7 @@ __device__ __forceinline__ void st_bf16x8(unsigned char *base, int off, const un
     *reinterpret_cast<uint4 *>(base + off) = make_uint4(a, b, c, e);
 }
 
-template <bool PACKED>
+template <bool PACKED, bool DET>
 __global__ void __launch_bounds__(NTHR, 2)
 dcn_bwd_tc_kernel(const float *__restrict__ in_blk, const float *__restrict__ weight,
                   const float *__restrict__ offset, const float *__restrict__ mask,
@@ -115,6 +115,7 @@ dcn_bwd_tc_kernel(const float *__restrict__ in_blk, const float *__restrict__ we
     const uint32_t lane_base = (uint32_t)(warp & 3) * 32u;
 
     const unsigned uplane = (unsigned)plane;
+    const float det_scale = DET ? ldexpf(1.f, det_scale_exp(d)) : 0.f;
 
     uint32_t ph1 = 0, ph3 = 0;
     int ntiles_done = 0;
@@ -225,9 +226,20 @@ dcn_bwd_tc_kernel(const float *__restrict__ in_blk, const float *__restrict__ we
                     s_x += wx * top[cc];
                     colv[cc] = val * m;
                 }
-                // grad_input scatter (:236-251): 16-byte vector reductions, two per corner
+                // grad_input scatter (:236-251): 16-byte vector reductions, two per corner; deterministic mode:
+                // scalar 64-bit integer reductions into the fixed-point copy
+                if (DET) {
+                    long long *g64 = reinterpret_cast<long long *>(gin_blk) + ((size_t)b * d.dg + g) * in_plane * CS;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
+                    for (int cc = 0; cc < CS; ++cc) {
+                        if (tq.c00) det_add(g64 + (size_t)tq.i00 * CS + cc, q1 * top[cc], det_scale);
+                        if (tq.c01) det_add(g64 + (size_t)tq.i01 * CS + cc, q2 * top[cc], det_scale);
+                        if (tq.c10) det_add(g64 + (size_t)tq.i10 * CS + cc, q3 * top[cc], det_scale);
+                        if (tq.c11) det_add(g64 + (size_t)tq.i11 * CS + cc, q4 * top[cc], det_scale);
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < (DET ? 0 : 2); ++h) {
                     const float *tt = top + 4 * h;
                     if (tq.c00) red_add_v4(gb + (size_t)tq.i00 * CS + 4 * h, q1 * tt[0], q1 * tt[1], q1 * tt[2], q1 * tt[3]);
                     if (tq.c01) red_add_v4(gb + (size_t)tq.i01 * CS + 4 * h, q2 * tt[0], q2 * tt[1], q2 * tt[2], q2 * tt[3]);
@@ -344,6 +356,24 @@ __global__ void blocked_to_nchw(const float *__restrict__ src, float *__restrict
     }
 }
 
+// fixed-point (BG, HW, 8) int64 -> fp32 NCHW: one rounding per element
+__global__ void blocked_i64_to_nchw(const long long *__restrict__ src, float *__restrict__ dst, int BG, int HW, DcnDims d)
+{
+    const float inv = ldexpf(1.f, -det_scale_exp(d));
+    const size_t n = (size_t)BG * HW;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t bg = i / HW, px = i - bg * HW;
+        const longlong2 *sp = reinterpret_cast<const longlong2 *>(src + i * CS);
+        float *dp = dst + bg * CS * HW + px;
+#pragma unroll
+        for (int c = 0; c < CS / 2; ++c) {
+            const longlong2 v = sp[c];
+            dp[(size_t)(2 * c) * HW] = __ll2float_rn(v.x) * inv;
+            dp[(size_t)(2 * c + 1) * HW] = __ll2float_rn(v.y) * inv;
+        }
+    }
+}
+
 bool make_plan(const DcnDims &d, BwdPlan &pl)
 {
     if (d.cpg != CS || d.Co != 64) return false;          // other shapes: CUDA-core kernel in dcn.cu
@@ -388,7 +418,7 @@ size_t backward_tc_scratch_bytes(const DcnDims &d)
 {
     BwdPlan pl{};
     if (!make_plan(d, pl)) return 0;
-    return 2 * (size_t)d.B * d.C * d.H * d.W * sizeof(float);
+    return (d.det ? 3 : 2) * (size_t)d.B * d.C * d.H * d.W * sizeof(float);     // int64 grad_input copy when deterministic
 }
 
 // Tensor-core backward: writes grad_input / grad_offset / grad_mask in full and the partials
@@ -405,16 +435,23 @@ int backward_tc(cudaStream_t st, const DcnDims &d, const float *input, const flo
     const int BG = d.B * d.dg, HW = d.H * d.W;
     const unsigned tgrid = (unsigned)std::min<size_t>(ceil_div((size_t)BG * HW, (size_t)256), (size_t)ebfi::sm_count() * 16);
     if (int rc = launch_nchw_to_blocked(st, input, in_blk, BG, HW)) return rc;
-    EBFI_CUDA_OK(cudaMemsetAsync(gin_blk, 0, n * sizeof(float), st));
+    EBFI_CUDA_OK(cudaMemsetAsync(gin_blk, 0, n * (d.det ? sizeof(long long) : sizeof(float)), st));
     dim3 grid(S, d.dg);
-    if (d.packed) {
-        EBFI_CUDA_OK(cudaFuncSetAttribute(dcn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
-        dcn_bwd_tc_kernel<true><<<grid, NTHR, pl.smem, st>>>(in_blk, weight, offset, mask, gout, gin_blk, goff, gmask, gw_part, gb_part, d, pl);
-    } else {
-        EBFI_CUDA_OK(cudaFuncSetAttribute(dcn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
-        dcn_bwd_tc_kernel<false><<<grid, NTHR, pl.smem, st>>>(in_blk, weight, offset, mask, gout, gin_blk, goff, gmask, gw_part, gb_part, d, pl);
-    }
+#define EBFI_BWD_TC(P, D)                                                                                     \
+    do {                                                                                                      \
+        EBFI_CUDA_OK(cudaFuncSetAttribute(dcn_bwd_tc_kernel<P, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem)); \
+        dcn_bwd_tc_kernel<P, D><<<grid, NTHR, pl.smem, st>>>(in_blk, weight, offset, mask, gout, gin_blk, goff, gmask, \
+                                                             gw_part, gb_part, d, pl);                        \
+    } while (0)
+    if (d.det) { if (d.packed) EBFI_BWD_TC(true, true); else EBFI_BWD_TC(false, true); }
+    else       { if (d.packed) EBFI_BWD_TC(true, false); else EBFI_BWD_TC(false, false); }
+#undef EBFI_BWD_TC
     EBFI_LAUNCH_OK("dcn_bwd_tc_kernel");
+    if (d.det) {
+        blocked_i64_to_nchw<<<tgrid, 256, 0, st>>>(reinterpret_cast<const long long *>(gin_blk), gin, BG, HW, d);
+        EBFI_LAUNCH_OK("blocked_i64_to_nchw");
+        return EBFI_OK;
+    }
     blocked_to_nchw<<<tgrid, 256, 0, st>>>(gin_blk, gin, BG, HW);
     EBFI_LAUNCH_OK("blocked_to_nchw");
     return EBFI_OK;

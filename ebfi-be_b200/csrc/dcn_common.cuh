@@ -22,7 +22,26 @@ struct DcnDims {
     long long off_bs, mask_bs;
     int packed;
     float *abs_sum;   // packed forward only, nullable: += sum |offset| (DCN_sep's `offset_mean` warning, :221-223)
+    // EBFI_DCN_DETERMINISTIC (backward): grad_input is accumulated as int64 fixed point. det_bound -> 3 device
+    // floats {max_px sum_co |gO|, max |weight|, max |mask|} whose product bounds every single contribution;
+    // det_head = 62 - bits(max contributions per element): sums stay below 2^62 for scale = 2^(det_head - e),
+    // bound < 2^e.
+    int det, det_head;
+    const float *det_bound;
 };
+
+__device__ __forceinline__ int det_scale_exp(const DcnDims &d)
+{
+    const float bound = d.det_bound[0] * d.det_bound[1] * d.det_bound[2];
+    int e = 0;
+    if (bound > 0.f && bound < 3.0e38f) frexpf(bound, &e);      // bound < 2^e
+    return max(-120, min(120, d.det_head - e));
+}
+__device__ __forceinline__ void det_add(long long *p, float v, float scale)
+{
+    // power-of-two scaling is exact; one rounding to the fixed-point grid; integer addition is associative
+    atomicAdd(reinterpret_cast<unsigned long long *>(p), (unsigned long long)__float2ll_rn(v * scale));
+}
 
 __device__ __forceinline__ const float *off_ptr(const DcnDims &d, const float *offset, int b, int g, size_t plane)
 {
@@ -125,6 +144,9 @@ __device__ __forceinline__ f8 ldg_f8(const float *p32B_aligned, bool ok)
     }
     return r;
 }
+
+// {max_px sum_co |gO|, max |weight|, max |mask|} -> bound[3] (dcn.cu)
+int launch_det_bound(cudaStream_t st, const DcnDims &d, const float *gout, const float *weight, const float *mask, float *bound);
 
 // NCHW (BG*8 planes of HW pixels) -> group-blocked (BG, HW, 8) copy (dcn_bwd_tc.cu)
 int launch_nchw_to_blocked(cudaStream_t st, const float *src, float *dst, int BG, int HW);

@@ -7,6 +7,8 @@ Differences, all deliberate:
   * the deformable PS-ROI pooling pair (dcn_v2.h:94-190) is out of scope and raises
     NotImplementedError (it is never imported by EBFI-BE).
 """
+import os
+
 import torch
 
 try:
@@ -20,8 +22,15 @@ except ImportError:  # shims directory used stand-alone on sys.path
     from ebfi_be_b200 import _lib as L
 
 
+def _deterministic():
+    """Deterministic backward (new; the reference's col2im atomics are not reproducible, im2col_cuda.cu:249):
+    follows torch.use_deterministic_algorithms(True), or EBFI_DCN_DETERMINISTIC=1."""
+    return (L.EBFI_DCN_DETERMINISTIC
+            if (torch.are_deterministic_algorithms_enabled() or os.environ.get("EBFI_DCN_DETERMINISTIC") == "1") else 0)
+
+
 def _geom(input, weight, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w,
-          dilation_h, dilation_w, deformable_group):
+          dilation_h, dilation_w, deformable_group, flags=0):
     if input.dim() != 4 or weight.dim() != 4:
         raise RuntimeError("dcn_v2: input and weight must be 4-D")
     channels_out, channels_kernel, kh_, kw_ = weight.shape
@@ -34,7 +43,7 @@ def _geom(input, weight, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w,
                            % (input.shape[1], channels_kernel))
     g = L.DcnGeom(input.shape[0], input.shape[1], input.shape[2], input.shape[3], channels_out,
                   kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w,
-                  deformable_group)
+                  deformable_group, flags)
     ho, wo = L.c_int(), L.c_int()
     L.check(L.load().ebfi_dcnv2_output_size(g, ho, wo), "dcn_v2 geometry")
     return g, ho.value, wo.value
@@ -103,7 +112,7 @@ def dcn_v2_backward(input, weight, bias, offset, mask, grad_output, kernel_h, ke
         return _bf16_via_fp32(dcn_v2_backward, (input, weight, bias, offset, mask, grad_output),
                               (kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w, deformable_group))
     g, ho, wo = _geom(input, weight, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w,
-                      dilation_h, dilation_w, deformable_group)
+                      dilation_h, dilation_w, deformable_group, _deterministic())
     _check_offset_mask(g, ho, wo, offset, mask)
     if tuple(grad_output.shape) != (g.batch, g.channels_out, ho, wo):
         raise RuntimeError("dcn_v2_backward: grad_output has the wrong shape")
@@ -170,7 +179,7 @@ def dcn_v2_backward_packed(input, weight, bias, offset_mask, grad_output, kernel
         return _bf16_via_fp32(dcn_v2_backward_packed, (input, weight, bias, offset_mask, grad_output),
                               (kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w, deformable_group))
     g, ho, wo = _geom(input, weight, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w,
-                      dilation_h, dilation_w, deformable_group)
+                      dilation_h, dilation_w, deformable_group, _deterministic())
     _check_packed(g, ho, wo, offset_mask)
     if tuple(grad_output.shape) != (g.batch, g.channels_out, ho, wo):
         raise RuntimeError("dcn_v2_backward_packed: grad_output has the wrong shape")

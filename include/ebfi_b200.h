@@ -43,7 +43,7 @@ extern "C" {
 #define EBFI_ERR_WORKSPACE   -3   /* workspace too small (query the *_workspace_bytes fn) */
 #define EBFI_ERR_UNSUPPORTED -4   /* valid request this build does not implement */
 
-#define EBFI_ABI_VERSION 1
+#define EBFI_ABI_VERSION 2
 
 /* ---- library ---------------------------------------------------------------- */
 
@@ -64,7 +64,16 @@ typedef struct ebfi_dcn_geom {
     int pad_h, pad_w;
     int dilation_h, dilation_w;
     int deformable_group;                 /* offset (B, 2*dg*kh*kw, Ho, Wo); mask (B, dg*kh*kw, Ho, Wo) */
+    int flags;                            /* 0, or EBFI_DCN_DETERMINISTIC (new; not in the reference's argument list) */
 } ebfi_dcn_geom;
+
+/* Backward only: accumulate grad_input in 64-bit fixed point (integer atomics are associative), so that
+ * ALL five gradients are bit-reproducible run to run. The reference's col2im uses float atomicAdd
+ * (dcn_v2_im2col_cuda.cu:249) and is not; neither is the default mode here. The fixed-point scale is a
+ * power of two derived on the device from max|grad_output|, max|weight| and max|mask| such that no
+ * sum can overflow; resolution is at least 2^-20 of the largest possible single contribution. About 2x
+ * slower than the default vector reductions. */
+#define EBFI_DCN_DETERMINISTIC 1
 
 /* Output spatial size, formula of dcn_v2_cuda.cu:64-65. Returns EBFI_ERR_INVALID
  * when the geometry is inconsistent (non-positive sizes, C % dg != 0, ...). */

@@ -37,7 +37,7 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 def test_abi_version_and_error_string():
     lib = L.load()
-    assert lib.ebfi_abi_version() == 1
+    assert lib.ebfi_abi_version() == 2
     assert isinstance(lib.ebfi_last_error(), bytes)
 
 
