@@ -1,0 +1,311 @@
+// kpn.cu — KernelConv producer -> FAC consumer, fused forward.
+//
+// Reference op sequence (models/Ours/model_singleframe.py:145-146,159-162, class Modification):
+//     Kernel = LeakyReLU(conv3x3(cat([Event, Frame], 1)))          # ConvLayer, (B, Ce*K*K, H, W): 1.68 GB at cfg2
+//     out    = KernelConv2D(K)(Event, Kernel)                      # ReplicationPad2d((K-1)/2) + FAC
+// The per-pixel kernel tensor is written once and read once; fused, it never exists in HBM: the 3x3
+// convolution is an implicit GEMM on the tcgen05 tensor cores whose accumulator (TMEM) is consumed in place
+// by the FAC contraction.
+//
+// Mapping: WEIGHT-STATIONARY. The conv's output channels are cut into slices of 3 FAC channels x K*K taps
+// (75 GEMM columns, N = 80); the slice's weights for all 9 x Cin reduction steps (184 KB as bf16) stay in
+// shared memory while the CTA streams pixel tiles through them — the opposite arrangement (pixel tile
+// stationary, weights streamed) needs ~60 B/clk/SM of weight traffic from L2 and is bandwidth-bound there.
+// Work items = (slice, pixel tile) in slice-major order, split evenly over one persistent CTA per SM; a CTA
+// reloads weights only when its range crosses a slice boundary.
+//   tile        16 rows x 8 columns = 128 pixels = M (one TMEM lane per pixel)
+//   A operand   the tile's input halo (18 x 10 pixels x Cin) in shared memory, laid out [8-ch chunk][y][x][8 ch]
+//               (bf16); for tap (dy, dx) the UMMA descriptor simply starts (dy*10 + dx) pixels later, with
+//               SBO = one halo row and LBO = one chunk plane: no im2col copy of any kind
+//   B operand   weights [80 rows][9*Cin], K-major, K order = (channel half, tap, 16-channel step)
+//   pipeline    loader warps fill the two channel halves of the halo alternately (the half that the tensor
+//               core has finished with is refilled for the next tile while the other half computes);
+//               two TMEM accumulators let the epilogue of item i overlap the MMAs of item i+1
+//   epilogue    thread = pixel: 75 accumulators -> + bias -> LeakyReLU -> x Event[c][clamp(y+ky-2)][clamp(x+kx-2)]
+//               summed in the reference's tap order (KernelConv2D_kernel.cu:44-50) -> 3 outputs
+//
+// Precision: tensors are fp32 at the boundary (like the reference); the conv operands are rounded to bf16
+// for the tensor cores, accumulation and the whole FAC part are fp32. Stated tolerance 1e-2 of max|out|
+// against the fp32/fp64 op sequence; 1e-5 against the same sequence with bf16-rounded conv operands.
+#include "common.cuh"
+#include "umma.cuh"
+
+#include <algorithm>
+
+namespace {
+
+using ebfi::ceil_div;
+
+constexpr int TH = 16, TW = 8, TM = TH * TW;     // pixel tile
+constexpr int HH = TH + 2, HW = TW + 2;          // conv halo (3x3, pad 1)
+constexpr int HPIX = HH * HW;                    // 180 halo pixels
+constexpr int CPS = 3;                           // FAC channels per weight slice
+constexpr int NTHR = 288;                        // 4 epilogue warps + 4 loader warps + 1 MMA warp
+constexpr int TMEM_COLS = 256;                   // two accumulators at columns 0 and 128
+
+struct KpnDims {
+    int B, Ce, Cin, H, W, K, KK;
+    int nslice, NP;              // weight slices; GEMM N (padded to 16) of a full slice
+    int tiles_x, tiles_y, ntile; // pixel tiles per sample row / column, per call
+    int Ktot, kchunks;           // 9 * Cin; Cin / 8
+    int half_chunks;             // 8-channel chunks per channel half
+    int a_half_bytes, w_bytes;
+    float slope;
+};
+
+// (ev | fr) NCHW fp32 -> [b][chunk of 8 channels][y][x][8] bf16: one thread per (b, chunk, y, x)
+__global__ void kpn_prep_input(const float *__restrict__ ev, const float *__restrict__ fr, __nv_bfloat16 *__restrict__ dst,
+                               KpnDims d)
+{
+    const size_t plane = (size_t)d.H * d.W, n = (size_t)d.B * d.kchunks * plane;
+    const int Cf = d.Cin - d.Ce;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t px = i % plane, bk = i / plane;
+        const int kc = (int)(bk % d.kchunks), b = (int)(bk / d.kchunks);
+        unsigned short v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int ch = kc * 8 + e;
+            const float x = ch < d.Ce ? __ldg(ev + ((size_t)b * d.Ce + ch) * plane + px)
+                                      : __ldg(fr + ((size_t)b * Cf + (ch - d.Ce)) * plane + px);
+            v[e] = __bfloat16_as_ushort(__float2bfloat16_rn(x));
+        }
+        *reinterpret_cast<uint4 *>(dst + i * 8) = make_uint4(v[0] | ((uint32_t)v[1] << 16), v[2] | ((uint32_t)v[3] << 16),
+                                                             v[4] | ((uint32_t)v[5] << 16), v[6] | ((uint32_t)v[7] << 16));
+    }
+}
+
+// conv weight (Ce*KK, Cin, 3, 3) fp32 -> per slice the shared-memory image [NP/8][Ktot/8][8 rows][8 k] bf16,
+// K order: chunk index = (half * 9 + tap) * half_chunks + j  <->  channel half * Cin/2 + j*8 + e
+__global__ void kpn_prep_weights(const float *__restrict__ w, __nv_bfloat16 *__restrict__ wimg, KpnDims d)
+{
+    const int per = d.NP * d.Ktot;
+    const int kch = d.Ktot / 8;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.nslice * per; i += gridDim.x * blockDim.x) {
+        const int s = i / per, e0 = i - s * per;
+        const int e = e0 & 7, r = (e0 >> 3) & 7, rest = e0 >> 6;
+        const int kc = rest % kch, rg = rest / kch;
+        const int nrow = rg * 8 + r;
+        const int j = kc % d.half_chunks, ht = kc / d.half_chunks, tap = ht % 9, h = ht / 9;
+        const int ch = h * (d.Cin / 2) + j * 8 + e;
+        const int c0 = s * CPS, ncols = min(CPS, d.Ce - c0) * d.KK;
+        float v = 0.f;
+        if (nrow < ncols) v = __ldg(w + ((size_t)(c0 * d.KK + nrow) * d.Cin + ch) * 9 + tap);
+        wimg[i] = __float2bfloat16_rn(v);
+    }
+}
+
+__global__ void __launch_bounds__(NTHR, 1)
+kpn_fused_kernel(const __nv_bfloat16 *__restrict__ featb, const __nv_bfloat16 *__restrict__ wimg,
+                 const float *__restrict__ bias, const float *__restrict__ ev, float *__restrict__ out,
+                 KpnDims d, int items_per_cta)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char *w_s = smem;                               // weight slice
+    unsigned char *a_s = smem + d.w_bytes;                   // two channel halves of the halo tile
+    __shared__ __align__(8) uint64_t bar_w, bar_wfree, a_full[2], a_free[2], acc_full[2], acc_free[2];
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int total = d.nslice * d.ntile;
+    const int item0 = blockIdx.x * items_per_cta, item1 = min(total, item0 + items_per_cta);
+
+    if (warp == 0) umma::tmem_alloc<TMEM_COLS>(&tmem_slot);
+    if (tid == 0) {
+        umma::mbar_init(&bar_w, 1);
+        umma::mbar_init(&bar_wfree, 1);
+        for (int i = 0; i < 2; ++i) {
+            umma::mbar_init(&a_full[i], 128);
+            umma::mbar_init(&a_free[i], 1);
+            umma::mbar_init(&acc_full[i], 1);
+            umma::mbar_init(&acc_free[i], 128);
+        }
+        umma::mbar_fence_init();
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    const int tiles_per_sample = d.tiles_x * d.tiles_y;
+
+    if (warp == 8) {
+        // ===================== MMA issue + weight loads: one lane =====================
+        if (lane == 0) {
+            int cur_slice = -1, nw = 0;
+            for (int item = item0, n = 0; item < item1; ++item, ++n) {
+                const int s = item / d.ntile;
+                const int ncols = min(CPS, d.Ce - s * CPS) * d.KK;
+                const uint32_t idesc = umma::instr_desc_bf16(TM, (ncols + 15) & ~15);
+                if (s != cur_slice) {
+                    if (cur_slice >= 0) {                    // every MMA that reads the old weights has completed
+                        umma::commit(&bar_wfree);
+                        umma::mbar_wait(&bar_wfree, (uint32_t)((nw - 1) & 1));
+                    }
+                    umma::mbar_expect_tx(&bar_w, (uint32_t)d.w_bytes);
+                    const unsigned char *src = reinterpret_cast<const unsigned char *>(wimg) + (size_t)s * d.w_bytes;
+                    const int piece = d.w_bytes / 8;
+                    for (int q = 0; q < 8; ++q) umma::bulk_g2s(w_s + q * piece, src + (size_t)q * piece, (uint32_t)piece, &bar_w);
+                    umma::mbar_wait(&bar_w, (uint32_t)(nw & 1));
+                    ++nw;
+                    cur_slice = s;
+                }
+                const int buf = n & 1;
+                umma::mbar_wait(&acc_free[buf], (uint32_t)(((n >> 1) & 1) ^ 1));   // epilogue of item n-2 has drained it
+                umma::fence_after_sync();
+                const uint32_t dcol = tmem + (uint32_t)buf * 128u;
+                const uint32_t w_sbo = (uint32_t)(d.Ktot / 8) * 128u;
+                bool first = true;
+                for (int h = 0; h < 2; ++h) {
+                    umma::mbar_wait(&a_full[h], (uint32_t)(n & 1));
+                    umma::fence_after_sync();
+                    const uint32_t a_base = umma::smem_u32(a_s + h * d.a_half_bytes);
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const uint32_t a_tap = a_base + (uint32_t)((tap / 3) * HW + (tap % 3)) * 16u;
+                        const uint32_t w_tap = umma::smem_u32(w_s) + (uint32_t)((h * 9 + tap) * d.half_chunks) * 128u;
+                        for (int j = 0; j < d.half_chunks / 2; ++j) {
+                            const uint64_t da = umma::smem_desc(a_tap + (uint32_t)(2 * j) * (HPIX * 16u), HPIX * 16u, HW * 16u);
+                            const uint64_t db = umma::smem_desc(w_tap + (uint32_t)(2 * j) * 128u, 128u, w_sbo);
+                            umma::mma_f16(dcol, da, db, idesc, !first);
+                            first = false;
+                        }
+                    }
+                    umma::commit(&a_free[h]);                // this half may be refilled for the next item
+                }
+                umma::commit(&acc_full[buf]);
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== loader warps: halo tile -> A operand =====================
+        const int lt = tid - 128;
+        for (int item = item0, n = 0; item < item1; ++item, ++n) {
+            const int t = item % d.ntile;
+            const int b = t / tiles_per_sample, tt = t % tiles_per_sample;
+            const int ty0 = (tt / d.tiles_x) * TH, tx0 = (tt % d.tiles_x) * TW;
+            for (int h = 0; h < 2; ++h) {
+                umma::mbar_wait(&a_free[h], (uint32_t)((n & 1) ^ 1));
+                unsigned char *dst = a_s + h * d.a_half_bytes;
+                for (int idx = lt; idx < d.half_chunks * HPIX; idx += 128) {
+                    const int kc = idx / HPIX, r = idx - kc * HPIX;
+                    const int y = ty0 - 1 + r / HW, x = tx0 - 1 + r % HW;
+                    uint4 v = make_uint4(0u, 0u, 0u, 0u);                         // zero padding of the conv
+                    if (y >= 0 && y < d.H && x >= 0 && x < d.W)
+                        v = __ldg(reinterpret_cast<const uint4 *>(
+                            featb + ((((size_t)b * d.kchunks + h * d.half_chunks + kc) * d.H + y) * d.W + x) * 8));
+                    *reinterpret_cast<uint4 *>(dst + (size_t)idx * 16) = v;
+                }
+                umma::fence_smem_to_async();
+                umma::mbar_arrive(&a_full[h]);
+            }
+        }
+    } else {
+        // ===================== epilogue warps: thread = pixel (TMEM lane) =====================
+        const int p = tid, py = p / TW, px = p % TW;
+        const uint32_t lane_base = (uint32_t)warp * 32u;
+        const size_t plane = (size_t)d.H * d.W;
+        const int R = (d.K - 1) / 2;
+        for (int item = item0, n = 0; item < item1; ++item, ++n) {
+            const int s = item / d.ntile, t = item % d.ntile;
+            const int b = t / tiles_per_sample, tt = t % tiles_per_sample;
+            const int y = (tt / d.tiles_x) * TH + py, x = (tt % d.tiles_x) * TW + px;
+            const bool valid = y < d.H && x < d.W;
+            const int c0 = s * CPS, nc = min(CPS, d.Ce - c0);
+            const int buf = n & 1;
+            umma::mbar_wait(&acc_full[buf], (uint32_t)((n >> 1) & 1));
+            umma::fence_after_sync();
+            float res[CPS] = {0.f, 0.f, 0.f};
+            const int ncols = nc * d.KK;
+            for (int cb = 0; cb < ncols; cb += 8) {
+                float v[8];
+                umma::tmem_ld8(umma::tmem_addr(tmem, lane_base, buf * 128 + cb), v);
+                umma::tmem_ld_wait();
+                if (valid) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int col = cb + i;
+                        if (col < ncols) {
+                            const int cc = col / d.KK, tap = col - cc * d.KK;
+                            float a = v[i] + __ldg(bias + (c0 + cc) * d.KK + tap);
+                            a = a > 0.f ? a : a * d.slope;                        // nn.LeakyReLU
+                            const int yy = min(max(y + tap / d.K - R, 0), d.H - 1);   // ReplicationPad2d (KernelConv2D.py:82-86)
+                            const int xx = min(max(x + tap % d.K - R, 0), d.W - 1);
+                            const float e = __ldg(ev + ((size_t)b * d.Ce + c0 + cc) * plane + (size_t)yy * d.W + xx);
+                            if (cc == 0) res[0] += e * a; else if (cc == 1) res[1] += e * a; else res[2] += e * a;
+                        }
+                    }
+                }
+            }
+            umma::fence_before_sync();
+            umma::mbar_arrive(&acc_free[buf]);
+            if (valid)
+                for (int cc = 0; cc < nc; ++cc) out[((size_t)b * d.Ce + c0 + cc) * plane + (size_t)y * d.W + x] = res[cc];
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc<TMEM_COLS>(tmem);
+}
+
+int fill(KpnDims &d, int B, int Ce, int Cf, int H, int W, int K, float slope)
+{
+    EBFI_REQUIRE(B > 0 && Ce > 0 && Cf >= 0 && H > 0 && W > 0, "kpn_fused: bad sizes");
+    EBFI_REQUIRE(K >= 1 && (K & 1) && K * K * CPS <= 80, "kpn_fused: kernel_size must be odd and <= 5");
+    d.B = B; d.Ce = Ce; d.Cin = Ce + Cf; d.H = H; d.W = W; d.K = K; d.KK = K * K; d.slope = slope;
+    if (d.Cin % 32 != 0 || d.Cin > 128)
+        return ebfi::fail(EBFI_ERR_UNSUPPORTED, "kpn_fused: event+frame channels (%d) must be a multiple of 32, <= 128", d.Cin);
+    d.nslice = ceil_div(Ce, CPS);
+    d.NP = ebfi::round_up(CPS * d.KK, 16);
+    d.tiles_x = ceil_div(W, TW); d.tiles_y = ceil_div(H, TH);
+    d.ntile = B * d.tiles_x * d.tiles_y;
+    d.Ktot = 9 * d.Cin; d.kchunks = d.Cin / 8; d.half_chunks = d.Cin / 16;
+    d.a_half_bytes = d.half_chunks * HPIX * 16;
+    d.w_bytes = d.NP * d.Ktot * 2;
+    EBFI_REQUIRE((long)d.nslice * d.ntile < (1L << 31), "kpn_fused: too many work items");
+    return EBFI_OK;
+}
+
+size_t ws_weights(const KpnDims &d) { return ebfi::round_up((size_t)d.nslice * d.w_bytes, (size_t)256); }
+size_t ws_input(const KpnDims &d) { return (size_t)d.B * d.Cin * d.H * d.W * 2; }
+
+}  // namespace
+
+extern "C" {
+
+size_t ebfi_kpn_fused_workspace_bytes(int batch, int channels_event, int channels_frame, int height, int width,
+                                      int kernel_size)
+{
+    KpnDims d{};
+    if (fill(d, batch, channels_event, channels_frame, height, width, kernel_size, 0.f) != EBFI_OK) return 0;
+    return ws_weights(d) + ws_input(d) + 256;
+}
+
+int ebfi_kpn_fused_forward(void *stream, const float *event_feat, const float *frame_feat, const float *conv_weight,
+                           const float *conv_bias, float negative_slope, float *output, int batch,
+                           int channels_event, int channels_frame, int height, int width, int kernel_size,
+                           void *workspace, size_t workspace_bytes)
+{
+    KpnDims d{};
+    if (int rc = fill(d, batch, channels_event, channels_frame, height, width, kernel_size, negative_slope)) return rc;
+    EBFI_REQUIRE(event_feat && (frame_feat || channels_frame == 0) && conv_weight && conv_bias && output,
+                 "kpn_fused: null pointer");
+    const size_t need = ws_weights(d) + ws_input(d);
+    if (!workspace || workspace_bytes < need)
+        return ebfi::fail(EBFI_ERR_WORKSPACE, "kpn_fused: workspace %zu < %zu bytes", workspace_bytes, need);
+    EBFI_REQUIRE(ebfi::aligned16(workspace), "kpn_fused: workspace must be 16-byte aligned");
+    cudaStream_t st = ebfi::as_stream(stream);
+    __nv_bfloat16 *wimg = static_cast<__nv_bfloat16 *>(workspace);
+    __nv_bfloat16 *featb = reinterpret_cast<__nv_bfloat16 *>(static_cast<char *>(workspace) + ws_weights(d));
+    kpn_prep_weights<<<ebfi::sm_count() * 4, 256, 0, st>>>(conv_weight, wimg, d);
+    EBFI_LAUNCH_OK("kpn_prep_weights");
+    kpn_prep_input<<<ebfi::sm_count() * 8, 256, 0, st>>>(event_feat, frame_feat, featb, d);
+    EBFI_LAUNCH_OK("kpn_prep_input");
+    const int smem = d.w_bytes + 2 * d.a_half_bytes;
+    EBFI_CUDA_OK(cudaFuncSetAttribute(kpn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int total = d.nslice * d.ntile;
+    const int grid = std::min(total, ebfi::sm_count());
+    const int per = ceil_div(total, grid);
+    kpn_fused_kernel<<<ceil_div(total, per), NTHR, smem, st>>>(featb, wimg, conv_bias, event_feat, output, d, per);
+    EBFI_LAUNCH_OK("kpn_fused_kernel");
+    return EBFI_OK;
+}
+
+}  // extern "C"

@@ -165,6 +165,24 @@ int ebfi_fac_backward_bf16(void *stream, const void *input, const void *kernel, 
                            int batch, int channels, int height_out, int width_out, int kernel_size,
                            void *workspace, size_t workspace_bytes);
 
+/* ---- KernelConv producer -> FAC fusion (forward) ------------- */
+
+/* models/Ours/model_singleframe.py:145-146,159-162 (class Modification) as ONE op:
+ *   Kernel = LeakyReLU(conv3x3(cat([event_feat, frame_feat], 1), conv_weight, conv_bias, pad 1))   (B, Ce*K*K, H, W)
+ *   output = KernelConv2D(K)(event_feat, Kernel)      = FAC on the ReplicationPad2d((K-1)/2)-padded event_feat
+ * The (B, Ce*K*K, H, W) kernel tensor never exists in HBM. All tensors fp32 NCHW contiguous:
+ *   event_feat (B, Ce, H, W); frame_feat (B, Cf, H, W); conv_weight (Ce*K*K, Ce+Cf, 3, 3); conv_bias (Ce*K*K);
+ *   output (B, Ce, H, W), every element written.
+ * Precision: the convolution's operands are rounded to bf16 for the tcgen05 tensor cores, accumulation and the
+ * FAC contraction are fp32 (the reference's conv runs in TF32 under torch's defaults). Shapes: (Ce+Cf) % 32 == 0,
+ * Ce+Cf <= 128, odd K <= 5; otherwise EBFI_ERR_UNSUPPORTED. Inference path: there is no fused backward. */
+size_t ebfi_kpn_fused_workspace_bytes(int batch, int channels_event, int channels_frame, int height, int width,
+                                      int kernel_size);
+int ebfi_kpn_fused_forward(void *stream, const float *event_feat, const float *frame_feat,
+                           const float *conv_weight, const float *conv_bias, float negative_slope,
+                           float *output, int batch, int channels_event, int channels_frame,
+                           int height, int width, int kernel_size, void *workspace, size_t workspace_bytes);
+
 /* ---- event encoders --------------------------------------------------------- */
 
 /* Coordinate / timestamp arrays may be fp32 or fp64, like the tensors the

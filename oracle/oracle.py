@@ -176,3 +176,43 @@ def dataset_event_stack(xs, ys, ts, ps, B, sensor_size):
     ts = (ts.astype(np.float64) - ts[0]) / (ts[-1] - ts[0] + 1e-6)
     stack, *_ = events_to_stack(xs.astype(np.float64), ys.astype(np.float64), ts, ps.astype(np.float32), B, sensor_size)
     return np.ascontiguousarray(stack.transpose(1, 0, 2, 3))
+
+
+def _bf16_round(a):
+    """Round-to-nearest-even to bfloat16, returned as float32 (numpy has no bf16)."""
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32).reshape(np.shape(a))
+
+
+def kpn_fused_forward(event_feat, frame_feat, conv_weight, conv_bias, K, negative_slope=0.01, bf16_operands=False):
+    """models/Ours/model_singleframe.py:145-146,159-162 (class Modification) restated in float64:
+        Kernel = LeakyReLU(conv3x3(cat([Event, Frame], 1)), pad 1)      # ConvLayer: nn.Conv2d + nn.LeakyReLU()
+        out    = KernelConv2D(K)(Event, Kernel)                          # ReplicationPad2d((K-1)/2) + FAC
+    bf16_operands=True rounds the convolution's inputs and weights to bf16 first (what the fused kernel feeds the
+    tensor cores); everything else stays float64. Returns (out float64, Kernel float64)."""
+    ev = np.asarray(event_feat, np.float64)
+    feat = np.concatenate([np.asarray(event_feat, np.float32), np.asarray(frame_feat, np.float32)], axis=1)
+    w = np.asarray(conv_weight, np.float32)
+    if bf16_operands:
+        feat, w = _bf16_round(feat), _bf16_round(w)
+    feat, w = feat.astype(np.float64), w.astype(np.float64)
+    B, Cin, H, W = feat.shape
+    Cout = w.shape[0]
+    fp = np.pad(feat, ((0, 0), (0, 0), (1, 1), (1, 1)))
+    cols = np.empty((B, Cin * 9, H * W))
+    for c in range(Cin):
+        for i in range(3):
+            for j in range(3):
+                cols[:, c * 9 + i * 3 + j] = fp[:, c, i:i + H, j:j + W].reshape(B, -1)
+    ker = np.einsum("ok,bkp->bop", w.reshape(Cout, Cin * 9), cols) + np.asarray(conv_bias, np.float64)[None, :, None]
+    ker = np.where(ker > 0, ker, ker * negative_slope).reshape(B, Cout, H, W)
+    R = (K - 1) // 2
+    evp = np.pad(ev, ((0, 0), (0, 0), (R, R), (R, R)), mode="edge")
+    Ce = ev.shape[1]
+    out = np.zeros((B, Ce, H, W))
+    for c in range(Ce):
+        for ky in range(K):
+            for kx in range(K):
+                out[:, c] += evp[:, c, ky:ky + H, kx:kx + W] * ker[:, c * K * K + ky * K + kx]
+    return out, ker

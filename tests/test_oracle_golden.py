@@ -102,3 +102,25 @@ def test_dataset_event_path_on_disk_dtypes(oracle, name):
         got = oracle.dataset_event_stack(g[f"{name}_xs"], g[f"{name}_ys"], g[f"{name}_ts"], g[f"{name}_ps"], nb, (H, W))
         assert got.shape == (nb, 2, H, W)
         assert np.array_equal(got, g[f"{name}_stack{nb}"]), (name, nb)
+
+
+def test_kpn_oracle_matches_torch_op_sequence(oracle):
+    """oracle.kpn_fused_forward vs the reference's modules applied literally with torch (nn.Conv2d -> nn.LeakyReLU
+    -> ReplicationPad2d -> unfold contraction), model_singleframe.py:145-146,159-162 + KernelConv2D.py:82-87."""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(0)
+    B, Ce, Cf, H, W, K = 2, 8, 8, 9, 7, 5
+    ev = rng.standard_normal((B, Ce, H, W), dtype=np.float32)
+    fr = rng.standard_normal((B, Cf, H, W), dtype=np.float32)
+    w = (0.1 * rng.standard_normal((Ce * K * K, Ce + Cf, 3, 3))).astype(np.float32)
+    b = rng.standard_normal(Ce * K * K).astype(np.float32)
+    out, ker = oracle.kpn_fused_forward(ev, fr, w, b, K)
+    feat = torch.cat([torch.from_numpy(ev), torch.from_numpy(fr)], 1).double()
+    kt = torch.nn.LeakyReLU()(F.conv2d(feat, torch.from_numpy(w).double(), torch.from_numpy(b).double(), padding=1))
+    evp = torch.nn.ReplicationPad2d(2)(torch.from_numpy(ev).double())
+    want = (F.unfold(evp, K).view(B, Ce, K * K, H, W) * kt.view(B, Ce, K * K, H, W)).sum(2)
+    assert np.abs(ker - kt.numpy()).max() < 1e-12 and np.abs(out - want.numpy()).max() < 1e-12
+    # the bf16 rounding helper is torch's round-to-nearest-even
+    x = rng.standard_normal(1000).astype(np.float32) * 3
+    assert np.array_equal(oracle._bf16_round(x), torch.from_numpy(x).bfloat16().float().numpy())
