@@ -95,11 +95,21 @@ __global__ void kpn_prep_weights(const float *__restrict__ w, __nv_bfloat16 *__r
     }
 }
 
+// 16-byte asynchronous global -> shared copy; src_bytes = 0 writes zeros (the conv's zero padding)
+__device__ __forceinline__ void cp_async16_zfill(void *smem_dst, const void *gmem_src, uint32_t src_bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(umma::smem_u32(smem_dst)), "l"(gmem_src), "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int K>
 __global__ void __launch_bounds__(NTHR, 1)
 kpn_fused_kernel(const __nv_bfloat16 *__restrict__ featb, const __nv_bfloat16 *__restrict__ wimg,
                  const float *__restrict__ bias, const float *__restrict__ ev, float *__restrict__ out,
                  KpnDims d, int items_per_cta)
 {
+    constexpr int KK = K * K, R = (K - 1) / 2;
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *w_s = smem;                               // weight slice
     unsigned char *a_s = smem + d.w_bytes;                   // two channel halves of the halo tile
@@ -132,9 +142,15 @@ kpn_fused_kernel(const __nv_bfloat16 *__restrict__ featb, const __nv_bfloat16 *_
         // ===================== MMA issue + weight loads: one lane =====================
         if (lane == 0) {
             int cur_slice = -1, nw = 0;
+            const uint32_t w_sbo = (uint32_t)(d.Ktot / 8) * 128u;
+            // descriptors differ only in their 16-byte-granular start address (low 14 bits): build once, add offsets
+            const uint64_t da0[2] = {umma::smem_desc(umma::smem_u32(a_s), HPIX * 16u, HW * 16u),
+                                     umma::smem_desc(umma::smem_u32(a_s + d.a_half_bytes), HPIX * 16u, HW * 16u)};
+            const uint64_t db0 = umma::smem_desc(umma::smem_u32(w_s), 128u, w_sbo);
+            const int ksteps = d.half_chunks / 2;            // K = 16 steps per (half, tap)
             for (int item = item0, n = 0; item < item1; ++item, ++n) {
                 const int s = item / d.ntile;
-                const int ncols = min(CPS, d.Ce - s * CPS) * d.KK;
+                const int ncols = min(CPS, d.Ce - s * CPS) * KK;
                 const uint32_t idesc = umma::instr_desc_bf16(TM, (ncols + 15) & ~15);
                 if (s != cur_slice) {
                     if (cur_slice >= 0) {                    // every MMA that reads the old weights has completed
@@ -153,20 +169,18 @@ kpn_fused_kernel(const __nv_bfloat16 *__restrict__ featb, const __nv_bfloat16 *_
                 umma::mbar_wait(&acc_free[buf], (uint32_t)(((n >> 1) & 1) ^ 1));   // epilogue of item n-2 has drained it
                 umma::fence_after_sync();
                 const uint32_t dcol = tmem + (uint32_t)buf * 128u;
-                const uint32_t w_sbo = (uint32_t)(d.Ktot / 8) * 128u;
-                bool first = true;
+                uint32_t acc = 0;
+#pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     umma::mbar_wait(&a_full[h], (uint32_t)(n & 1));
                     umma::fence_after_sync();
-                    const uint32_t a_base = umma::smem_u32(a_s + h * d.a_half_bytes);
+#pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
-                        const uint32_t a_tap = a_base + (uint32_t)((tap / 3) * HW + (tap % 3)) * 16u;
-                        const uint32_t w_tap = umma::smem_u32(w_s) + (uint32_t)((h * 9 + tap) * d.half_chunks) * 128u;
-                        for (int j = 0; j < d.half_chunks / 2; ++j) {
-                            const uint64_t da = umma::smem_desc(a_tap + (uint32_t)(2 * j) * (HPIX * 16u), HPIX * 16u, HW * 16u);
-                            const uint64_t db = umma::smem_desc(w_tap + (uint32_t)(2 * j) * 128u, 128u, w_sbo);
-                            umma::mma_f16(dcol, da, db, idesc, !first);
-                            first = false;
+                        uint64_t da = da0[h] + (uint64_t)((tap / 3) * HW + (tap % 3));
+                        uint64_t db = db0 + (uint64_t)((h * 9 + tap) * d.half_chunks * 8);
+                        for (int j = 0; j < ksteps; ++j, da += 2 * HPIX, db += 16) {
+                            umma::mma_f16(dcol, da, db, idesc, acc);
+                            acc = 1;
                         }
                     }
                     umma::commit(&a_free[h]);                // this half may be refilled for the next item
@@ -175,7 +189,7 @@ kpn_fused_kernel(const __nv_bfloat16 *__restrict__ featb, const __nv_bfloat16 *_
             }
         }
     } else if (warp >= 4) {
-        // ===================== loader warps: halo tile -> A operand =====================
+        // ===================== loader warps: halo tile -> A operand (cp.async, zero fill outside the image) ==========
         const int lt = tid - 128;
         for (int item = item0, n = 0; item < item1; ++item, ++n) {
             const int t = item % d.ntile;
@@ -184,15 +198,15 @@ kpn_fused_kernel(const __nv_bfloat16 *__restrict__ featb, const __nv_bfloat16 *_
             for (int h = 0; h < 2; ++h) {
                 umma::mbar_wait(&a_free[h], (uint32_t)((n & 1) ^ 1));
                 unsigned char *dst = a_s + h * d.a_half_bytes;
+                const __nv_bfloat16 *src_h = featb + ((size_t)b * d.kchunks + h * d.half_chunks) * (size_t)d.H * d.W * 8;
                 for (int idx = lt; idx < d.half_chunks * HPIX; idx += 128) {
                     const int kc = idx / HPIX, r = idx - kc * HPIX;
                     const int y = ty0 - 1 + r / HW, x = tx0 - 1 + r % HW;
-                    uint4 v = make_uint4(0u, 0u, 0u, 0u);                         // zero padding of the conv
-                    if (y >= 0 && y < d.H && x >= 0 && x < d.W)
-                        v = __ldg(reinterpret_cast<const uint4 *>(
-                            featb + ((((size_t)b * d.kchunks + h * d.half_chunks + kc) * d.H + y) * d.W + x) * 8));
-                    *reinterpret_cast<uint4 *>(dst + (size_t)idx * 16) = v;
+                    const bool in = y >= 0 && y < d.H && x >= 0 && x < d.W;
+                    const __nv_bfloat16 *src = src_h + (((size_t)kc * d.H + (in ? y : 0)) * d.W + (in ? x : 0)) * 8;
+                    cp_async16_zfill(dst + (size_t)idx * 16, src, in ? 16u : 0u);
                 }
+                cp_async_wait_all();
                 umma::fence_smem_to_async();
                 umma::mbar_arrive(&a_full[h]);
             }
@@ -202,7 +216,7 @@ kpn_fused_kernel(const __nv_bfloat16 *__restrict__ featb, const __nv_bfloat16 *_
         const int p = tid, py = p / TW, px = p % TW;
         const uint32_t lane_base = (uint32_t)warp * 32u;
         const size_t plane = (size_t)d.H * d.W;
-        const int R = (d.K - 1) / 2;
+        constexpr int NLD = (CPS * KK + 7) / 8;              // 8-column TMEM loads of a full slice
         for (int item = item0, n = 0; item < item1; ++item, ++n) {
             const int s = item / d.ntile, t = item % d.ntile;
             const int b = t / tiles_per_sample, tt = t % tiles_per_sample;
@@ -212,32 +226,39 @@ kpn_fused_kernel(const __nv_bfloat16 *__restrict__ featb, const __nv_bfloat16 *_
             const int buf = n & 1;
             umma::mbar_wait(&acc_full[buf], (uint32_t)((n >> 1) & 1));
             umma::fence_after_sync();
-            float res[CPS] = {0.f, 0.f, 0.f};
-            const int ncols = nc * d.KK;
-            for (int cb = 0; cb < ncols; cb += 8) {
-                float v[8];
-                umma::tmem_ld8(umma::tmem_addr(tmem, lane_base, buf * 128 + cb), v);
-                umma::tmem_ld_wait();
-                if (valid) {
+            float v[NLD * 8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int col = cb + i;
-                        if (col < ncols) {
-                            const int cc = col / d.KK, tap = col - cc * d.KK;
-                            float a = v[i] + __ldg(bias + (c0 + cc) * d.KK + tap);
-                            a = a > 0.f ? a : a * d.slope;                        // nn.LeakyReLU
-                            const int yy = min(max(y + tap / d.K - R, 0), d.H - 1);   // ReplicationPad2d (KernelConv2D.py:82-86)
-                            const int xx = min(max(x + tap % d.K - R, 0), d.W - 1);
-                            const float e = __ldg(ev + ((size_t)b * d.Ce + c0 + cc) * plane + (size_t)yy * d.W + xx);
-                            if (cc == 0) res[0] += e * a; else if (cc == 1) res[1] += e * a; else res[2] += e * a;
+            for (int q = 0; q < NLD; ++q) {
+                float (&vq)[8] = *reinterpret_cast<float (*)[8]>(&v[q * 8]);
+                if (q * 8 < nc * KK) umma::tmem_ld8(umma::tmem_addr(tmem, lane_base, buf * 128 + q * 8), vq);
+            }
+            umma::tmem_ld_wait();
+            umma::fence_before_sync();
+            umma::mbar_arrive(&acc_free[buf]);               // accumulator drained into registers: the next item may reuse it
+            if (valid) {
+                int xo[K];
+#pragma unroll
+                for (int kx = 0; kx < K; ++kx) xo[kx] = min(max(x + kx - R, 0), d.W - 1);   // ReplicationPad2d (KernelConv2D.py:82-86)
+#pragma unroll
+                for (int cc = 0; cc < CPS; ++cc) {
+                    if (cc < nc) {
+                        const float *evc = ev + ((size_t)b * d.Ce + c0 + cc) * plane;
+                        const float *bc = bias + (c0 + cc) * KK;
+                        float res = 0.f;
+#pragma unroll
+                        for (int ky = 0; ky < K; ++ky) {
+                            const float *row = evc + (size_t)min(max(y + ky - R, 0), d.H - 1) * d.W;
+#pragma unroll
+                            for (int kx = 0; kx < K; ++kx) {
+                                float a = v[cc * KK + ky * K + kx] + __ldg(bc + ky * K + kx);
+                                a = a > 0.f ? a : a * d.slope;                 // nn.LeakyReLU
+                                res += __ldg(row + xo[kx]) * a;                // tap order of KernelConv2D_kernel.cu:44-50
+                            }
                         }
+                        out[((size_t)b * d.Ce + c0 + cc) * plane + (size_t)y * d.W + x] = res;
                     }
                 }
             }
-            umma::fence_before_sync();
-            umma::mbar_arrive(&acc_free[buf]);
-            if (valid)
-                for (int cc = 0; cc < nc; ++cc) out[((size_t)b * d.Ce + c0 + cc) * plane + (size_t)y * d.W + x] = res[cc];
         }
     }
     umma::fence_before_sync();
@@ -299,11 +320,20 @@ int ebfi_kpn_fused_forward(void *stream, const float *event_feat, const float *f
     kpn_prep_input<<<ebfi::sm_count() * 8, 256, 0, st>>>(event_feat, frame_feat, featb, d);
     EBFI_LAUNCH_OK("kpn_prep_input");
     const int smem = d.w_bytes + 2 * d.a_half_bytes;
-    EBFI_CUDA_OK(cudaFuncSetAttribute(kpn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int total = d.nslice * d.ntile;
     const int grid = std::min(total, ebfi::sm_count());
     const int per = ceil_div(total, grid);
-    kpn_fused_kernel<<<ceil_div(total, per), NTHR, smem, st>>>(featb, wimg, conv_bias, event_feat, output, d, per);
+#define EBFI_KPN(KS)                                                                                          \
+    do {                                                                                                      \
+        EBFI_CUDA_OK(cudaFuncSetAttribute(kpn_fused_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        kpn_fused_kernel<KS><<<ceil_div(total, per), NTHR, smem, st>>>(featb, wimg, conv_bias, event_feat, output, d, per); \
+    } while (0)
+    switch (d.K) {
+    case 1: EBFI_KPN(1); break;
+    case 3: EBFI_KPN(3); break;
+    default: EBFI_KPN(5); break;
+    }
+#undef EBFI_KPN
     EBFI_LAUNCH_OK("kpn_fused_kernel");
     return EBFI_OK;
 }
