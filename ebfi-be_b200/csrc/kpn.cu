@@ -103,7 +103,15 @@ __device__ __forceinline__ void cp_async16_zfill(void *smem_dst, const void *gme
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <int K>
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// K: FAC kernel size; KSTEPS: K = 16 MMA steps per (channel half, tap) = Cin / 32
+template <int K, int KSTEPS>
 __global__ void __launch_bounds__(NTHR, 1)
 kpn_fused_kernel(const __nv_bfloat16 *__restrict__ featb, const __nv_bfloat16 *__restrict__ wimg,
                  const float *__restrict__ bias, const float *__restrict__ ev, float *__restrict__ out,
@@ -139,54 +147,58 @@ kpn_fused_kernel(const __nv_bfloat16 *__restrict__ featb, const __nv_bfloat16 *_
     const int tiles_per_sample = d.tiles_x * d.tiles_y;
 
     if (warp == 8) {
-        // ===================== MMA issue + weight loads: one lane =====================
-        if (lane == 0) {
-            int cur_slice = -1, nw = 0;
-            const uint32_t w_sbo = (uint32_t)(d.Ktot / 8) * 128u;
-            // descriptors differ only in their 16-byte-granular start address (low 14 bits): build once, add offsets
-            const uint64_t da0[2] = {umma::smem_desc(umma::smem_u32(a_s), HPIX * 16u, HW * 16u),
-                                     umma::smem_desc(umma::smem_u32(a_s + d.a_half_bytes), HPIX * 16u, HW * 16u)};
-            const uint64_t db0 = umma::smem_desc(umma::smem_u32(w_s), 128u, w_sbo);
-            const int ksteps = d.half_chunks / 2;            // K = 16 steps per (half, tap)
-            for (int item = item0, n = 0; item < item1; ++item, ++n) {
-                const int s = item / d.ntile;
-                const int ncols = min(CPS, d.Ce - s * CPS) * KK;
-                const uint32_t idesc = umma::instr_desc_bf16(TM, (ncols + 15) & ~15);
-                if (s != cur_slice) {
-                    if (cur_slice >= 0) {                    // every MMA that reads the old weights has completed
-                        umma::commit(&bar_wfree);
-                        umma::mbar_wait(&bar_wfree, (uint32_t)((nw - 1) & 1));
-                    }
+        // ===================== MMA issue + weight loads =====================
+        // All 32 lanes run this loop with warp-uniform values (descriptor arithmetic stays on the uniform
+        // datapath); only the tcgen05 / bulk-copy / commit instructions themselves are issued by one elected
+        // lane. With `if (lane == 0)` around the whole loop the issue cost was ~40 instructions per MMA and the
+        // tensor pipe sat idle 77 % of the time (profiles/README.md).
+        const bool leader = elect_one();
+        int cur_slice = -1, nw = 0;
+        const uint32_t w_sbo = (uint32_t)(36 * KSTEPS) * 128u;             // Ktot / 8 = 9 * Cin / 8 chunks of 128 bytes
+        // descriptors differ only in their 16-byte-granular start address (low 14 bits): build once, add offsets
+        const uint64_t da0[2] = {umma::smem_desc(umma::smem_u32(a_s), HPIX * 16u, HW * 16u),
+                                 umma::smem_desc(umma::smem_u32(a_s + d.a_half_bytes), HPIX * 16u, HW * 16u)};
+        const uint64_t db0 = umma::smem_desc(umma::smem_u32(w_s), 128u, w_sbo);
+        for (int item = item0, n = 0; item < item1; ++item, ++n) {
+            const int s = item / d.ntile;
+            const int ncols = min(CPS, d.Ce - s * CPS) * KK;
+            const uint32_t idesc = umma::instr_desc_bf16(TM, (ncols + 15) & ~15);
+            if (s != cur_slice) {
+                if (cur_slice >= 0) {                        // every MMA that reads the old weights has completed
+                    if (leader) umma::commit(&bar_wfree);
+                    umma::mbar_wait(&bar_wfree, (uint32_t)((nw - 1) & 1));
+                }
+                if (leader) {
                     umma::mbar_expect_tx(&bar_w, (uint32_t)d.w_bytes);
                     const unsigned char *src = reinterpret_cast<const unsigned char *>(wimg) + (size_t)s * d.w_bytes;
                     const int piece = d.w_bytes / 8;
                     for (int q = 0; q < 8; ++q) umma::bulk_g2s(w_s + q * piece, src + (size_t)q * piece, (uint32_t)piece, &bar_w);
-                    umma::mbar_wait(&bar_w, (uint32_t)(nw & 1));
-                    ++nw;
-                    cur_slice = s;
                 }
-                const int buf = n & 1;
-                umma::mbar_wait(&acc_free[buf], (uint32_t)(((n >> 1) & 1) ^ 1));   // epilogue of item n-2 has drained it
-                umma::fence_after_sync();
-                const uint32_t dcol = tmem + (uint32_t)buf * 128u;
-                uint32_t acc = 0;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    umma::mbar_wait(&a_full[h], (uint32_t)(n & 1));
-                    umma::fence_after_sync();
-#pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
-                        uint64_t da = da0[h] + (uint64_t)((tap / 3) * HW + (tap % 3));
-                        uint64_t db = db0 + (uint64_t)((h * 9 + tap) * d.half_chunks * 8);
-                        for (int j = 0; j < ksteps; ++j, da += 2 * HPIX, db += 16) {
-                            umma::mma_f16(dcol, da, db, idesc, acc);
-                            acc = 1;
-                        }
-                    }
-                    umma::commit(&a_free[h]);                // this half may be refilled for the next item
-                }
-                umma::commit(&acc_full[buf]);
+                umma::mbar_wait(&bar_w, (uint32_t)(nw & 1));
+                ++nw;
+                cur_slice = s;
             }
+            const int buf = n & 1;
+            umma::mbar_wait(&acc_free[buf], (uint32_t)(((n >> 1) & 1) ^ 1));   // epilogue of item n-2 has drained it
+            umma::fence_after_sync();
+            const uint32_t dcol = tmem + (uint32_t)buf * 128u;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                umma::mbar_wait(&a_full[h], (uint32_t)(n & 1));
+                umma::fence_after_sync();
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+                    for (int j = 0; j < KSTEPS; ++j) {
+                        const uint64_t da = da0[h] + (uint64_t)((tap / 3) * HW + (tap % 3) + j * 2 * HPIX);
+                        const uint64_t db = db0 + (uint64_t)(((h * 9 + tap) * KSTEPS + j) * 16);
+                        if (leader) umma::mma_f16(dcol, da, db, idesc, (h | tap | j) != 0);
+                    }
+                }
+                if (leader) umma::commit(&a_free[h]);        // this half may be refilled for the next item
+            }
+            if (leader) umma::commit(&acc_full[buf]);
+            __syncwarp();
         }
     } else if (warp >= 4) {
         // ===================== loader warps: halo tile -> A operand (cp.async, zero fill outside the image) ==========
@@ -323,16 +335,24 @@ int ebfi_kpn_fused_forward(void *stream, const float *event_feat, const float *f
     const int total = d.nslice * d.ntile;
     const int grid = std::min(total, ebfi::sm_count());
     const int per = ceil_div(total, grid);
-#define EBFI_KPN(KS)                                                                                          \
+#define EBFI_KPN(KS, ST)                                                                                      \
     do {                                                                                                      \
-        EBFI_CUDA_OK(cudaFuncSetAttribute(kpn_fused_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        kpn_fused_kernel<KS><<<ceil_div(total, per), NTHR, smem, st>>>(featb, wimg, conv_bias, event_feat, output, d, per); \
+        EBFI_CUDA_OK(cudaFuncSetAttribute(kpn_fused_kernel<KS, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        kpn_fused_kernel<KS, ST><<<ceil_div(total, per), NTHR, smem, st>>>(featb, wimg, conv_bias, event_feat, output, d, per); \
     } while (0)
-    switch (d.K) {
-    case 1: EBFI_KPN(1); break;
-    case 3: EBFI_KPN(3); break;
-    default: EBFI_KPN(5); break;
+#define EBFI_KPN_K(KS)                                                                                        \
+    switch (d.Cin / 32) {                                                                                     \
+    case 1: EBFI_KPN(KS, 1); break;                                                                           \
+    case 2: EBFI_KPN(KS, 2); break;                                                                           \
+    case 3: EBFI_KPN(KS, 3); break;                                                                           \
+    default: EBFI_KPN(KS, 4); break;                                                                          \
     }
+    switch (d.K) {
+    case 1: EBFI_KPN_K(1); break;
+    case 3: EBFI_KPN_K(3); break;
+    default: EBFI_KPN_K(5); break;
+    }
+#undef EBFI_KPN_K
 #undef EBFI_KPN
     EBFI_LAUNCH_OK("kpn_fused_kernel");
     return EBFI_OK;
