@@ -18,8 +18,9 @@
 //               (bf16); for tap (dy, dx) the UMMA descriptor simply starts (dy*10 + dx) pixels later, with
 //               SBO = one halo row and LBO = one chunk plane: no im2col copy of any kind
 //   B operand   weights [80 rows][9*Cin], K-major, K order = (channel half, tap, 16-channel step)
-//   pipeline    loader warps fill the two channel halves of the halo alternately (the half that the tensor
-//               core has finished with is refilled for the next tile while the other half computes);
+//   pipeline    the halo is held as Cin/32 channel PARTS (32 channels, 11.5 KB each). One producer lane refills a
+//               part for the next tile with a single 3-D TMA tensor copy (zero fill outside the image = the
+//               conv's padding) as soon as the MMAs that read it have completed, while the other parts compute;
 //               two TMEM accumulators let the epilogue of item i overlap the MMAs of item i+1
 //   epilogue    thread = pixel: 75 accumulators -> + bias -> LeakyReLU -> x Event[c][clamp(y+ky-2)][clamp(x+kx-2)]
 //               summed in the reference's tap order (KernelConv2D_kernel.cu:44-50) -> 3 outputs
@@ -30,6 +31,7 @@
 #include "common.cuh"
 #include "umma.cuh"
 
+#include <cuda.h>        // CUtensorMap types; cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint
 #include <algorithm>
 
 namespace {
@@ -40,7 +42,9 @@ constexpr int TH = 16, TW = 8, TM = TH * TW;     // pixel tile
 constexpr int HH = TH + 2, HW = TW + 2;          // conv halo (3x3, pad 1)
 constexpr int HPIX = HH * HW;                    // 180 halo pixels
 constexpr int CPS = 3;                           // FAC channels per weight slice
-constexpr int NTHR = 288;                        // 4 epilogue warps + 4 loader warps + 1 MMA warp
+constexpr int NTHR = 192;                        // 4 epilogue warps + 1 TMA producer warp + 1 MMA warp
+constexpr int PART_CH = 32;                      // channels per halo part = two K = 16 MMA steps per tap
+constexpr int PART_BYTES = (PART_CH / 8) * HPIX * 16;
 constexpr int TMEM_COLS = 256;                   // two accumulators at columns 0 and 128
 
 struct KpnDims {
@@ -48,8 +52,8 @@ struct KpnDims {
     int nslice, NP;              // weight slices; GEMM N (padded to 16) of a full slice
     int tiles_x, tiles_y, ntile; // pixel tiles per sample row / column, per call
     int Ktot, kchunks;           // 9 * Cin; Cin / 8
-    int half_chunks;             // 8-channel chunks per channel half
-    int a_half_bytes, w_bytes;
+    int npart;                   // Cin / 32 halo parts
+    int w_bytes;
     float slope;
 };
 
@@ -76,7 +80,7 @@ __global__ void kpn_prep_input(const float *__restrict__ ev, const float *__rest
 }
 
 // conv weight (Ce*KK, Cin, 3, 3) fp32 -> per slice the shared-memory image [NP/8][Ktot/8][8 rows][8 k] bf16,
-// K order: chunk index = (half * 9 + tap) * half_chunks + j  <->  channel half * Cin/2 + j*8 + e
+// K order: chunk index = (part * 9 + tap) * 4 + j  <->  channel part * 32 + j*8 + e
 __global__ void kpn_prep_weights(const float *__restrict__ w, __nv_bfloat16 *__restrict__ wimg, KpnDims d)
 {
     const int per = d.NP * d.Ktot;
@@ -86,22 +90,14 @@ __global__ void kpn_prep_weights(const float *__restrict__ w, __nv_bfloat16 *__r
         const int e = e0 & 7, r = (e0 >> 3) & 7, rest = e0 >> 6;
         const int kc = rest % kch, rg = rest / kch;
         const int nrow = rg * 8 + r;
-        const int j = kc % d.half_chunks, ht = kc / d.half_chunks, tap = ht % 9, h = ht / 9;
-        const int ch = h * (d.Cin / 2) + j * 8 + e;
+        const int j = kc % 4, pt = kc / 4, tap = pt % 9, part = pt / 9;
+        const int ch = part * PART_CH + j * 8 + e;
         const int c0 = s * CPS, ncols = min(CPS, d.Ce - c0) * d.KK;
         float v = 0.f;
         if (nrow < ncols) v = __ldg(w + ((size_t)(c0 * d.KK + nrow) * d.Cin + ch) * 9 + tap);
         wimg[i] = __float2bfloat16_rn(v);
     }
 }
-
-// 16-byte asynchronous global -> shared copy; src_bytes = 0 writes zeros (the conv's zero padding)
-__device__ __forceinline__ void cp_async16_zfill(void *smem_dst, const void *gmem_src, uint32_t src_bytes)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(umma::smem_u32(smem_dst)), "l"(gmem_src), "r"(src_bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __device__ __forceinline__ bool elect_one()
 {
@@ -110,21 +106,29 @@ __device__ __forceinline__ bool elect_one()
     return pred != 0;
 }
 
-// K: FAC kernel size; KSTEPS: K = 16 MMA steps per (channel half, tap) = Cin / 32
-template <int K, int KSTEPS>
+// 3-D tiled TMA load global -> shared; out-of-range coordinates read as zero
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *tmap, int c0, int c1, int c2, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(umma::smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(umma::smem_u32(bar))
+                 : "memory");
+}
+
+// K: FAC kernel size; NPART: halo parts = Cin / 32
+template <int K, int NPART>
 __global__ void __launch_bounds__(NTHR, 1)
-kpn_fused_kernel(const __nv_bfloat16 *__restrict__ featb, const __nv_bfloat16 *__restrict__ wimg,
+kpn_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16 *__restrict__ wimg,
                  const float *__restrict__ bias, const float *__restrict__ ev, float *__restrict__ out,
                  KpnDims d, int items_per_cta)
 {
     constexpr int KK = K * K, R = (K - 1) / 2;
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *w_s = smem;                               // weight slice
-    unsigned char *a_s = smem + d.w_bytes;                   // two channel halves of the halo tile
-    __shared__ __align__(8) uint64_t bar_w, bar_wfree, a_full[2], a_free[2], acc_full[2], acc_free[2];
+    unsigned char *a_s = smem + d.w_bytes;                   // NPART channel parts of the halo tile
+    __shared__ __align__(8) uint64_t bar_w, bar_wfree, a_full[NPART], a_free[NPART], acc_full[2], acc_free[2];
     __shared__ uint32_t tmem_slot;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5;
     const int total = d.nslice * d.ntile;
     const int item0 = blockIdx.x * items_per_cta, item1 = min(total, item0 + items_per_cta);
 
@@ -132,12 +136,8 @@ kpn_fused_kernel(const __nv_bfloat16 *__restrict__ featb, const __nv_bfloat16 *_
     if (tid == 0) {
         umma::mbar_init(&bar_w, 1);
         umma::mbar_init(&bar_wfree, 1);
-        for (int i = 0; i < 2; ++i) {
-            umma::mbar_init(&a_full[i], 128);
-            umma::mbar_init(&a_free[i], 1);
-            umma::mbar_init(&acc_full[i], 1);
-            umma::mbar_init(&acc_free[i], 128);
-        }
+        for (int i = 0; i < NPART; ++i) { umma::mbar_init(&a_full[i], 1); umma::mbar_init(&a_free[i], 1); }
+        for (int i = 0; i < 2; ++i) { umma::mbar_init(&acc_full[i], 1); umma::mbar_init(&acc_free[i], 128); }
         umma::mbar_fence_init();
     }
     umma::fence_before_sync();
@@ -146,7 +146,7 @@ kpn_fused_kernel(const __nv_bfloat16 *__restrict__ featb, const __nv_bfloat16 *_
     const uint32_t tmem = tmem_slot;
     const int tiles_per_sample = d.tiles_x * d.tiles_y;
 
-    if (warp == 8) {
+    if (warp == 5) {
         // ===================== MMA issue + weight loads =====================
         // All 32 lanes run this loop with warp-uniform values (descriptor arithmetic stays on the uniform
         // datapath); only the tcgen05 / bulk-copy / commit instructions themselves are issued by one elected
@@ -154,10 +154,9 @@ kpn_fused_kernel(const __nv_bfloat16 *__restrict__ featb, const __nv_bfloat16 *_
         // tensor pipe sat idle 77 % of the time (profiles/README.md).
         const bool leader = elect_one();
         int cur_slice = -1, nw = 0;
-        const uint32_t w_sbo = (uint32_t)(36 * KSTEPS) * 128u;             // Ktot / 8 = 9 * Cin / 8 chunks of 128 bytes
+        const uint32_t w_sbo = (uint32_t)(36 * NPART) * 128u;              // Ktot / 8 = 9 * Cin / 8 chunks of 128 bytes
         // descriptors differ only in their 16-byte-granular start address (low 14 bits): build once, add offsets
-        const uint64_t da0[2] = {umma::smem_desc(umma::smem_u32(a_s), HPIX * 16u, HW * 16u),
-                                 umma::smem_desc(umma::smem_u32(a_s + d.a_half_bytes), HPIX * 16u, HW * 16u)};
+        const uint64_t da0 = umma::smem_desc(umma::smem_u32(a_s), HPIX * 16u, HW * 16u);
         const uint64_t db0 = umma::smem_desc(umma::smem_u32(w_s), 128u, w_sbo);
         for (int item = item0, n = 0; item < item1; ++item, ++n) {
             const int s = item / d.ntile;
@@ -183,45 +182,40 @@ kpn_fused_kernel(const __nv_bfloat16 *__restrict__ featb, const __nv_bfloat16 *_
             umma::fence_after_sync();
             const uint32_t dcol = tmem + (uint32_t)buf * 128u;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                umma::mbar_wait(&a_full[h], (uint32_t)(n & 1));
+            for (int part = 0; part < NPART; ++part) {
+                umma::mbar_wait(&a_full[part], (uint32_t)(n & 1));
                 umma::fence_after_sync();
 #pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
-                    for (int j = 0; j < KSTEPS; ++j) {
-                        const uint64_t da = da0[h] + (uint64_t)((tap / 3) * HW + (tap % 3) + j * 2 * HPIX);
-                        const uint64_t db = db0 + (uint64_t)(((h * 9 + tap) * KSTEPS + j) * 16);
-                        if (leader) umma::mma_f16(dcol, da, db, idesc, (h | tap | j) != 0);
+                    for (int j = 0; j < 2; ++j) {
+                        const uint64_t da = da0 + (uint64_t)(part * (PART_BYTES / 16) + (tap / 3) * HW + (tap % 3) + j * 2 * HPIX);
+                        const uint64_t db = db0 + (uint64_t)(((part * 9 + tap) * 2 + j) * 16);
+                        if (leader) umma::mma_f16(dcol, da, db, idesc, (part | tap | j) != 0);
                     }
                 }
-                if (leader) umma::commit(&a_free[h]);        // this half may be refilled for the next item
+                if (leader) umma::commit(&a_free[part]);     // this part may be refilled for the next item
             }
             if (leader) umma::commit(&acc_full[buf]);
             __syncwarp();
         }
-    } else if (warp >= 4) {
-        // ===================== loader warps: halo tile -> A operand (cp.async, zero fill outside the image) ==========
-        const int lt = tid - 128;
+    } else if (warp == 4) {
+        // ===================== producer warp: one TMA tensor copy per (item, part) =====================
+        const bool leader = elect_one();
         for (int item = item0, n = 0; item < item1; ++item, ++n) {
             const int t = item % d.ntile;
             const int b = t / tiles_per_sample, tt = t % tiles_per_sample;
             const int ty0 = (tt / d.tiles_x) * TH, tx0 = (tt % d.tiles_x) * TW;
-            for (int h = 0; h < 2; ++h) {
-                umma::mbar_wait(&a_free[h], (uint32_t)((n & 1) ^ 1));
-                unsigned char *dst = a_s + h * d.a_half_bytes;
-                const __nv_bfloat16 *src_h = featb + ((size_t)b * d.kchunks + h * d.half_chunks) * (size_t)d.H * d.W * 8;
-                for (int idx = lt; idx < d.half_chunks * HPIX; idx += 128) {
-                    const int kc = idx / HPIX, r = idx - kc * HPIX;
-                    const int y = ty0 - 1 + r / HW, x = tx0 - 1 + r % HW;
-                    const bool in = y >= 0 && y < d.H && x >= 0 && x < d.W;
-                    const __nv_bfloat16 *src = src_h + (((size_t)kc * d.H + (in ? y : 0)) * d.W + (in ? x : 0)) * 8;
-                    cp_async16_zfill(dst + (size_t)idx * 16, src, in ? 16u : 0u);
+#pragma unroll
+            for (int part = 0; part < NPART; ++part) {
+                umma::mbar_wait(&a_free[part], (uint32_t)((n & 1) ^ 1));
+                if (leader) {
+                    umma::mbar_expect_tx(&a_full[part], (uint32_t)PART_BYTES);
+                    tma_load_3d(a_s + part * PART_BYTES, &tmap, (tx0 - 1) * 8, ty0 - 1, b * d.kchunks + part * (PART_CH / 8),
+                                &a_full[part]);
                 }
-                cp_async_wait_all();
-                umma::fence_smem_to_async();
-                umma::mbar_arrive(&a_full[h]);
             }
+            __syncwarp();
         }
     } else {
         // ===================== epilogue warps: thread = pixel (TMEM lane) =====================
@@ -278,6 +272,39 @@ kpn_fused_kernel(const __nv_bfloat16 *__restrict__ featb, const __nv_bfloat16 *_
     if (warp == 0) umma::tmem_dealloc<TMEM_COLS>(tmem);
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled without linking libcuda: resolved through the (statically linked) runtime
+EncodeTiledFn encode_tiled()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// featb [B*kchunks][H][W*8] bf16, box = one halo part: [4 chunks][18 rows][10 pixels * 8 channels]
+int make_tmap(CUtensorMap &tm, const KpnDims &d, void *featb)
+{
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return ebfi::fail(EBFI_ERR_CUDA, "kpn_fused: cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t gdim[3] = {(cuuint64_t)d.W * 8, (cuuint64_t)d.H, (cuuint64_t)d.B * d.kchunks};
+    const cuuint64_t gstr[2] = {(cuuint64_t)d.W * 16, (cuuint64_t)d.H * d.W * 16};
+    const cuuint32_t box[3] = {HW * 8, HH, PART_CH / 8};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, featb, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return ebfi::fail(EBFI_ERR_CUDA, "kpn_fused: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return EBFI_OK;
+}
+
 int fill(KpnDims &d, int B, int Ce, int Cf, int H, int W, int K, float slope)
 {
     EBFI_REQUIRE(B > 0 && Ce > 0 && Cf >= 0 && H > 0 && W > 0, "kpn_fused: bad sizes");
@@ -289,8 +316,7 @@ int fill(KpnDims &d, int B, int Ce, int Cf, int H, int W, int K, float slope)
     d.NP = ebfi::round_up(CPS * d.KK, 16);
     d.tiles_x = ceil_div(W, TW); d.tiles_y = ceil_div(H, TH);
     d.ntile = B * d.tiles_x * d.tiles_y;
-    d.Ktot = 9 * d.Cin; d.kchunks = d.Cin / 8; d.half_chunks = d.Cin / 16;
-    d.a_half_bytes = d.half_chunks * HPIX * 16;
+    d.Ktot = 9 * d.Cin; d.kchunks = d.Cin / 8; d.npart = d.Cin / PART_CH;
     d.w_bytes = d.NP * d.Ktot * 2;
     EBFI_REQUIRE((long)d.nslice * d.ntile < (1L << 31), "kpn_fused: too many work items");
     return EBFI_OK;
@@ -331,14 +357,16 @@ int ebfi_kpn_fused_forward(void *stream, const float *event_feat, const float *f
     EBFI_LAUNCH_OK("kpn_prep_weights");
     kpn_prep_input<<<ebfi::sm_count() * 8, 256, 0, st>>>(event_feat, frame_feat, featb, d);
     EBFI_LAUNCH_OK("kpn_prep_input");
-    const int smem = d.w_bytes + 2 * d.a_half_bytes;
+    const int smem = d.w_bytes + d.npart * PART_BYTES;
+    CUtensorMap tmap;
+    if (int rc = make_tmap(tmap, d, featb)) return rc;
     const int total = d.nslice * d.ntile;
     const int grid = std::min(total, ebfi::sm_count());
     const int per = ceil_div(total, grid);
 #define EBFI_KPN(KS, ST)                                                                                      \
     do {                                                                                                      \
         EBFI_CUDA_OK(cudaFuncSetAttribute(kpn_fused_kernel<KS, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        kpn_fused_kernel<KS, ST><<<ceil_div(total, per), NTHR, smem, st>>>(featb, wimg, conv_bias, event_feat, output, d, per); \
+        kpn_fused_kernel<KS, ST><<<ceil_div(total, per), NTHR, smem, st>>>(tmap, wimg, conv_bias, event_feat, output, d, per); \
     } while (0)
 #define EBFI_KPN_K(KS)                                                                                        \
     switch (d.Cin / 32) {                                                                                     \
