@@ -22,8 +22,11 @@
 //               part for the next tile with a single 3-D TMA tensor copy (zero fill outside the image = the
 //               conv's padding) as soon as the MMAs that read it have completed, while the other parts compute;
 //               two TMEM accumulators let the epilogue of item i overlap the MMAs of item i+1
-//   epilogue    thread = pixel: 75 accumulators -> + bias -> LeakyReLU -> x Event[c][clamp(y+ky-2)][clamp(x+kx-2)]
-//               summed in the reference's tap order (KernelConv2D_kernel.cu:44-50) -> 3 outputs
+//   epilogue    three warpgroups, one per FAC channel of the slice; thread = (pixel, channel): its 25 Event window
+//               values are fetched BEFORE it waits for the accumulator, then 25 accumulators -> + bias -> LeakyReLU
+//               -> x Event[c][clamp(y+ky-2)][clamp(x+kx-2)], summed in the reference's tap order
+//               (KernelConv2D_kernel.cu:44-50) -> 1 output. (With one warpgroup doing all 75 columns after the
+//               wait, the epilogue's load latency was the bottleneck: tensor pipe 42 % busy.)
 //
 // Precision: tensors are fp32 at the boundary (like the reference); the conv operands are rounded to bf16
 // for the tensor cores, accumulation and the whole FAC part are fp32. Stated tolerance 1e-2 of max|out|
@@ -42,7 +45,8 @@ constexpr int TH = 16, TW = 8, TM = TH * TW;     // pixel tile
 constexpr int HH = TH + 2, HW = TW + 2;          // conv halo (3x3, pad 1)
 constexpr int HPIX = HH * HW;                    // 180 halo pixels
 constexpr int CPS = 3;                           // FAC channels per weight slice
-constexpr int NTHR = 192;                        // 4 epilogue warps + 1 TMA producer warp + 1 MMA warp
+constexpr int NEPI = CPS * 128;                  // epilogue threads: one warpgroup (128 TMEM lanes) per FAC channel of the slice
+constexpr int NTHR = NEPI + 64;                  // + 1 TMA producer warp + 1 MMA warp
 constexpr int PART_CH = 32;                      // channels per halo part = two K = 16 MMA steps per tap
 constexpr int PART_BYTES = (PART_CH / 8) * HPIX * 16;
 constexpr int TMEM_COLS = 256;                   // two accumulators at columns 0 and 128
@@ -114,6 +118,74 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *t
                  : "memory");
 }
 
+// Epilogue of warpgroup G: FAC channel c0 + G of every item's slice.
+template <int K, int G>
+__device__ __forceinline__ void kpn_epilogue(uint32_t tmem, uint64_t *acc_full, uint64_t *acc_free,
+                                             const float *__restrict__ bias, const float *__restrict__ ev,
+                                             float *__restrict__ out, const KpnDims &d, int item0, int item1)
+{
+    constexpr int KK = K * K, R = (K - 1) / 2;
+    constexpr int COL0 = (G * KK / 8) * 8, OFF = G * KK - COL0, NLD = (OFF + KK + 7) / 8;   // 8-column TMEM loads covering the channel
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = (warp & 3) * 32 + lane, py = p / TW, px = p % TW;
+    const uint32_t lane_base = (uint32_t)(warp & 3) * 32u;
+    const size_t plane = (size_t)d.H * d.W;
+    const int tiles_per_sample = d.tiles_x * d.tiles_y;
+    float bv[KK];
+    int bias_slice = -1;
+    for (int item = item0, n = 0; item < item1; ++item, ++n) {
+        const int s = item / d.ntile, t = item % d.ntile;
+        const int b = t / tiles_per_sample, tt = t % tiles_per_sample;
+        const int y = (tt / d.tiles_x) * TH + py, x = (tt % d.tiles_x) * TW + px;
+        const int c = s * CPS + G;
+        const bool active = c < d.Ce;                        // warp-uniform: the last slice may hold fewer channels
+        const bool valid = active && y < d.H && x < d.W;
+        // Event window of this pixel: independent of the accumulator -> in flight while waiting for it
+        float e[KK];
+        if (valid) {
+            const float *evc = ev + ((size_t)b * d.Ce + c) * plane;
+            int xo[K];
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx) xo[kx] = min(max(x + kx - R, 0), d.W - 1);   // ReplicationPad2d (KernelConv2D.py:82-86)
+#pragma unroll
+            for (int ky = 0; ky < K; ++ky) {
+                const float *row = evc + (size_t)min(max(y + ky - R, 0), d.H - 1) * d.W;
+#pragma unroll
+                for (int kx = 0; kx < K; ++kx) e[ky * K + kx] = __ldg(row + xo[kx]);
+            }
+        }
+        if (active && s != bias_slice) {
+#pragma unroll
+            for (int q = 0; q < KK; ++q) bv[q] = __ldg(bias + c * KK + q);
+            bias_slice = s;
+        }
+        const int buf = n & 1;
+        umma::mbar_wait(&acc_full[buf], (uint32_t)((n >> 1) & 1));
+        umma::fence_after_sync();
+        float v[NLD * 8];
+        if (active) {
+#pragma unroll
+            for (int q = 0; q < NLD; ++q) {
+                float (&vq)[8] = *reinterpret_cast<float (*)[8]>(&v[q * 8]);
+                umma::tmem_ld8(umma::tmem_addr(tmem, lane_base, buf * 128 + COL0 + q * 8), vq);
+            }
+            umma::tmem_ld_wait();
+        }
+        umma::fence_before_sync();
+        umma::mbar_arrive(&acc_free[buf]);                   // accumulator drained into registers: the next item may reuse it
+        if (valid) {
+            float res = 0.f;
+#pragma unroll
+            for (int q = 0; q < KK; ++q) {                   // tap order of KernelConv2D_kernel.cu:44-50
+                float a = v[OFF + q] + bv[q];
+                a = a > 0.f ? a : a * d.slope;               // nn.LeakyReLU
+                res += e[q] * a;
+            }
+            out[((size_t)b * d.Ce + c) * plane + (size_t)y * d.W + x] = res;
+        }
+    }
+}
+
 // K: FAC kernel size; NPART: halo parts = Cin / 32
 template <int K, int NPART>
 __global__ void __launch_bounds__(NTHR, 1)
@@ -137,7 +209,7 @@ kpn_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16 *
         umma::mbar_init(&bar_w, 1);
         umma::mbar_init(&bar_wfree, 1);
         for (int i = 0; i < NPART; ++i) { umma::mbar_init(&a_full[i], 1); umma::mbar_init(&a_free[i], 1); }
-        for (int i = 0; i < 2; ++i) { umma::mbar_init(&acc_full[i], 1); umma::mbar_init(&acc_free[i], 128); }
+        for (int i = 0; i < 2; ++i) { umma::mbar_init(&acc_full[i], 1); umma::mbar_init(&acc_free[i], NEPI); }
         umma::mbar_fence_init();
     }
     umma::fence_before_sync();
@@ -146,7 +218,7 @@ kpn_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16 *
     const uint32_t tmem = tmem_slot;
     const int tiles_per_sample = d.tiles_x * d.tiles_y;
 
-    if (warp == 5) {
+    if (warp == NEPI / 32 + 1) {
         // ===================== MMA issue + weight loads =====================
         // All 32 lanes run this loop with warp-uniform values (descriptor arithmetic stays on the uniform
         // datapath); only the tcgen05 / bulk-copy / commit instructions themselves are issued by one elected
@@ -199,7 +271,7 @@ kpn_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16 *
             if (leader) umma::commit(&acc_full[buf]);
             __syncwarp();
         }
-    } else if (warp == 4) {
+    } else if (warp == NEPI / 32) {
         // ===================== producer warp: one TMA tensor copy per (item, part) =====================
         const bool leader = elect_one();
         for (int item = item0, n = 0; item < item1; ++item, ++n) {
@@ -218,54 +290,11 @@ kpn_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16 *
             __syncwarp();
         }
     } else {
-        // ===================== epilogue warps: thread = pixel (TMEM lane) =====================
-        const int p = tid, py = p / TW, px = p % TW;
-        const uint32_t lane_base = (uint32_t)warp * 32u;
-        const size_t plane = (size_t)d.H * d.W;
-        constexpr int NLD = (CPS * KK + 7) / 8;              // 8-column TMEM loads of a full slice
-        for (int item = item0, n = 0; item < item1; ++item, ++n) {
-            const int s = item / d.ntile, t = item % d.ntile;
-            const int b = t / tiles_per_sample, tt = t % tiles_per_sample;
-            const int y = (tt / d.tiles_x) * TH + py, x = (tt % d.tiles_x) * TW + px;
-            const bool valid = y < d.H && x < d.W;
-            const int c0 = s * CPS, nc = min(CPS, d.Ce - c0);
-            const int buf = n & 1;
-            umma::mbar_wait(&acc_full[buf], (uint32_t)((n >> 1) & 1));
-            umma::fence_after_sync();
-            float v[NLD * 8];
-#pragma unroll
-            for (int q = 0; q < NLD; ++q) {
-                float (&vq)[8] = *reinterpret_cast<float (*)[8]>(&v[q * 8]);
-                if (q * 8 < nc * KK) umma::tmem_ld8(umma::tmem_addr(tmem, lane_base, buf * 128 + q * 8), vq);
-            }
-            umma::tmem_ld_wait();
-            umma::fence_before_sync();
-            umma::mbar_arrive(&acc_free[buf]);               // accumulator drained into registers: the next item may reuse it
-            if (valid) {
-                int xo[K];
-#pragma unroll
-                for (int kx = 0; kx < K; ++kx) xo[kx] = min(max(x + kx - R, 0), d.W - 1);   // ReplicationPad2d (KernelConv2D.py:82-86)
-#pragma unroll
-                for (int cc = 0; cc < CPS; ++cc) {
-                    if (cc < nc) {
-                        const float *evc = ev + ((size_t)b * d.Ce + c0 + cc) * plane;
-                        const float *bc = bias + (c0 + cc) * KK;
-                        float res = 0.f;
-#pragma unroll
-                        for (int ky = 0; ky < K; ++ky) {
-                            const float *row = evc + (size_t)min(max(y + ky - R, 0), d.H - 1) * d.W;
-#pragma unroll
-                            for (int kx = 0; kx < K; ++kx) {
-                                float a = v[cc * KK + ky * K + kx] + __ldg(bc + ky * K + kx);
-                                a = a > 0.f ? a : a * d.slope;                 // nn.LeakyReLU
-                                res += __ldg(row + xo[kx]) * a;                // tap order of KernelConv2D_kernel.cu:44-50
-                            }
-                        }
-                        out[((size_t)b * d.Ce + c0 + cc) * plane + (size_t)y * d.W + x] = res;
-                    }
-                }
-            }
-        }
+        // ===================== epilogue warpgroups: thread = (pixel = TMEM lane, FAC channel G of the slice) ==========
+        const int g = warp >> 2;
+        if (g == 0) kpn_epilogue<K, 0>(tmem, acc_full, acc_free, bias, ev, out, d, item0, item1);
+        else if (g == 1) kpn_epilogue<K, 1>(tmem, acc_full, acc_free, bias, ev, out, d, item0, item1);
+        else kpn_epilogue<K, 2>(tmem, acc_full, acc_free, bias, ev, out, d, item0, item1);
     }
     umma::fence_before_sync();
     __syncthreads();
