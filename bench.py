@@ -322,6 +322,11 @@ def run_ours(args):
                                       "h2d_bytes": 13 * NEV}
         del exs, eys, ets, eps_, rxs, rys, rts, rps, feeder
 
+    # ---- SURVEY 8f widenings, reported beside the headline metric (rank 0, N=1 runs only)
+    widen = None
+    if rank == 0 and world == 1 and not args.kernels_only:
+        widen = widening_numbers(torch, dev, d, timed)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -362,6 +367,7 @@ def run_ours(args):
                 "api": "ebfi_be_b200.host_pipeline (dcn_v2_conv / KernelConv2DFunction autograd, pinned host in/out, "
                        "per-sample H2D | compute | D2H on three streams)"},
         "events": events,
+        "widening": widen,
         "gpu_launches": LAUNCHES_PER_STEP * args.steps,
         "clocks": clk.summary(),
     }
@@ -373,6 +379,53 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def widening_numbers(torch, dev, d, timed):
+    """The two operator-level widenings of SURVEY 8f at the benchmark shapes, each against the reference's own op
+    sequence on the same GPU (torch/cuDNN ops + this repo's unfused operators), L2 flushed before every call."""
+    from ebfi_be_b200 import dcn_v2, modification
+    from ebfi_be_b200.kernelconv2d import KernelConv2D
+    out = {}
+    with torch.no_grad():
+        # rank 1: KernelConv (3x3 conv 128 -> 1600, LeakyReLU) -> KPN, model_singleframe.py:145-146,161-162
+        ev, fr = d["xi"][:, :, 2:-2, 2:-2].contiguous(), d["go_f"]
+        conv = torch.nn.Conv2d(2 * C, C * K_FAC * K_FAC, 3, 1, 1).to(dev)
+        act, kpn = torch.nn.LeakyReLU(), KernelConv2D(kernel_size=K_FAC)
+        t_ref = timed(lambda: kpn(ev, act(conv(torch.cat([ev, fr], 1)))), n=5)
+        t_fused = timed(lambda: modification.kernelconv_fac_fused(ev, fr, conv.weight, conv.bias, K_FAC, 0.01), n=5)
+        flops = 2.0 * B_FAC * H * W * (C * K_FAC * K_FAC) * (2 * C * 9)
+        out["kernelconv_to_fac_forward"] = {
+            "workload": f"B={B_FAC} C={C} K={K_FAC} {H}x{W}, fp32 tensors (conv operands bf16 on the tensor cores)",
+            "reference_sequence_ms": round(t_ref, 4), "fused_ms": round(t_fused, 4), "speedup": round(t_ref / t_fused, 2),
+            "fused_TFLOPs": round(flops / (t_fused * 1e-3) / 1e12, 1),
+            "note": "reference sequence = cuDNN conv (TF32, torch default) + LeakyReLU + this repo's FAC forward; the "
+                    "1.68 GB kernel tensor is never materialised by the fused kernel"}
+        del conv
+    # rank 2: DCN_sep tail (chunk, cat, mean|offset| + host sync, sigmoid, op) forward + backward, dcn_v2.py:217-227
+    x = d["x"].clone().requires_grad_()
+    om = torch.cat([d["off"], torch.logit(d["msk"].clamp(1e-4, 1 - 1e-4))], 1).requires_grad_()
+    w, b = d["w"].clone().requires_grad_(), d["b"].clone().requires_grad_()
+    watch = dcn_v2._OffsetWatch()
+
+    def ref_tail():
+        o1, o2, mask = torch.chunk(om, 3, dim=1)
+        offset = torch.cat((o1, o2), dim=1)
+        if torch.mean(torch.abs(offset)) > 100:
+            pass
+        dcn_v2.dcn_v2_conv(x, offset, torch.sigmoid(mask), w, b, 1, 1, 1, DG).backward(d["go_d"])
+
+    def packed_tail():
+        watch.poll()
+        stat = torch.empty(1, device=dev)
+        o = dcn_v2.dcn_v2_conv_packed(x, om, w, b, 1, 1, 1, DG, stat)
+        watch.submit(stat, om.numel() // 3 * 2)
+        o.backward(d["go_d"])
+
+    t_ref, t_pk = timed(ref_tail, n=10), timed(packed_tail, n=10)
+    out["dcn_sep_tail_fwd_bwd"] = {"workload": "cfg1 (B=1, 64->64, 3x3, dg=8, 256x256)", "reference_sequence_ms": round(t_ref, 4),
+                                   "packed_ms": round(t_pk, 4), "speedup": round(t_ref / t_pk, 2)}
+    return out
 
 
 def _load_ref_ext(subdir, name):
