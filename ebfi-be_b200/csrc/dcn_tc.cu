@@ -85,40 +85,46 @@ dcn_fwd_tc_kernel(const float *__restrict__ in_blk,
         // ================= controller warp: weight prefetch + MMA issue, one elected lane =================
         // Keeping this off the sampler warps takes the serial issue of 9 MMAs + descriptors per stage out
         // of their critical path (with it on thread 0, a stage cost T_sample + T_issue; now max of the two).
-        if (lane == 0) {
-            const uint32_t idesc = umma::instr_desc_tf32(TM, d.Co, 0, 0);
-            const uint32_t wb = 2u * (uint32_t)pl.b_bytes;
-            int step = 0;
-            for (int n = 0; n < total_stages; ++n) {
-                const int bi = n & 1;
-                if (n == 0) {
+        // All lanes run the loop with warp-uniform values (uniform datapath); one elected lane issues.
+        const bool leader = umma::elect_one();
+        const uint32_t idesc = umma::instr_desc_tf32(TM, d.Co, 0, 0);
+        const uint32_t wb = 2u * (uint32_t)pl.b_bytes;
+        const int ksteps = pl.Ksp / 8;
+        int step = 0;
+        for (int n = 0; n < total_stages; ++n) {
+            const int bi = n & 1;
+            if (n == 0) {
+                if (leader)
                     for (int ns = 0; ns < 3 && ns < total_stages; ++ns) {
                         umma::mbar_expect_tx(&bar_w[ns & 3], wb);
                         umma::bulk_g2s(wring + (ns & 3) * wb, wimg + (size_t)ns * (wb / 4), wb, &bar_w[ns & 3]);
                     }
-                } else if (n + 2 < total_stages) {
-                    // ring slot (n+2) & 3 was read by stage n-2: wait for its MMAs, then refill it
-                    if (n >= 2) umma::mbar_wait(&bar_free[bi], (uint32_t)(((n - 2) >> 1) & 1));
-                    const int ns = n + 2;
+            } else if (n + 2 < total_stages) {
+                // ring slot (n+2) & 3 was read by stage n-2: wait for its MMAs, then refill it
+                if (n >= 2) umma::mbar_wait(&bar_free[bi], (uint32_t)(((n - 2) >> 1) & 1));
+                const int ns = n + 2;
+                if (leader) {
                     umma::mbar_expect_tx(&bar_w[ns & 3], wb);
                     umma::bulk_g2s(wring + (ns & 3) * wb, wimg + (size_t)ns * (wb / 4), wb, &bar_w[ns & 3]);
                 }
-                umma::mbar_wait(&bar_w[n & 3], (uint32_t)((n >> 2) & 1));
-                umma::mbar_wait(&bar_full[bi], (uint32_t)((n >> 1) & 1));
-                umma::fence_after_sync();
-                const uint32_t ah = umma::smem_u32(opnd + bi * 2 * pl.a_bytes), al = ah + (uint32_t)pl.a_bytes;
-                const uint32_t bh = umma::smem_u32(wring + (n & 3) * wb), bl = bh + (uint32_t)pl.b_bytes;
-                for (int ks = 0; ks < pl.Ksp / 8; ++ks, ++step) {
-                    const uint32_t ko = (uint32_t)ks * 256u;
-                    const uint64_t dah = umma::smem_desc(ah + ko, 128, sbo), dal = umma::smem_desc(al + ko, 128, sbo);
-                    const uint64_t dbh = umma::smem_desc(bh + ko, 128, sbo), dbl = umma::smem_desc(bl + ko, 128, sbo);
-                    const uint32_t d_x = tmem + pl.nacc * d.Co, d_h = tmem + (step % pl.nacc) * d.Co;
+            }
+            umma::mbar_wait(&bar_w[n & 3], (uint32_t)((n >> 2) & 1));
+            umma::mbar_wait(&bar_full[bi], (uint32_t)((n >> 1) & 1));
+            umma::fence_after_sync();
+            const uint32_t ah = umma::smem_u32(opnd + bi * 2 * pl.a_bytes), bh = umma::smem_u32(wring + (n & 3) * wb);
+            // descriptors of K-step ks = descriptor of step 0 + ks * 256 bytes (start-address field, 16-byte units)
+            uint64_t dah = umma::smem_desc(ah, 128, sbo), dal = umma::smem_desc(ah + (uint32_t)pl.a_bytes, 128, sbo);
+            uint64_t dbh = umma::smem_desc(bh, 128, sbo), dbl = umma::smem_desc(bh + (uint32_t)pl.b_bytes, 128, sbo);
+            for (int ks = 0; ks < ksteps; ++ks, ++step, dah += 16, dal += 16, dbh += 16, dbl += 16) {
+                const uint32_t d_x = tmem + pl.nacc * d.Co, d_h = tmem + (step % pl.nacc) * d.Co;
+                if (leader) {
                     umma::mma_tf32(d_x, dal, dbh, idesc, step > 0);
                     umma::mma_tf32(d_x, dah, dbl, idesc, true);
                     umma::mma_tf32(d_h, dah, dbh, idesc, step >= pl.nacc);
                 }
-                umma::commit(&bar_free[bi]);
             }
+            if (leader) umma::commit(&bar_free[bi]);
+            __syncwarp();
         }
     } else {
         // ================= sampler warps: thread (pixel p, row r) =================

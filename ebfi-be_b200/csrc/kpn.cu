@@ -103,13 +103,6 @@ __global__ void kpn_prep_weights(const float *__restrict__ w, __nv_bfloat16 *__r
     }
 }
 
-__device__ __forceinline__ bool elect_one()
-{
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-
 // 3-D tiled TMA load global -> shared; out-of-range coordinates read as zero
 __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *tmap, int c0, int c1, int c2, uint64_t *bar)
 {
@@ -224,7 +217,7 @@ kpn_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16 *
         // datapath); only the tcgen05 / bulk-copy / commit instructions themselves are issued by one elected
         // lane. With `if (lane == 0)` around the whole loop the issue cost was ~40 instructions per MMA and the
         // tensor pipe sat idle 77 % of the time (profiles/README.md).
-        const bool leader = elect_one();
+        const bool leader = umma::elect_one();
         int cur_slice = -1, nw = 0;
         const uint32_t w_sbo = (uint32_t)(36 * NPART) * 128u;              // Ktot / 8 = 9 * Cin / 8 chunks of 128 bytes
         // descriptors differ only in their 16-byte-granular start address (low 14 bits): build once, add offsets
@@ -273,7 +266,7 @@ kpn_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16 *
         }
     } else if (warp == NEPI / 32) {
         // ===================== producer warp: one TMA tensor copy per (item, part) =====================
-        const bool leader = elect_one();
+        const bool leader = umma::elect_one();
         for (int item = item0, n = 0; item < item1; ++item, ++n) {
             const int t = item % d.ntile;
             const int b = t / tiles_per_sample, tt = t % tiles_per_sample;

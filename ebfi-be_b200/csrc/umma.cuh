@@ -116,6 +116,16 @@ __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence
 // (tensor core / bulk copy) — required between st.shared of an operand and the MMA.
 __device__ __forceinline__ void fence_smem_to_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// One lane of a converged warp. Pattern for the MMA-issuing warp: ALL lanes run the (warp-uniform) issue loop so
+// that descriptor arithmetic stays on the uniform datapath, and only the tcgen05 / bulk-copy / commit instructions
+// are predicated on the elected lane — `if (lane == 0) { whole loop }` costs ~40 instructions per MMA instead of ~4.
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- mbarrier -----------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
