@@ -51,6 +51,8 @@ SIGNATURES = {
     "ebfi_events_to_voxel": (c_int, [c_void] * 5 + [c_int, c_i64, c_int, c_int, c_int, c_void, c_int]),
     "ebfi_events_to_stack": (c_int, [c_void] * 5 + [c_int, c_i64, c_int, c_int, c_int, c_void, c_void, c_int, c_void]),
     "ebfi_events_raw_to_stack": (c_int, [c_void] * 5 + [c_i64, c_int, c_int, c_int, c_void, c_void, c_int]),
+    "ebfi_frame_to_lap": (c_int, [c_void] * 3 + [c_int] * 3),
+    "ebfi_frame_to_dcp": (c_int, [c_void] * 4 + [c_int] * 4),
     "ebfi_selftest_gemm_tf32x3": (c_int, [c_void] * 4 + [c_int] * 4),
     "ebfi_selftest_gemm_bf16x3": (c_int, [c_void] * 4 + [c_int] * 4),
     "ebfi_selftest_umma_probe": (c_int, [c_void, c_void, c_int, c_int, c_int]),

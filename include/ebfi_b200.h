@@ -247,6 +247,19 @@ int ebfi_events_raw_to_stack(void *stream, const int16_t *xs, const int16_t *ys,
                              const int8_t *ps, int64_t n_events, int num_bins, int height, int width,
                              float *stack, int64_t *bounds, int bins_major);
 
+/* ---- per-frame maps the model computes on the host ---------- */
+
+/* Frame2Lap (myutils/utils.py:34-49; model_singleframe.py:311-326): frames (B, 3, H, W) fp32 in [0, 1] ->
+ * (im*255).astype(uint8) -> cv2.cvtColor(BGR2GRAY) -> cv2.Laplacian(CV_64F) -> lap (B, 1, H, W) fp32.
+ * Integer arithmetic, bit-identical to OpenCV >= 4 (15-bit gray coefficients, BORDER_REFLECT_101). */
+int ebfi_frame_to_lap(void *stream, const float *frames, float *lap, int batch, int height, int width);
+
+/* Frame2DCP (myutils/utils.py:15-31): dark channel = min over the 3 channels, then cv2.erode with a
+ * window x window rectangle (35 in the reference) = window minimum, pixels outside the image ignored.
+ * dark (B, 1, H, W); scratch (B, H, W) fp32. Bit-identical to OpenCV. */
+int ebfi_frame_to_dcp(void *stream, const float *frames, float *dark, float *scratch,
+                      int batch, int height, int width, int window);
+
 /* ---- self test --------------------------------------------------------------- */
 
 /* One-CTA GEMM on the tcgen05 tensor-core path with the 3xTF32 split the DCN kernels use:

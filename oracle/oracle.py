@@ -216,3 +216,36 @@ def kpn_fused_forward(event_feat, frame_feat, conv_weight, conv_bias, K, negativ
             for kx in range(K):
                 out[:, c] += evp[:, c, ky:ky + H, kx:kx + W] * ker[:, c * K * K + ky * K + kx]
     return out, ker
+
+
+def frame_to_lap(ims):
+    """Frame2Lap (myutils/utils.py:34-49) restated with the arithmetic OpenCV >= 4 uses: uint8 cast of im*255,
+    15-bit fixed-point BGR2GRAY, 4-neighbour Laplacian with BORDER_REFLECT_101. (B,3,H,W) -> (B,1,H,W) float32."""
+    ims = np.asarray(ims, np.float32)
+    u8 = (ims * np.float32(255)).astype(np.int64) & 0xFF
+    gray = (3735 * u8[:, 0] + 19235 * u8[:, 1] + 9798 * u8[:, 2] + (1 << 14)) >> 15
+    H, W = gray.shape[1:]
+    ry = np.array([_reflect101(i, H) for i in range(-1, H + 1)])
+    rx = np.array([_reflect101(i, W) for i in range(-1, W + 1)])
+    p = gray[:, ry][:, :, rx]
+    lap = p[:, :-2, 1:-1] + p[:, 2:, 1:-1] + p[:, 1:-1, :-2] + p[:, 1:-1, 2:] - 4 * gray
+    return lap[:, None].astype(np.float32)
+
+
+def _reflect101(i, n):
+    if n == 1:
+        return 0
+    while i < 0 or i >= n:
+        i = -i if i < 0 else 2 * n - 2 - i
+    return i
+
+
+def frame_to_dcp(ims, sz=35):
+    """Frame2DCP (myutils/utils.py:15-31): channel minimum, then cv2.erode with a sz x sz rectangle = window minimum
+    with anchor sz//2, pixels outside the image ignored. (B,3,H,W) -> (B,1,H,W) float32."""
+    ims = np.asarray(ims, np.float32)
+    dc = ims.min(axis=1)
+    a = sz // 2
+    pad = np.pad(dc, ((0, 0), (a, sz - 1 - a), (a, sz - 1 - a)), constant_values=np.inf)
+    from numpy.lib.stride_tricks import sliding_window_view
+    return sliding_window_view(pad, (sz, sz), axis=(1, 2)).min(axis=(3, 4))[:, None].astype(np.float32)

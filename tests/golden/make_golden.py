@@ -191,6 +191,39 @@ def events_raw_cases():
     save("events_raw", **out)
 
 
+def frame_cases():
+    """myutils/utils.py:15-49 (Frame2DCP, Frame2Lap) executed with the OpenCV of this image. The module itself imports
+    the trainer's data-list code and calls .cuda(); its two function bodies are restated without the device move."""
+    import cv2
+
+    def Frame2DCP(ims, sz=35):                                            # utils.py:15-31
+        out = []
+        for i in range(ims.size(0)):
+            im = ims[i].permute(1, 2, 0).cpu().numpy()
+            b, g, r = cv2.split(im)
+            dc = cv2.min(cv2.min(r, g), b)
+            kernel = cv2.getStructuringElement(cv2.MORPH_RECT, (sz, sz))
+            out.append(torch.from_numpy(cv2.erode(dc, kernel)).unsqueeze(0))
+        return torch.stack(out, dim=0)
+
+    def Frame2Lap(ims):                                                   # utils.py:34-49
+        out = []
+        for i in range(ims.size(0)):
+            im = ims[i].permute(1, 2, 0).cpu().numpy()
+            im = (im * 255).astype(np.uint8)
+            gray = cv2.cvtColor(im, cv2.COLOR_BGR2GRAY)
+            out.append(torch.from_numpy(cv2.Laplacian(gray, cv2.CV_64F).astype('float32')).unsqueeze(0))
+        return torch.stack(out, dim=0)
+
+    g = torch.Generator().manual_seed(41)
+    frames = torch.rand(2, 3, 45, 52, generator=g)
+    frames[0, :, 0, 0] = 1.0                                              # exactly 255 after the cast
+    frames[1, :, 10:14, 20:30] = 0.0
+    tiny = torch.rand(1, 3, 1, 7, generator=g)                            # single row: reflect-101 degenerates
+    save("frames", cv2_version=np.array(cv2.__version__), frames=frames, lap=Frame2Lap(frames), dcp35=Frame2DCP(frames),
+         dcp4=Frame2DCP(frames, 4), dcp1=Frame2DCP(frames, 1), tiny=tiny, tiny_lap=Frame2Lap(tiny), tiny_dcp=Frame2DCP(tiny, 35))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     dcn_zero_offset()
@@ -208,3 +241,4 @@ if __name__ == "__main__":
     fac_case("fac_k5_odd", 24, 1, 2, 5, 7, 13)
     events_cases()
     events_raw_cases()
+    frame_cases()

@@ -124,3 +124,14 @@ def test_kpn_oracle_matches_torch_op_sequence(oracle):
     # the bf16 rounding helper is torch's round-to-nearest-even
     x = rng.standard_normal(1000).astype(np.float32) * 3
     assert np.array_equal(oracle._bf16_round(x), torch.from_numpy(x).bfloat16().float().numpy())
+
+
+def test_frame_maps_match_opencv_golden(oracle):
+    """oracle.frame_to_lap / frame_to_dcp vs Frame2Lap / Frame2DCP (myutils/utils.py:15-49) run with OpenCV
+    (tests/golden/make_golden.py::frame_cases) — integer / min arithmetic: bit-exact."""
+    g = load_golden("frames")
+    assert np.array_equal(oracle.frame_to_lap(g["frames"]), g["lap"])
+    assert np.array_equal(oracle.frame_to_lap(g["tiny"]), g["tiny_lap"])
+    for sz, key in ((35, "dcp35"), (4, "dcp4"), (1, "dcp1")):
+        assert np.array_equal(oracle.frame_to_dcp(g["frames"], sz), g[key]), sz
+    assert np.array_equal(oracle.frame_to_dcp(g["tiny"], 35), g["tiny_dcp"])
