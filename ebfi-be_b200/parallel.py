@@ -40,23 +40,40 @@ def shard_batch(*tensors, rank=None, world_size=None):
     return out if len(out) > 1 else out[0]
 
 
-def allreduce_weight_grads(grads, group=None, average=False):
+class _BucketWork:
+    """Handle of an in-flight flat-bucket all-reduce; `wait()` orders the current stream after the collective
+    and copies the reduced values back into the gradient tensors."""
+
+    def __init__(self, grads, flat, work, scale):
+        self.grads, self.flat, self.work, self.scale = grads, flat, work, scale
+
+    def wait(self):
+        if self.work is not None:
+            self.work.wait()
+            self.work = None
+            if self.scale != 1.0:
+                self.flat *= self.scale
+            o = 0
+            for g in self.grads:
+                n = g.numel()
+                g.copy_(self.flat[o:o + n].view_as(g))
+                o += n
+        return self.grads
+
+
+def allreduce_weight_grads(grads, group=None, average=False, async_op=False):
     """Sum (or average) parameter gradients across ranks with ONE collective: the tensors are packed
     into a flat bucket, all-reduced, and copied back in place. Deterministic for a fixed world size
-    (NCCL/gloo ring order is fixed). Returns the list it was given."""
+    (NCCL/gloo ring order is fixed). Returns the list it was given — or, with async_op=True, a handle
+    whose `wait()` does the copy-back: the collective (147 KB: pure latency, ~0.15 ms on 8 GPUs) then runs on
+    NCCL's stream underneath whatever is launched in between (the FAC kernels of the same step)."""
     grads = [g for g in grads if g is not None]
     if not grads or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return grads
+        return _BucketWork(grads, None, None, 1.0) if async_op else grads
     flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    if average:
-        flat /= dist.get_world_size(group)
-    o = 0
-    for g in grads:
-        n = g.numel()
-        g.copy_(flat[o:o + n].view_as(g))
-        o += n
-    return grads
+    scale = 1.0 / dist.get_world_size(group) if average else 1.0
+    handle = _BucketWork(grads, flat, dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True), scale)
+    return handle if async_op else handle.wait()
 
 
 def dcn_backward_data_parallel(backward_fn, input, weight, bias, offset, mask, grad_output, *geom, group=None):

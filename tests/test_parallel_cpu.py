@@ -45,6 +45,12 @@ def _worker(rank, world_size, port, q):
     res = parallel.dcn_backward_data_parallel(_oracle_backward, x, w, b, off, msk, go, *geom)
     s, e = parallel.shard_range(x.shape[0])
     enc = parallel.encode_windows_data_parallel(lambda a, k: a * k, [(np.arange(3), i) for i in range(5)])
+    # asynchronous bucket: other work may be issued between the call and wait(); averaged variant
+    a, c = torch.full((3, 2), float(rank + 1)), torch.full((5,), 10.0 * (rank + 1))
+    h = parallel.allreduce_weight_grads([a, None, c], average=True, async_op=True)
+    busy = torch.ones(4).sum()
+    h.wait()
+    assert float(busy) == 4 and torch.equal(a, torch.full((3, 2), 1.5)) and torch.equal(c, torch.full((5,), 15.0))
     q.put((rank, s, e, [t.numpy() for t in res], [(i, v.tolist()) for i, v in enc]))
     dist.barrier()
     dist.destroy_process_group()
