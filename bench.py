@@ -177,22 +177,41 @@ def run_ours(args):
     gi_f, gk_f = torch.empty_like(d["xi"]), torch.empty_like(d["ker"])
     op_names = ["dcn_fwd", "dcn_bwd", "fac_fwd", "fac_bwd"]
 
+    # The four operator calls of a step, each through the drop-in extension module. After the warm-up they are
+    # captured into one CUDA graph per operator and replayed: a step then costs four graph launches on the host
+    # instead of ~9 kernel launches + a dozen allocator calls from Python, which matters when 8 ranks share the
+    # host's cores (the GPUs were starved at N = 8: 1.74 ms per step for 1.41 ms of kernels). `--no-graphs` keeps
+    # the eager calls.
+    ops = {
+        "dcn_fwd": lambda: _ext.dcn_v2_forward(d["x"], d["w"], d["b"], d["off"], d["msk"], *geom),
+        "dcn_bwd": lambda: _ext.dcn_v2_backward(d["x"], d["w"], d["b"], d["off"], d["msk"], d["go_d"], *geom),
+        "fac_fwd": lambda: kc.forward(d["xi"], d["ker"], K_FAC, out_f),
+        "fac_bwd": lambda: kc.backward(d["xi"], d["ker"], K_FAC, d["go_f"], gi_f, gk_f),
+    }
+    graphs, graph_out = {}, {}
+
+    def run(name):
+        if name in graphs:
+            graphs[name].replay()
+            return graph_out[name]
+        return ops[name]()
+
     def step(marks=None):
-        """One pass of the hot path, device-resident, through the drop-in extension modules."""
+        """One pass of the hot path, device-resident."""
         def mark():
             if marks is not None:
                 e = ev(); e.record(); marks.append(e)
         mark()
-        _ext.dcn_v2_forward(d["x"], d["w"], d["b"], d["off"], d["msk"], *geom)
+        run("dcn_fwd")
         mark()
-        grads = _ext.dcn_v2_backward(d["x"], d["w"], d["b"], d["off"], d["msk"], d["go_d"], *geom)
+        grads = run("dcn_bwd")
         # data-parallel weight-gradient all-reduce (the only collective on the path): ONE flat bucket, issued
         # asynchronously so that its latency hides under the FAC kernels; completed before the step ends
         pending = parallel.allreduce_weight_grads(grads[3:5], async_op=True) if world > 1 else None
         mark()
-        kc.forward(d["xi"], d["ker"], K_FAC, out_f)
+        run("fac_fwd")
         mark()
-        kc.backward(d["xi"], d["ker"], K_FAC, d["go_f"], gi_f, gk_f)
+        run("fac_bwd")
         if pending is not None:
             pending.wait()
         mark()
@@ -200,6 +219,15 @@ def run_ours(args):
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
+    if not args.no_graphs:
+        for name, fn in ops.items():
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                graph_out[name] = fn()
+            graphs[name] = g
+        for _ in range(max(3, args.warmup)):      # warm the replay path as well
+            step()
+        torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -372,6 +400,7 @@ def run_ours(args):
         "events": events,
         "widening": widen,
         "gpu_launches": LAUNCHES_PER_STEP * args.steps,
+        "launch_mode": "eager" if args.no_graphs else "one CUDA graph per operator call (4 replays per step)",
         "clocks": clk.summary(),
     }
     if world == 1 and not (args.no_cpu_baseline or args.kernels_only):
@@ -600,6 +629,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="eager operator calls instead of CUDA-graph replays")
     ap.add_argument("--kernels-only", action="store_true",
                     help="profiling runs: skip the e2e, cold-breakdown and CPU-baseline legs")
     args = ap.parse_args()
