@@ -135,6 +135,17 @@ class ClockSampler:
                 "samples": len(sm), "source": self.source}
 
 
+def _bind_to_gpu_numa_node(torch, dev):
+    """Multi-rank runs: pin this process to the CPUs NVML reports as local to its GPU, so that the pinned host
+    buffers of the e2e leg are allocated on the GPU's NUMA node (one process per GPU, all ranks share the host)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByUUID(_gpu_uuid(torch, dev)))
+    except Exception:
+        pass
+
+
 def _gpu_uuid(torch, dev):
     try:
         return "GPU-" + str(torch.cuda.get_device_properties(dev).uuid)
@@ -168,6 +179,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        _bind_to_gpu_numa_node(torch, dev)
     ebfi_be_b200._lib.load()
     host = make_inputs(torch, dev, 1234 + rank)
     d = {k: v.to(dev) for k, v in host.items()}
