@@ -343,6 +343,22 @@ def run_ours(args):
                                   "algorithmic_GBps": round((16 * NEV + 4 * 5 * EH * EW) / (t_vox * 1e-3) / 1e9, 1)},
                   "stack_16bins": {"ms": round(t_stk, 4), "Mev_s": round(NEV / 1e6 / (t_stk * 1e-3), 1),
                                    "algorithmic_GBps": round((16 * NEV + 4 * 32 * EH * EW) / (t_stk * 1e-3) / 1e9, 1)}}
+        # clustered events (90 % of them on Gaussian blobs covering ~1 % of the pixels) expose the
+        # atomic contention of the scatter
+        nb = int(0.9 * NEV)
+        cidx = torch.randint(0, 8, (nb,), generator=g)
+        cx = torch.tensor([160., 480, 800, 1120, 320, 640, 960, 200])[cidx] + 16 * torch.randn(nb, generator=g)
+        cy = torch.tensor([180., 540, 360, 180, 540, 120, 600, 400])[cidx] + 16 * torch.randn(nb, generator=g)
+        cxs = torch.cat([cx.clamp(0, EW - 1).floor(), torch.randint(0, EW, (NEV - nb,), generator=g).float()]).to(dev)
+        cys = torch.cat([cy.clamp(0, EH - 1).floor(), torch.randint(0, EH, (NEV - nb,), generator=g).float()]).to(dev)
+        perm = torch.randperm(NEV, generator=g).to(dev)
+        cxs, cys = cxs[perm].contiguous(), cys[perm].contiguous()
+        t_cv = timed(lambda: encodings.events_to_voxel(cxs, cys, ets, eps_, 5, sensor_size=(EH, EW)), n=10)
+        t_cs = timed(lambda: encodings.events_to_stack(cxs, cys, ets, eps_, 16, sensor_size=(EH, EW)), n=10)
+        events["clustered_90pct_on_1pct_of_pixels"] = {
+            "voxel_5bins": {"ms": round(t_cv, 4), "Mev_s": round(NEV / 1e6 / (t_cv * 1e-3), 1)},
+            "stack_16bins": {"ms": round(t_cs, 4), "Mev_s": round(NEV / 1e6 / (t_cs * 1e-3), 1)}}
+        del cxs, cys, perm
         # the datasets' path on the on-disk dtypes (int16, int16, float64, int8): device-resident, and end to end
         # from pageable numpy arrays (what h5py returns) through the pinned staging of EventSliceFeeder
         rxs, rys = exs.to(torch.int16), eys.to(torch.int16)

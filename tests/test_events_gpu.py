@@ -193,3 +193,25 @@ def test_raw_rejects_wrong_dtypes(enc):
     z = torch.zeros(8, device=dev())
     with pytest.raises(RuntimeError, match="int16"):
         enc.events_raw_to_stack(z, z, z.double(), z.to(torch.int8), 4, (4, 4))
+
+
+def test_clustered_events_exact_under_contention(enc, oracle):
+    """90 % of the events on Gaussian blobs covering ~1 % of the pixels (heavy atomic contention):
+    the polarity counts stay exact, the voxel grid within fp32 summation-order noise."""
+    from gpu_util import n, t
+    rng = np.random.default_rng(21)
+    N, H, W = 400_000, 180, 240
+    nb = int(0.9 * N)
+    c = rng.integers(0, 3, nb)
+    xs = np.concatenate([np.clip(np.array([40, 120, 200])[c] + 3 * rng.standard_normal(nb), 0, W - 1), rng.integers(0, W, N - nb)])
+    ys = np.concatenate([np.clip(np.array([50, 90, 140])[c] + 3 * rng.standard_normal(nb), 0, H - 1), rng.integers(0, H, N - nb)])
+    perm = rng.permutation(N)
+    xs, ys = np.floor(xs[perm]).astype(np.float32), np.floor(ys[perm]).astype(np.float32)
+    ts = np.sort(rng.random(N)).astype(np.float32)
+    ps = (rng.integers(0, 2, N) * 2 - 1).astype(np.float32)
+    st = enc.events_to_stack(t(xs), t(ys), t(ts), t(ps), 16, sensor_size=(H, W))
+    assert np.array_equal(n(st), oracle.events_to_stack(xs, ys, ts, ps, 16, (H, W))[0])
+    assert float(st.max()) > 500                                  # thousands of events per hot pixel
+    vox = enc.events_to_voxel(t(xs), t(ys), t(ts), t(ps), 5, sensor_size=(H, W))
+    want = oracle.events_to_voxel(xs, ys, ts, ps, 5, (H, W))[0]
+    assert np.abs(n(vox) - want).max() < 1e-3 * max(1.0, np.abs(want).max())
