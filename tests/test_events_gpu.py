@@ -211,7 +211,7 @@ def test_clustered_events_exact_under_contention(enc, oracle):
     ps = (rng.integers(0, 2, N) * 2 - 1).astype(np.float32)
     st = enc.events_to_stack(t(xs), t(ys), t(ts), t(ps), 16, sensor_size=(H, W))
     assert np.array_equal(n(st), oracle.events_to_stack(xs, ys, ts, ps, 16, (H, W))[0])
-    assert float(st.max()) > 500                                  # thousands of events per hot pixel
+    assert float(st.max()) > 50                                   # hot pixels: thousands of events over 16 bins x 2 polarities
     vox = enc.events_to_voxel(t(xs), t(ys), t(ts), t(ps), 5, sensor_size=(H, W))
     want = oracle.events_to_voxel(xs, ys, ts, ps, 5, (H, W))[0]
     assert np.abs(n(vox) - want).max() < 1e-3 * max(1.0, np.abs(want).max())
