@@ -105,3 +105,28 @@ def test_reference_wrappers_import_unchanged_on_our_shims():
         spec.loader.exec_module(mod)
         assert hasattr(mod, attr)
     sys.modules.pop("_ext", None), sys.modules.pop("kernelconv2d_cuda", None)
+
+
+def test_header_is_plain_c_and_links_against_the_library(tmp_path):
+    """include/ebfi_b200.h compiles as C99 and as C++17 (no torch, no CUDA headers), and a C program linked against
+    libebfi_b200.so resolves the entry points — what a cgo / JNI / pybind maintainer relies on."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "ebfi_b200.h"\n'
+                   "int main(void) {\n"
+                   "    ebfi_dcn_geom g = {1, 64, 256, 256, 64, 3, 3, 1, 1, 1, 1, 1, 1, 8, 0};\n"
+                   "    int ho = 0, wo = 0;\n"
+                   "    if (ebfi_abi_version() != EBFI_ABI_VERSION) return 1;\n"
+                   "    if (ebfi_dcnv2_output_size(&g, &ho, &wo) != EBFI_OK || ho != 256 || wo != 256) return 2;\n"
+                   "    return ebfi_kpn_fused_workspace_bytes(4, 64, 64, 256, 256, 5) > 0 ? 0 : 3;\n"
+                   "}\n")
+    inc = os.path.join(ROOT, "include")
+    libdir = os.path.dirname(L.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", inc, "-c", str(src), "-o", str(tmp_path / "abi.o")], check=True)
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-I", inc, "-x", "c++", "-c", str(src), "-o", str(tmp_path / "abi_cxx.o")], check=True)
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", str(tmp_path / "abi.o"), "-L", libdir, "-lebfi_b200", "-Wl,-rpath," + libdir, "-o", str(exe)], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
