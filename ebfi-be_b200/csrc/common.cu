@@ -1,5 +1,6 @@
 // common.cu — library-level entry points and error plumbing of libebfi_b200.so.
 #include "common.cuh"
+#include "tma.cuh"
 
 #include <cstring>
 
@@ -35,6 +36,42 @@ int sm_count()
 }
 
 }  // namespace ebfi
+
+namespace tma {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int encode_3d(CUtensorMap &tm, const void *base, CUtensorMapDataType dtype, const uint64_t (&dims)[3],
+              const uint64_t (&strides)[2], const uint32_t (&box)[3])
+{
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return ebfi::fail(EBFI_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t gdim[3] = {dims[0], dims[1], dims[2]};
+    const cuuint64_t gstr[2] = {strides[0], strides[1]};
+    const cuuint32_t bx[3] = {box[0], box[1], box[2]};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(&tm, dtype, 3, const_cast<void *>(base), gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return ebfi::fail(EBFI_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return EBFI_OK;
+}
+
+}  // namespace tma
 
 extern "C" {
 

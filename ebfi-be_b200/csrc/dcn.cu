@@ -401,6 +401,7 @@ int fill_dims(const ebfi_dcn_geom *q, DcnDims &d)
     EBFI_REQUIRE(d.B <= 65535 && ceil_div(d.Co, COT) <= 65535, "dcn: batch / Cout too large for the grid");
     const long long taps = (long long)d.dg * d.KK * Ho * Wo;
     d.off_bs = 2 * taps; d.mask_bs = taps; d.packed = 0; d.abs_sum = nullptr;
+    d.off_bp = 2 * d.dg * d.KK; d.mask_bp = d.dg * d.KK;
     EBFI_REQUIRE((q->flags & ~EBFI_DCN_DETERMINISTIC) == 0, "dcn: unknown flags 0x%x", q->flags);
     d.det = (q->flags & EBFI_DCN_DETERMINISTIC) ? 1 : 0;
     d.det_bound = nullptr;
@@ -415,6 +416,7 @@ int fill_dims(const ebfi_dcn_geom *q, DcnDims &d)
 void set_packed(DcnDims &d)
 {
     d.off_bs = d.mask_bs = 3 * d.mask_bs;
+    d.off_bp = d.mask_bp = 3 * d.dg * d.KK;
     d.packed = 1;
 }
 

@@ -21,6 +21,7 @@
 // kind::tf32/f16 MN-major no-swizzle operands are not usable; the [px][co] copy
 // shares its storage with the column operand, which is written only after GEMM1 has completed.
 #include "dcn_common.cuh"
+#include "tma.cuh"
 #include "umma.cuh"
 
 #include <algorithm>
@@ -44,6 +45,7 @@ struct BwdPlan {
     int kch1;            // Co / 8: K chunks of the Co-contraction operands
     int tiles_x, tiles_y;
     int wt_part, p_part, q_part, col_part, col_sbo;    // bytes of one (hi or lo) image
+    int om_off, om_bytes;                              // offset/mask tile staged by TMA (0 bytes: read from global)
     int smem;
 };
 
@@ -72,7 +74,8 @@ dcn_bwd_tc_kernel(const float *__restrict__ in_blk, const float *__restrict__ we
                   const float *__restrict__ offset, const float *__restrict__ mask,
                   const float *__restrict__ gout, float *__restrict__ gin_blk,
                   float *__restrict__ goff, float *__restrict__ gmask,
-                  float *__restrict__ gw_part, float *__restrict__ gb_part, DcnDims d, BwdPlan pl)
+                  float *__restrict__ gw_part, float *__restrict__ gb_part, DcnDims d, BwdPlan pl,
+                  const __grid_constant__ CUtensorMap tm_off, const __grid_constant__ CUtensorMap tm_mask)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *wt_hi = smem, *wt_lo = smem + pl.wt_part;                       // B of GEMM1: [N1 rows k'][Co]
@@ -80,7 +83,12 @@ dcn_bwd_tc_kernel(const float *__restrict__ in_blk, const float *__restrict__ we
     unsigned char *u_base = q_lo + pl.q_part;                                      // union: P (A of GEMM1) | col (B of GEMM3)
     unsigned char *p_hi = u_base, *p_lo = u_base + pl.p_part;                      //   P: [128 px rows][Co]
     unsigned char *c_hi = u_base, *c_lo = u_base + pl.col_part;                    //   col: [N3 rows k'][128 px], LBO 144
-    __shared__ __align__(8) uint64_t bar1, bar3;
+    // offsets (2*KK planes) and mask (KK planes) of the tile, [plane][8 x 16 pixels] fp32: one TMA tensor copy each,
+    // issued at the top of the tile loop -> their DRAM latency (every element is read exactly once) hides behind the
+    // grad_output staging and GEMM1, without holding registers
+    const float *s_om = reinterpret_cast<const float *>(smem + pl.om_off);
+    const bool use_tma = pl.om_bytes > 0;
+    __shared__ __align__(8) uint64_t bar1, bar3, bar_om;
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -92,7 +100,7 @@ dcn_bwd_tc_kernel(const float *__restrict__ in_blk, const float *__restrict__ we
     const int ntile = pl.tiles_x * pl.tiles_y;
 
     if (warp == 0) umma::tmem_alloc<TMEM_COLS>(&tmem_slot);
-    if (tid == 0) { umma::mbar_init(&bar1, 1); umma::mbar_init(&bar3, 1); umma::mbar_fence_init(); }
+    if (tid == 0) { umma::mbar_init(&bar1, 1); umma::mbar_init(&bar3, 1); umma::mbar_init(&bar_om, 1); umma::mbar_fence_init(); }
     // ---- W_g^T, resident for the whole CTA: wt[k'][co] = weight[co][(c0 + cc) * KK + tap], k' = tap * 8 + cc
     for (int e = tid; e < pl.N1 * d.Co; e += NTHR) {
         const int j = e & 7, rr = (e >> 3) & 7, rest = e >> 6;
@@ -117,7 +125,7 @@ dcn_bwd_tc_kernel(const float *__restrict__ in_blk, const float *__restrict__ we
     const unsigned uplane = (unsigned)plane;
     const float det_scale = DET ? ldexpf(1.f, det_scale_exp(d)) : 0.f;
 
-    uint32_t ph1 = 0, ph3 = 0;
+    uint32_t ph1 = 0, ph3 = 0, ph_om = 0;
     int ntiles_done = 0;
     for (int tile = s; tile < d.B * ntile; tile += S, ++ntiles_done) {
         const int b = tile / ntile, tl = tile % ntile;
@@ -126,6 +134,11 @@ dcn_bwd_tc_kernel(const float *__restrict__ in_blk, const float *__restrict__ we
         const bool valid = ho < d.Ho && wo < d.Wo;
         const int pix = ho * d.Wo + wo;
         const float *go_b = gout + (size_t)b * d.Co * plane;
+        if (use_tma && tid == 0) {                   // every reader of the previous tile's copy has passed the barrier before GEMM3
+            umma::mbar_expect_tx(&bar_om, (uint32_t)pl.om_bytes);
+            tma::load_3d(smem + pl.om_off, &tm_off, tx0, ty0, b * d.off_bp + g * 2 * d.KK, &bar_om);
+            tma::load_3d(smem + pl.om_off + 2 * d.KK * TM * 4, &tm_mask, tx0, ty0, b * d.mask_bp + g * d.KK, &bar_om);
+        }
         if (ntiles_done > 0) {                       // GEMM3 of the previous tile has read Q and col
             umma::mbar_wait(&bar3, ph3);
             ph3 ^= 1;
@@ -186,6 +199,10 @@ dcn_bwd_tc_kernel(const float *__restrict__ in_blk, const float *__restrict__ we
         umma::mbar_wait(&bar1, ph1);                 // D1 complete; P is dead, its storage becomes `col`
         ph1 ^= 1;
         umma::fence_after_sync();
+        if (use_tma) {
+            umma::mbar_wait(&bar_om, ph_om);
+            ph_om ^= 1;
+        }
         for (int sidx = 0; sidx < pl.TPR; ++sidx) {
             const int t = r * pl.TPR + sidx;
             if (t >= d.KK) break;
@@ -198,7 +215,13 @@ dcn_bwd_tc_kernel(const float *__restrict__ in_blk, const float *__restrict__ we
             for (int j = 0; j < 8; ++j) colv[j] = 0.f;
             if (valid) {
                 float dy, dx, m;
-                tap_read(offset + off_e, mask + mask_e, uplane, (unsigned)t, (unsigned)pix, dy, dx, m);
+                if (use_tma) {
+                    dy = s_om[(2 * t) * TM + p];
+                    dx = s_om[(2 * t + 1) * TM + p];
+                    m = s_om[(2 * d.KK + t) * TM + p];
+                } else {
+                    tap_read(offset + off_e, mask + mask_e, uplane, (unsigned)t, (unsigned)pix, dy, dx, m);
+                }
                 m = mask_act_t<PACKED>(m);
                 const float y = (float)(ho * d.sh - d.ph + ti * d.dh) + dy;
                 const float x = (float)(wo * d.sw - d.pw + tj * d.dw) + dx;
@@ -391,8 +414,13 @@ bool make_plan(const DcnDims &d, BwdPlan &pl)
     pl.q_part = d.Co * TM * 2;
     pl.col_sbo = (TM / 8) * COL_LBO;
     pl.col_part = (pl.N3 / 8) * pl.col_sbo;
-    pl.smem = 2 * pl.wt_part + 2 * pl.q_part + 2 * std::max(pl.p_part, pl.col_part);
-    return pl.smem <= 110 * 1024;
+    pl.om_off = 2 * pl.wt_part + 2 * pl.q_part + 2 * std::max(pl.p_part, pl.col_part);
+    // TMA staging of the offset/mask tile needs 16-byte row strides; two CTAs (+1 KB each) must fit one SM's 228 KB
+    const bool tma_ok = d.Wo % 4 == 0 && getenv("EBFI_DCN_NO_TMA") == nullptr;
+    pl.om_bytes = tma_ok ? 3 * d.KK * TM * 4 : 0;
+    if (pl.om_off + pl.om_bytes > 113 * 1024) pl.om_bytes = 0;
+    pl.smem = pl.om_off + pl.om_bytes;
+    return pl.smem <= 113 * 1024;
 }
 
 }  // namespace
@@ -437,11 +465,20 @@ int backward_tc(cudaStream_t st, const DcnDims &d, const float *input, const flo
     if (int rc = launch_nchw_to_blocked(st, input, in_blk, BG, HW)) return rc;
     EBFI_CUDA_OK(cudaMemsetAsync(gin_blk, 0, n * (d.det ? sizeof(long long) : sizeof(float)), st));
     dim3 grid(S, d.dg);
+    CUtensorMap tm_off{}, tm_mask{};
+    if (pl.om_bytes > 0) {
+        const uint64_t str[2] = {(uint64_t)d.Wo * 4, (uint64_t)d.Ho * d.Wo * 4};
+        const uint64_t dims_o[3] = {(uint64_t)d.Wo, (uint64_t)d.Ho, (uint64_t)(d.B - 1) * d.off_bp + 2 * d.dg * d.KK};
+        const uint64_t dims_m[3] = {(uint64_t)d.Wo, (uint64_t)d.Ho, (uint64_t)(d.B - 1) * d.mask_bp + d.dg * d.KK};
+        const uint32_t box_o[3] = {TW, TH, (uint32_t)(2 * d.KK)}, box_m[3] = {TW, TH, (uint32_t)d.KK};
+        if (int rc = tma::encode_3d(tm_off, offset, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, dims_o, str, box_o)) return rc;
+        if (int rc = tma::encode_3d(tm_mask, mask, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, dims_m, str, box_m)) return rc;
+    }
 #define EBFI_BWD_TC(P, D)                                                                                     \
     do {                                                                                                      \
         EBFI_CUDA_OK(cudaFuncSetAttribute(dcn_bwd_tc_kernel<P, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem)); \
         dcn_bwd_tc_kernel<P, D><<<grid, NTHR, pl.smem, st>>>(in_blk, weight, offset, mask, gout, gin_blk, goff, gmask, \
-                                                             gw_part, gb_part, d, pl);                        \
+                                                             gw_part, gb_part, d, pl, tm_off, tm_mask);       \
     } while (0)
     if (d.det) { if (d.packed) EBFI_BWD_TC(true, true); else EBFI_BWD_TC(false, true); }
     else       { if (d.packed) EBFI_BWD_TC(true, false); else EBFI_BWD_TC(false, false); }

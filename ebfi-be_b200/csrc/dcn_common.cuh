@@ -20,6 +20,7 @@ struct DcnDims {
     // output of conv_offset_mask (dcn_v2.py:217-219: offset = channels [0, 2*dg*KK), mask logits = the last
     // third), off_bs = mask_bs = 3*dg*KK*plane, and the mask is sigmoid(logit) (dcn_v2.py:225).
     long long off_bs, mask_bs;
+    int off_bp, mask_bp;      // the same batch strides in planes (off_bs / (Ho*Wo), ...), for TMA plane coordinates
     int packed;
     float *abs_sum;   // packed forward only, nullable: += sum |offset| (DCN_sep's `offset_mean` warning, :221-223)
     // EBFI_DCN_DETERMINISTIC (backward): grad_input is accumulated as int64 fixed point. det_bound -> 3 device

@@ -32,9 +32,9 @@
 // for the tensor cores, accumulation and the whole FAC part are fp32. Stated tolerance 1e-2 of max|out|
 // against the fp32/fp64 op sequence; 1e-5 against the same sequence with bf16-rounded conv operands.
 #include "common.cuh"
+#include "tma.cuh"
 #include "umma.cuh"
 
-#include <cuda.h>        // CUtensorMap types; cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint
 #include <algorithm>
 
 namespace {
@@ -101,14 +101,6 @@ __global__ void kpn_prep_weights(const float *__restrict__ w, __nv_bfloat16 *__r
         if (nrow < ncols) v = __ldg(w + ((size_t)(c0 * d.KK + nrow) * d.Cin + ch) * 9 + tap);
         wimg[i] = __float2bfloat16_rn(v);
     }
-}
-
-// 3-D tiled TMA load global -> shared; out-of-range coordinates read as zero
-__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *tmap, int c0, int c1, int c2, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                 ::"r"(umma::smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(umma::smem_u32(bar))
-                 : "memory");
 }
 
 // Epilogue of warpgroup G: FAC channel c0 + G of every item's slice.
@@ -276,7 +268,7 @@ kpn_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16 *
                 umma::mbar_wait(&a_free[part], (uint32_t)((n & 1) ^ 1));
                 if (leader) {
                     umma::mbar_expect_tx(&a_full[part], (uint32_t)PART_BYTES);
-                    tma_load_3d(a_s + part * PART_BYTES, &tmap, (tx0 - 1) * 8, ty0 - 1, b * d.kchunks + part * (PART_CH / 8),
+                    tma::load_3d(a_s + part * PART_BYTES, &tmap, (tx0 - 1) * 8, ty0 - 1, b * d.kchunks + part * (PART_CH / 8),
                                 &a_full[part]);
                 }
             }
@@ -294,37 +286,13 @@ kpn_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16 *
     if (warp == 0) umma::tmem_dealloc<TMEM_COLS>(tmem);
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-// cuTensorMapEncodeTiled without linking libcuda: resolved through the (statically linked) runtime
-EncodeTiledFn encode_tiled()
-{
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
 // featb [B*kchunks][H][W*8] bf16, box = one halo part: [4 chunks][18 rows][10 pixels * 8 channels]
 int make_tmap(CUtensorMap &tm, const KpnDims &d, void *featb)
 {
-    EncodeTiledFn enc = encode_tiled();
-    if (!enc) return ebfi::fail(EBFI_ERR_CUDA, "kpn_fused: cuTensorMapEncodeTiled is not available from this driver");
-    const cuuint64_t gdim[3] = {(cuuint64_t)d.W * 8, (cuuint64_t)d.H, (cuuint64_t)d.B * d.kchunks};
-    const cuuint64_t gstr[2] = {(cuuint64_t)d.W * 16, (cuuint64_t)d.H * d.W * 16};
-    const cuuint32_t box[3] = {HW * 8, HH, PART_CH / 8};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, featb, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return ebfi::fail(EBFI_ERR_CUDA, "kpn_fused: cuTensorMapEncodeTiled failed (%d)", (int)r);
-    return EBFI_OK;
+    const uint64_t gdim[3] = {(uint64_t)d.W * 8, (uint64_t)d.H, (uint64_t)d.B * d.kchunks};
+    const uint64_t gstr[2] = {(uint64_t)d.W * 16, (uint64_t)d.H * d.W * 16};
+    const uint32_t box[3] = {HW * 8, HH, PART_CH / 8};
+    return tma::encode_3d(tm, featb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, gdim, gstr, box);
 }
 
 int fill(KpnDims &d, int B, int Ce, int Cf, int H, int W, int K, float slope)
