@@ -485,6 +485,28 @@ def widening_numbers(torch, dev, d, timed):
     t_ref, t_pk = timed(ref_tail, n=10), timed(packed_tail, n=10)
     out["dcn_sep_tail_fwd_bwd"] = {"workload": "cfg1 (B=1, 64->64, 3x3, dg=8, 256x256)", "reference_sequence_ms": round(t_ref, 4),
                                    "packed_ms": round(t_pk, 4), "speedup": round(t_ref / t_pk, 2)}
+    del x, om, w, b
+    # BASELINE configs[3] (720p inference) cannot run here (the model needs the reference tree); this is the slice of
+    # it that this repo owns, at that config's shapes: the two per-frame maps at 1280x720, and at the half-resolution
+    # feature grid (360x640, model_singleframe.py:244-245) the packed DCN forward and the fused KernelConv -> FAC.
+    from ebfi_be_b200 import frame_ops
+    with torch.no_grad():
+        g = torch.Generator(device="cpu").manual_seed(11)
+        frame = torch.rand(1, 3, 720, 1280, generator=g).to(dev)
+        fh, fw = 360, 640
+        feat = torch.randn(1, C, fh, fw, generator=g).to(dev)
+        fea2 = torch.randn(1, C, fh, fw, generator=g).to(dev)
+        om4 = torch.randn(1, 3 * DG * 9, fh, fw, generator=g).to(dev)
+        wk = (0.03 * torch.randn(C * 25, 2 * C, 3, 3, generator=g)).to(dev)
+        bk = torch.zeros(C * 25, device=dev)
+        t_maps = timed(lambda: (frame_ops.Frame2Lap(frame), frame_ops.Frame2DCP(frame)), n=10)
+        t_dcn = timed(lambda: dcn_v2.dcn_v2_conv_packed(feat, om4, d["w"], d["b"], 1, 1, 1, DG), n=10)
+        t_kpn = timed(lambda: modification.kernelconv_fac_fused(feat, fea2, wk, bk, K_FAC, 0.01), n=10)
+    out["cfg4_owned_slice_720p_inference"] = {
+        "frame_maps_ms": round(t_maps, 4), "dcn_packed_forward_360x640_ms": round(t_dcn, 4),
+        "kernelconv_fac_fused_360x640_ms": round(t_kpn, 4), "total_ms": round(t_maps + t_dcn + t_kpn, 4),
+        "note": "one call of each owned operator at the shapes of the 720p inference config; the rest of the model "
+                "(stock cuDNN layers) is out of scope"}
     return out
 
 
