@@ -279,3 +279,58 @@ extern "C" int ebfi_selftest_umma_probe(void *stream, float *C, int lbo_bytes, i
     EBFI_LAUNCH_OK("umma_probe_kernel");
     return EBFI_OK;
 }
+
+// ---- MMA issue-interval probe -----------------------------------------------------------------------------------
+// One CTA per SM issues `iters` back-to-back kind::f16 (bf16) MMAs of shape 128 x N x 16 on fixed shared-memory
+// operands (contents irrelevant) and reports clock64 cycles per MMA: the steady-state rate of the tensor pipe for
+// that shape, including its shared-memory operand reads. Used to decide whether small-N GEMMs (N = 80 in kpn.cu)
+// are bound by operand traffic rather than by math.
+namespace {
+__global__ void __launch_bounds__(128, 1)
+mma_rate_kernel(float *__restrict__ cycles_per_mma, int N, int iters, int a_sbo_bytes)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (64 * 1024) / 4; i += 128) reinterpret_cast<uint32_t *>(smem)[i] = 0x3C003C00u;
+    if (warp == 0) umma::tmem_alloc<256>(&tmem_slot);
+    if (tid == 0) { umma::mbar_init(&bar, 1); umma::mbar_fence_init(); }
+    umma::fence_smem_to_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    if (warp == 0) {
+        const bool leader = umma::elect_one();
+        const uint32_t idesc = umma::instr_desc_bf16(128, N);
+        const uint64_t da = umma::smem_desc(umma::smem_u32(smem), 2880, (uint32_t)a_sbo_bytes);          // A: like kpn.cu's halo view
+        const uint64_t db = umma::smem_desc(umma::smem_u32(smem) + 32768, 128, 256);                     // B: dense K-major, N x 16
+        const long long t0 = clock64();
+        for (int i = 0; i < iters; i += 8) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (leader) umma::mma_f16(tmem, da + (uint64_t)(u & 3), db + (uint64_t)(512 * (u & 3)), idesc, true);
+        }
+        if (leader) umma::commit(&bar);
+        umma::mbar_wait(&bar, 0);
+        const long long t1 = clock64();
+        if (leader) cycles_per_mma[blockIdx.x] = (float)(t1 - t0) / (float)iters;
+        __syncwarp();
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc<256>(tmem);
+}
+}  // namespace
+
+extern "C" int ebfi_selftest_mma_rate(void *stream, float *cycles_per_mma, int n_ctas, int N, int iters, int a_sbo_bytes)
+{
+    EBFI_REQUIRE(cycles_per_mma != nullptr && n_ctas > 0, "mma_rate: bad arguments");
+    EBFI_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0 && iters >= 8 && iters % 8 == 0, "mma_rate: N multiple of 16 in [16, 256], iters multiple of 8");
+    const int smem = 200 * 1024;      // one CTA per SM
+    EBFI_CUDA_OK(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    mma_rate_kernel<<<n_ctas, 128, smem, ebfi::as_stream(stream)>>>(cycles_per_mma, N, iters, a_sbo_bytes);
+    EBFI_LAUNCH_OK("mma_rate_kernel");
+    return EBFI_OK;
+}

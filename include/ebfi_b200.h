@@ -281,6 +281,11 @@ int ebfi_selftest_gemm_bf16x3(void *stream, const float *A, const float *B, floa
  * Documents how the hardware interprets the descriptor fields. */
 int ebfi_selftest_umma_probe(void *stream, float *C, int lbo_bytes, int sbo_bytes, int a_mn_major);
 
+/* Tensor-pipe rate probe: n_ctas CTAs (one per SM) each issue `iters` back-to-back bf16 MMAs of shape 128 x N x 16
+ * on shared-memory operands and write the measured clock cycles per MMA (n_ctas floats). a_sbo_bytes: stride between
+ * the 8-row groups of the A operand (128 = dense; 160 = the halo view of the fused KernelConv kernel). */
+int ebfi_selftest_mma_rate(void *stream, float *cycles_per_mma, int n_ctas, int N, int iters, int a_sbo_bytes);
+
 #ifdef __cplusplus
 }
 #endif
