@@ -287,7 +287,7 @@ extern "C" int ebfi_selftest_umma_probe(void *stream, float *C, int lbo_bytes, i
 // are bound by operand traffic rather than by math.
 namespace {
 __global__ void __launch_bounds__(128, 1)
-mma_rate_kernel(float *__restrict__ cycles_per_mma, int N, int iters, int a_sbo_bytes)
+mma_rate_kernel(float *__restrict__ cycles_per_mma, int N, int iters, int a_sbo_bytes, int b_sbo_bytes)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
@@ -305,12 +305,15 @@ mma_rate_kernel(float *__restrict__ cycles_per_mma, int N, int iters, int a_sbo_
         const bool leader = umma::elect_one();
         const uint32_t idesc = umma::instr_desc_bf16(128, N);
         const uint64_t da = umma::smem_desc(umma::smem_u32(smem), 2880, (uint32_t)a_sbo_bytes);          // A: like kpn.cu's halo view
-        const uint64_t db = umma::smem_desc(umma::smem_u32(smem) + 32768, 128, 256);                     // B: dense K-major, N x 16
+        // B: K-major rows, 8-row groups b_sbo_bytes apart (256 = dense N x 16; 18432 = kpn.cu's 9*128-channel weight image,
+        // in which consecutive MMAs also walk along K)
+        const uint64_t db = umma::smem_desc(umma::smem_u32(smem) + 32768, 128, (uint32_t)b_sbo_bytes);
+        const uint64_t bstep = b_sbo_bytes > 256 ? 16 : 512;
         const long long t0 = clock64();
         for (int i = 0; i < iters; i += 8) {
 #pragma unroll
             for (int u = 0; u < 8; ++u)
-                if (leader) umma::mma_f16(tmem, da + (uint64_t)(u & 3), db + (uint64_t)(512 * (u & 3)), idesc, true);
+                if (leader) umma::mma_f16(tmem, da + (uint64_t)(u & 3), db + bstep * (uint64_t)(u & 7), idesc, true);
         }
         if (leader) umma::commit(&bar);
         umma::mbar_wait(&bar, 0);
@@ -324,13 +327,16 @@ mma_rate_kernel(float *__restrict__ cycles_per_mma, int N, int iters, int a_sbo_
 }
 }  // namespace
 
-extern "C" int ebfi_selftest_mma_rate(void *stream, float *cycles_per_mma, int n_ctas, int N, int iters, int a_sbo_bytes)
+extern "C" int ebfi_selftest_mma_rate(void *stream, float *cycles_per_mma, int n_ctas, int N, int iters, int a_sbo_bytes,
+                                      int b_sbo_bytes)
 {
+    EBFI_REQUIRE(b_sbo_bytes >= 256 && b_sbo_bytes % 16 == 0 && 32768 + (N / 8) * (long)b_sbo_bytes <= 200 * 1024,
+                 "mma_rate: B operand does not fit the probe's shared memory");
     EBFI_REQUIRE(cycles_per_mma != nullptr && n_ctas > 0, "mma_rate: bad arguments");
     EBFI_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0 && iters >= 8 && iters % 8 == 0, "mma_rate: N multiple of 16 in [16, 256], iters multiple of 8");
     const int smem = 200 * 1024;      // one CTA per SM
     EBFI_CUDA_OK(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    mma_rate_kernel<<<n_ctas, 128, smem, ebfi::as_stream(stream)>>>(cycles_per_mma, N, iters, a_sbo_bytes);
+    mma_rate_kernel<<<n_ctas, 128, smem, ebfi::as_stream(stream)>>>(cycles_per_mma, N, iters, a_sbo_bytes, b_sbo_bytes);
     EBFI_LAUNCH_OK("mma_rate_kernel");
     return EBFI_OK;
 }
