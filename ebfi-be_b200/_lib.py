@@ -55,7 +55,7 @@ SIGNATURES = {
     "ebfi_frame_to_dcp": (c_int, [c_void] * 4 + [c_int] * 4),
     "ebfi_selftest_gemm_tf32x3": (c_int, [c_void] * 4 + [c_int] * 4),
     "ebfi_selftest_gemm_bf16x3": (c_int, [c_void] * 4 + [c_int] * 4),
-    "ebfi_selftest_mma_rate": (c_int, [c_void, c_void] + [c_int] * 5),
+    "ebfi_selftest_mma_rate": (c_int, [c_void, c_void] + [c_int] * 6),
     "ebfi_selftest_umma_probe": (c_int, [c_void, c_void, c_int, c_int, c_int]),
 }
 

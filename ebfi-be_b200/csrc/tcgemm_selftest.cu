@@ -286,16 +286,17 @@ extern "C" int ebfi_selftest_umma_probe(void *stream, float *C, int lbo_bytes, i
 // that shape, including its shared-memory operand reads. Used to decide whether small-N GEMMs (N = 80 in kpn.cu)
 // are bound by operand traffic rather than by math.
 namespace {
+template <int COMMIT_EVERY>
 __global__ void __launch_bounds__(128, 1)
 mma_rate_kernel(float *__restrict__ cycles_per_mma, int N, int iters, int a_sbo_bytes, int b_sbo_bytes)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(8) uint64_t bar, bar2;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5;
     for (int i = tid; i < (64 * 1024) / 4; i += 128) reinterpret_cast<uint32_t *>(smem)[i] = 0x3C003C00u;
     if (warp == 0) umma::tmem_alloc<256>(&tmem_slot);
-    if (tid == 0) { umma::mbar_init(&bar, 1); umma::mbar_fence_init(); }
+    if (tid == 0) { umma::mbar_init(&bar, 1); umma::mbar_init(&bar2, 1); umma::mbar_fence_init(); }
     umma::fence_smem_to_async();
     umma::fence_before_sync();
     __syncthreads();
@@ -310,6 +311,25 @@ mma_rate_kernel(float *__restrict__ cycles_per_mma, int N, int iters, int a_sbo_
         const uint64_t db = umma::smem_desc(umma::smem_u32(smem) + 32768, 128, (uint32_t)b_sbo_bytes);
         const uint64_t bstep = b_sbo_bytes > 256 ? 16 : 512;
         const long long t0 = clock64();
+        if (b_sbo_bytes == 18432) {
+            // the exact operand walk of kpn.cu: 4 halo parts x 9 taps x 2 K steps = 72 distinct (A, B) pairs per item
+            const uint64_t da_k = umma::smem_desc(umma::smem_u32(smem), 2880, 160);
+            const uint64_t db_k = umma::smem_desc(umma::smem_u32(smem) + 46080, 128, 18432);
+            for (int i = 0; i < iters; i += 72) {
+#pragma unroll
+                for (int part = 0; part < 4; ++part)
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            if (leader)
+                                umma::mma_f16(tmem, da_k + (uint64_t)(part * 720 + (tap / 3) * 10 + tap % 3 + j * 360),
+                                              db_k + (uint64_t)(((part * 9 + tap) * 2 + j) * 16), idesc, true);
+                            // commit_every > 0: a tcgen05.commit (to a barrier nobody waits on) after every n-th MMA
+                            if (COMMIT_EVERY > 0 && ((part * 9 + tap) * 2 + j + 1) % COMMIT_EVERY == 0 && leader) umma::commit(&bar2);
+                        }
+            }
+        } else
         for (int i = 0; i < iters; i += 8) {
 #pragma unroll
             for (int u = 0; u < 8; ++u)
@@ -328,15 +348,28 @@ mma_rate_kernel(float *__restrict__ cycles_per_mma, int N, int iters, int a_sbo_
 }  // namespace
 
 extern "C" int ebfi_selftest_mma_rate(void *stream, float *cycles_per_mma, int n_ctas, int N, int iters, int a_sbo_bytes,
-                                      int b_sbo_bytes)
+                                      int b_sbo_bytes, int commit_every)
 {
-    EBFI_REQUIRE(b_sbo_bytes >= 256 && b_sbo_bytes % 16 == 0 && 32768 + (N / 8) * (long)b_sbo_bytes <= 200 * 1024,
+    EBFI_REQUIRE(b_sbo_bytes >= 256 && b_sbo_bytes % 16 == 0 &&
+                     (b_sbo_bytes == 18432 ? (N <= 80 && iters % 72 == 0) : 32768 + (N / 8) * (long)b_sbo_bytes <= 200 * 1024),
                  "mma_rate: B operand does not fit the probe's shared memory");
     EBFI_REQUIRE(cycles_per_mma != nullptr && n_ctas > 0, "mma_rate: bad arguments");
     EBFI_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0 && iters >= 8 && iters % 8 == 0, "mma_rate: N multiple of 16 in [16, 256], iters multiple of 8");
-    const int smem = 200 * 1024;      // one CTA per SM
-    EBFI_CUDA_OK(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    mma_rate_kernel<<<n_ctas, 128, smem, ebfi::as_stream(stream)>>>(cycles_per_mma, N, iters, a_sbo_bytes, b_sbo_bytes);
+    const int smem = 225 * 1024;      // one CTA per SM
+#define EBFI_RATE(CE)                                                                                          \
+    do {                                                                                                       \
+        EBFI_CUDA_OK(cudaFuncSetAttribute(mma_rate_kernel<CE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        mma_rate_kernel<CE><<<n_ctas, 128, smem, ebfi::as_stream(stream)>>>(cycles_per_mma, N, iters, a_sbo_bytes, b_sbo_bytes); \
+    } while (0)
+    switch (commit_every) {
+    case 0: EBFI_RATE(0); break;
+    case 1: EBFI_RATE(1); break;
+    case 9: EBFI_RATE(9); break;
+    case 18: EBFI_RATE(18); break;
+    case 72: EBFI_RATE(72); break;
+    default: return ebfi::fail(EBFI_ERR_INVALID, "mma_rate: commit_every must be 0, 1, 9, 18 or 72");
+    }
+#undef EBFI_RATE
     EBFI_LAUNCH_OK("mma_rate_kernel");
     return EBFI_OK;
 }

@@ -284,9 +284,10 @@ int ebfi_selftest_umma_probe(void *stream, float *C, int lbo_bytes, int sbo_byte
 /* Tensor-pipe rate probe: n_ctas CTAs (one per SM) each issue `iters` back-to-back bf16 MMAs of shape 128 x N x 16
  * on shared-memory operands and write the measured clock cycles per MMA (n_ctas floats). a_sbo_bytes: stride between
  * the 8-row groups of the A operand (128 = dense; 160 = the halo view of the fused KernelConv kernel); b_sbo_bytes:
- * the same for B (256 = dense N x 16; 18432 = the weight image of the fused KernelConv kernel). */
+ * the same for B (256 = dense N x 16; 18432 = the weight image and operand walk of the fused KernelConv kernel, where
+ * commit_every > 0 additionally issues a tcgen05.commit after every commit_every-th MMA of the 72-MMA item). */
 int ebfi_selftest_mma_rate(void *stream, float *cycles_per_mma, int n_ctas, int N, int iters, int a_sbo_bytes,
-                           int b_sbo_bytes);
+                           int b_sbo_bytes, int commit_every);
 
 #ifdef __cplusplus
 }
