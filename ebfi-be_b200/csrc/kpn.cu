@@ -145,7 +145,7 @@ __device__ __forceinline__ void kpn_epilogue(uint32_t tmem, uint64_t *acc_full, 
             bias_slice = s;
         }
         const int buf = n & 1;
-        umma::mbar_wait(&acc_full[buf], (uint32_t)((n >> 1) & 1));
+        umma::mbar_wait_warp(&acc_full[buf], (uint32_t)((n >> 1) & 1));
         umma::fence_after_sync();
         float v[NLD * 8];
         if (active) {
@@ -265,7 +265,7 @@ kpn_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16 *
             const int ty0 = (tt / d.tiles_x) * TH, tx0 = (tt % d.tiles_x) * TW;
 #pragma unroll
             for (int part = 0; part < NPART; ++part) {
-                umma::mbar_wait(&a_free[part], (uint32_t)((n & 1) ^ 1));
+                umma::mbar_wait_warp(&a_free[part], (uint32_t)((n & 1) ^ 1));
                 if (leader) {
                     umma::mbar_expect_tx(&a_full[part], (uint32_t)PART_BYTES);
                     tma::load_3d(a_s + part * PART_BYTES, &tmap, (tx0 - 1) * 8, ty0 - 1, b * d.kchunks + part * (PART_CH / 8),

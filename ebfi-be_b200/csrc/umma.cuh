@@ -140,6 +140,26 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// Warp-level wait for warps that are NOT on the critical path (epilogue, producer): one lane polls, with a
+// hardware suspend-time hint, and the warp reconverges. 384 threads spinning on try_wait take shared-memory cycles
+// away from the tensor core's operand reads.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity)
+{
+    if ((threadIdx.x & 31) == 0) {
+        uint32_t done;
+        do {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}\n"
+                : "=r"(done)
+                : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+                : "memory");
+        } while (!done);
+    }
+    __syncwarp();
+}
+
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     uint32_t done;
