@@ -157,7 +157,8 @@ __device__ __forceinline__ void kpn_epilogue(uint32_t tmem, uint64_t *acc_full, 
             umma::tmem_ld_wait();
         }
         umma::fence_before_sync();
-        umma::mbar_arrive(&acc_free[buf]);                   // accumulator drained into registers: the next item may reuse it
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(&acc_free[buf]);    // accumulator drained into registers (one arrival per warp): the next item may reuse it
         if (valid) {
             float res = 0.f;
 #pragma unroll
@@ -194,7 +195,7 @@ kpn_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16 *
         umma::mbar_init(&bar_w, 1);
         umma::mbar_init(&bar_wfree, 1);
         for (int i = 0; i < NPART; ++i) { umma::mbar_init(&a_full[i], 1); umma::mbar_init(&a_free[i], 1); }
-        for (int i = 0; i < 2; ++i) { umma::mbar_init(&acc_full[i], 1); umma::mbar_init(&acc_free[i], NEPI); }
+        for (int i = 0; i < 2; ++i) { umma::mbar_init(&acc_full[i], 1); umma::mbar_init(&acc_free[i], NEPI / 32); }
         umma::mbar_fence_init();
     }
     umma::fence_before_sync();
