@@ -17,9 +17,15 @@ def kernelconv_fac_fused(event_feat, frame_feat, conv_weight, conv_bias, kernel_
     """out = KernelConv2D(K)(event_feat, LeakyReLU(conv3x3(cat([event_feat, frame_feat], 1)))) — fp32 CUDA tensors;
     conv operands are rounded to bf16 for the tensor cores (fp32 accumulate, fp32 FAC)."""
     L.require_cuda(event_feat, frame_feat, conv_weight, conv_bias)
-    for name, t in (("event_feat", event_feat), ("frame_feat", frame_feat), ("conv_weight", conv_weight), ("conv_bias", conv_bias)):
-        if t.dtype != torch.float32:
-            raise RuntimeError(f"kernelconv_fac_fused: {name} must be float32, got {t.dtype}")
+    dts = {t.dtype for t in (event_feat, frame_feat, conv_weight, conv_bias)}
+    if dts == {torch.bfloat16}:
+        # bfloat16 model (the 720p inference config): the kernel's conv operands are bf16 anyway, so the values are used
+        # exactly; the fp32 staging copies and the final rounding of the output to bf16 happen at this boundary
+        return kernelconv_fac_fused(event_feat.float(), frame_feat.float(), conv_weight.float(), conv_bias.float(),
+                                    kernel_size, negative_slope).bfloat16()
+    if dts != {torch.float32}:
+        raise RuntimeError("kernelconv_fac_fused: all tensors must be float32 or all bfloat16, got "
+                           f"{sorted(str(d) for d in dts)}")
     if torch.is_grad_enabled() and any(t.requires_grad for t in (event_feat, frame_feat, conv_weight, conv_bias)):
         raise RuntimeError("kernelconv_fac_fused is forward-only; run it under torch.no_grad() "
                            "(training goes through KernelConv2DFunction)")
@@ -69,7 +75,7 @@ class KernelPrediction(nn.Module):
         conv = self.KernelConv.conv2d
         needs_grad = torch.is_grad_enabled() and (EventTensor.requires_grad or FrameTensor.requires_grad
                                                   or conv.weight.requires_grad)
-        if EventTensor.is_cuda and EventTensor.dtype == torch.float32 and not needs_grad:
+        if EventTensor.is_cuda and EventTensor.dtype in (torch.float32, torch.bfloat16) and not needs_grad:
             return kernelconv_fac_fused(EventTensor, FrameTensor, conv.weight, conv.bias, self.kernel_size,
                                         self.KernelConv.activation.negative_slope)
         Kernel = self.KernelConv(torch.cat([EventTensor, FrameTensor], dim=1))

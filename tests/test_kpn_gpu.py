@@ -87,3 +87,22 @@ def test_unsupported_channel_count_raises(mod):
     ev = torch.randn(1, 24, 8, 8, device=dev())
     with pytest.raises(RuntimeError, match="multiple of 32"):
         mod.kernelconv_fac_fused(ev, ev, torch.randn(24 * 25, 48, 3, 3, device=dev()), torch.zeros(600, device=dev()), 5)
+
+
+def test_bf16_tensors_stated_tolerance(mod, oracle):
+    """bfloat16 tensors (BASELINE config 4 runs the model in bf16; the reference is fp32-only): the conv operands are the
+    bf16 values themselves, accumulation and FAC are fp32, the output is rounded once to bf16. Stated tolerance
+    (SURVEY 8d): max-abs error <= 2^-7 of max|out| against the float64 op sequence on the same bf16-valued inputs."""
+    from gpu_util import n, t
+    rng = np.random.default_rng(3)
+    B, Ce, Cf, H, W, K = 1, 64, 64, 24, 16, 5
+    ev, fr, w, b = _case(rng, B, Ce, Cf, H, W, K)
+    tb = [t(a).bfloat16() for a in (ev, fr, w, b)]
+    with torch.no_grad():
+        got = mod.kernelconv_fac_fused(*tb, K, 0.01)
+    assert got.dtype == torch.bfloat16
+    ev_r, fr_r, w_r, b_r = (n(x.float()) for x in tb)
+    want, _ = oracle.kpn_fused_forward(ev_r, fr_r, w_r, b_r, K, 0.01)
+    assert rel_err(n(got.float()), want) < 2.0 ** -7
+    with pytest.raises(RuntimeError, match="all tensors must be"):
+        mod.kernelconv_fac_fused(tb[0], tb[1].float(), tb[2], tb[3], K)
