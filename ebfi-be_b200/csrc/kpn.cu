@@ -17,7 +17,7 @@
 //   A operand   the tile's input halo (18 x 10 pixels x Cin) in shared memory, laid out [8-ch chunk][y][x][8 ch]
 //               (bf16); for tap (dy, dx) the UMMA descriptor simply starts (dy*10 + dx) pixels later, with
 //               SBO = one halo row and LBO = one chunk plane: no im2col copy of any kind
-//   B operand   weights [80 rows][9*Cin], K-major, K order = (channel half, tap, 16-channel step)
+//   B operand   weights [80 rows][9*Cin], K-major, K order = (32-channel part, tap, 16-channel step)
 //   pipeline    the halo is held as Cin/32 channel PARTS (32 channels, 11.5 KB each). One producer lane refills a
 //               part for the next tile with a single 3-D TMA tensor copy (zero fill outside the image = the
 //               conv's padding) as soon as the MMAs that read it have completed, while the other parts compute;
@@ -27,6 +27,10 @@
 //               -> x Event[c][clamp(y+ky-2)][clamp(x+kx-2)], summed in the reference's tap order
 //               (KernelConv2D_kernel.cu:44-50) -> 1 output. (With one warpgroup doing all 75 columns after the
 //               wait, the epilogue's load latency was the bottleneck: tensor pipe 42 % busy.)
+//   waiting     the MMA warp spins on its barriers with all lanes (critical path); epilogue and producer warps wait
+//               with ONE polling lane and a suspend hint and arrive once per warp: at N = 80 the tensor core needs
+//               every shared-memory cycle for its operands (128 x 80 x 16 MMA: 52 clk = 32 for A + 20 for B), and
+//               400 threads spinning on mbarrier.try_wait take some of them away
 //
 // Precision: tensors are fp32 at the boundary (like the reference); the conv operands are rounded to bf16
 // for the tensor cores, accumulation and the whole FAC part are fp32. Stated tolerance 1e-2 of max|out|
