@@ -73,6 +73,33 @@ def test_ops_refuse_cpu_tensors():
                            torch.randn(2, 2, 3, 3), torch.zeros(2), 1, 1, 1, 1)
     with pytest.raises(RuntimeError, match="no CPU path"):
         encodings.events_to_image(torch.zeros(3), torch.zeros(3), torch.ones(3), (4, 4))
+    # the widenings refuse CPU tensors the same way (nothing in the product path falls back to the host)
+    from ebfi_be_b200 import frame_ops, modification
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        dcn_v2.dcn_v2_conv_packed(x, torch.zeros(1, 27, 6, 6), torch.randn(2, 2, 3, 3), torch.zeros(2), 1, 1, 1, 1)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        encodings.events_raw_to_stack(torch.zeros(4, dtype=torch.int16), torch.zeros(4, dtype=torch.int16),
+                                      torch.zeros(4, dtype=torch.float64), torch.zeros(4, dtype=torch.int8), 4, (4, 4))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        modification.kernelconv_fac_fused(torch.randn(1, 32, 8, 8), torch.randn(1, 32, 8, 8),
+                                          torch.randn(800, 64, 3, 3), torch.zeros(800), 5)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        frame_ops.Frame2Lap(torch.rand(1, 3, 8, 8))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        frame_ops.Frame2DCP(torch.rand(1, 3, 8, 8))
+
+
+def test_product_code_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under ebfi-be_b200/ may import, load or execute it."""
+    pkg = os.path.join(ROOT, "ebfi-be_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b|oracle/_ref|libebfi_oracle|oracle\.oracle", text, re.M):
+                    offenders.append(os.path.relpath(os.path.join(dirpath, f), ROOT))
+    assert offenders == []
 
 
 def test_module_parameters_match_reference_layout():
