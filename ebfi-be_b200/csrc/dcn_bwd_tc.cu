@@ -466,6 +466,10 @@ int backward_tc(cudaStream_t st, const DcnDims &d, const float *input, const flo
     EBFI_CUDA_OK(cudaMemsetAsync(gin_blk, 0, n * (d.det ? sizeof(long long) : sizeof(float)), st));
     dim3 grid(S, d.dg);
     CUtensorMap tm_off{}, tm_mask{};
+    if (pl.om_bytes > 0 && !(ebfi::aligned16(offset) && ebfi::aligned16(mask))) {   // TMA needs 16-byte aligned bases
+        pl.om_bytes = 0;
+        pl.smem = pl.om_off;
+    }
     if (pl.om_bytes > 0) {
         const uint64_t str[2] = {(uint64_t)d.Wo * 4, (uint64_t)d.Ho * d.Wo * 4};
         const uint64_t dims_o[3] = {(uint64_t)d.Wo, (uint64_t)d.Ho, (uint64_t)(d.B - 1) * d.off_bp + 2 * d.dg * d.KK};

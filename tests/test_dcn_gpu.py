@@ -398,3 +398,30 @@ def test_deterministic_follows_torch_switch(dcn):
     finally:
         torch.use_deterministic_algorithms(False)
     assert torch.equal(outs[0], outs[1])
+
+
+def test_backward_with_misaligned_offset_views(dcn, oracle):
+    """offset / mask tensors whose storage starts 4 bytes off a 16-byte boundary (contiguous views of a larger buffer):
+    the TMA staging of the backward cannot be used; the kernel must fall back to direct loads, not fail."""
+    from gpu_util import dev, n, t
+    rng = np.random.default_rng(17)
+    B, C, H, W, dg = 1, 64, 16, 16, 8
+    x = rng.standard_normal((B, C, H, W), dtype=np.float32)
+    w = ((rng.random((64, C, 3, 3), dtype=np.float32) * 2 - 1) / 24).astype(np.float32)
+    b = rng.standard_normal(64, dtype=np.float32)
+    off = (2 * rng.standard_normal((B, 2 * dg * 9, H, W))).astype(np.float32)
+    msk = rng.random((B, dg * 9, H, W), dtype=np.float32)
+    go = rng.standard_normal((B, 64, H, W), dtype=np.float32)
+
+    def shifted(a):
+        buf = torch.empty(a.size + 1, device=dev())
+        v = buf[1:].view(a.shape)
+        v.copy_(t(a))
+        assert v.is_contiguous() and v.data_ptr() % 16 == 4
+        return v
+
+    from ebfi_be_b200.shims import _ext
+    grads = _ext.dcn_v2_backward(t(x), t(w), t(b), shifted(off), shifted(msk), t(go), 3, 3, 1, 1, 1, 1, 1, 1, dg)
+    want = oracle.dcn_backward(x, off, msk, w, b, go, 1, 1, 1, dg)
+    for name, got, ref in zip(GRADS, grads, want):
+        assert rel_err(n(got), ref) < GRAD_TOL, name
