@@ -501,7 +501,8 @@ static int run_backward(void *stream, const DcnDims &d_in, const float *input, c
     cudaStream_t st = ebfi::as_stream(stream);
     DcnDims d = d_in;
     const char *impl = getenv("EBFI_DCN_IMPL");
-    const int S_tc = (impl && impl[0] == 's') ? 0 : backward_tc_splits(d);
+    // the tensor-core backward stages grad_output with 128-bit loads: it needs a 16-byte aligned base
+    const int S_tc = ((impl && impl[0] == 's') || !ebfi::aligned16(grad_output)) ? 0 : backward_tc_splits(d);
     const int S = S_tc > 0 ? S_tc : bwd_splits(d);
     const size_t n_w = (size_t)d.Co * d.C * d.KK, n_b = (size_t)d.Co;
     const size_t n_in = (size_t)d.B * d.C * d.H * d.W;
