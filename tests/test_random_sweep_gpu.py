@@ -91,3 +91,49 @@ def test_event_stack_random_bins_and_sizes(oracle, seed):
     tn = ((ts - ts[0]) / (ts[-1] - ts[0] + 1e-6)).astype(np.float32)
     st = encodings.events_to_stack(t(xs.astype(np.float32)), t(ys.astype(np.float32)), t(tn), t(ps.astype(np.float32)), bins, (H, W))
     assert np.array_equal(n(st), oracle.events_to_stack(xs.astype(np.float32), ys.astype(np.float32), tn, ps.astype(np.float32), bins, (H, W))[0])
+
+
+def _shifted(a, dtype=torch.float32):
+    """Contiguous CUDA copy of `a` whose storage starts one element off the allocation (not 16-byte aligned)."""
+    from gpu_util import dev
+    src = torch.as_tensor(a).to(dtype)
+    buf = torch.empty(src.numel() + 1, dtype=dtype, device=dev())
+    v = buf[1:].view(src.shape)
+    v.copy_(src)
+    assert v.data_ptr() % 16 != 0
+    return v
+
+
+def test_misaligned_views_fac_kpn_events(oracle):
+    """Vector loads / TMA need 16-byte aligned bases; contiguous views that are not aligned must take the scalar
+    paths and still match the oracle (FAC forward + backward, fused KernelConv->FAC, raw event stack)."""
+    from ebfi_be_b200 import encodings, modification
+    from ebfi_be_b200.shims import kernelconv2d_cuda as kc
+    from gpu_util import n
+    rng = np.random.default_rng(5)
+    B, C, K, H, W = 1, 3, 5, 20, 256
+    xi = rng.standard_normal((B, C, H + 4, W + 4), dtype=np.float32)
+    ker = rng.standard_normal((B, C * 25, H, W), dtype=np.float32)
+    go = rng.standard_normal((B, C, H, W), dtype=np.float32)
+    out, gi, gk = _shifted(np.zeros_like(go)), _shifted(np.zeros_like(xi)), _shifted(np.zeros_like(ker))
+    kc.forward(_shifted(xi), _shifted(ker), K, out)
+    kc.backward(_shifted(xi), _shifted(ker), K, _shifted(go), gi, gk)
+    assert rel_err(n(out), oracle.fac_forward(xi, ker, K)) < FWD_TOL
+    wi, wk = oracle.fac_backward(xi, ker, go, K)
+    assert rel_err(n(gi), wi) < GRAD_TOL and rel_err(n(gk), wk) < GRAD_TOL
+
+    ev = rng.standard_normal((1, 32, 19, 12), dtype=np.float32)
+    fr = rng.standard_normal((1, 32, 19, 12), dtype=np.float32)
+    w = (0.05 * rng.standard_normal((800, 64, 3, 3))).astype(np.float32)
+    b = (0.1 * rng.standard_normal(800)).astype(np.float32)
+    with torch.no_grad():
+        got = modification.kernelconv_fac_fused(_shifted(ev), _shifted(fr), _shifted(w), _shifted(b), 5, 0.01)
+    assert rel_err(n(got), oracle.kpn_fused_forward(ev, fr, w, b, 5, 0.01, bf16_operands=True)[0]) < 1e-5
+
+    N = 5000
+    xs, ys = rng.integers(0, 40, N).astype(np.int16), rng.integers(0, 30, N).astype(np.int16)
+    ts = 1.0 + np.sort(rng.random(N))
+    ps = (rng.integers(0, 2, N) * 2 - 1).astype(np.int8)
+    st = encodings.events_raw_to_stack(_shifted(xs, torch.int16), _shifted(ys, torch.int16), _shifted(ts, torch.float64),
+                                       _shifted(ps, torch.int8), 8, (30, 40))
+    assert np.array_equal(n(st), oracle.dataset_event_stack(xs, ys, ts, ps, 8, (30, 40)))
