@@ -351,7 +351,11 @@ dcn_bwd_tc_kernel(const float *__restrict__ in_blk, const float *__restrict__ we
 
 // NCHW (B, dg*8, H, W)  <->  group-blocked (B, dg, H, W, 8): one thread per (b, g, y, x); reads and
 // writes are both coalesced (8 plane reads of consecutive x, 32 contiguous bytes per thread).
-__global__ void nchw_to_blocked(const float *__restrict__ src, float *__restrict__ dst, int BG, int HW)
+// `zero` (nullable): a second (BG, HW, 8)-shaped buffer of `zero_f4` float4 per item that is cleared in the same pass
+// (the backward's grad_input accumulator: 2 float4 per item, 4 for the int64 copy of the deterministic mode) — saves the
+// separate memset launch.
+__global__ void nchw_to_blocked(const float *__restrict__ src, float *__restrict__ dst, int BG, int HW,
+                                float4 *__restrict__ zero, int zero_f4)
 {
     const size_t n = (size_t)BG * HW;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -363,6 +367,8 @@ __global__ void nchw_to_blocked(const float *__restrict__ src, float *__restrict
         float4 *dp = reinterpret_cast<float4 *>(dst + i * CS);
         dp[0] = make_float4(v[0], v[1], v[2], v[3]);
         dp[1] = make_float4(v[4], v[5], v[6], v[7]);
+        if (zero)
+            for (int q = 0; q < zero_f4; ++q) zero[i * zero_f4 + q] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 
@@ -433,10 +439,10 @@ int backward_tc_splits(const DcnDims &d)
     return std::max(1, std::min(tiles, ceil_div(2 * ebfi::sm_count(), d.dg)));
 }
 
-int launch_nchw_to_blocked(cudaStream_t st, const float *src, float *dst, int BG, int HW)
+int launch_nchw_to_blocked(cudaStream_t st, const float *src, float *dst, int BG, int HW, void *zero, int zero_f4)
 {
     const unsigned tgrid = (unsigned)std::min<size_t>(ceil_div((size_t)BG * HW, (size_t)256), (size_t)ebfi::sm_count() * 16);
-    nchw_to_blocked<<<tgrid, 256, 0, st>>>(src, dst, BG, HW);
+    nchw_to_blocked<<<tgrid, 256, 0, st>>>(src, dst, BG, HW, static_cast<float4 *>(zero), zero_f4);
     EBFI_LAUNCH_OK("nchw_to_blocked");
     return EBFI_OK;
 }
@@ -462,8 +468,8 @@ int backward_tc(cudaStream_t st, const DcnDims &d, const float *input, const flo
     float *in_blk = static_cast<float *>(scratch), *gin_blk = in_blk + n;
     const int BG = d.B * d.dg, HW = d.H * d.W;
     const unsigned tgrid = (unsigned)std::min<size_t>(ceil_div((size_t)BG * HW, (size_t)256), (size_t)ebfi::sm_count() * 16);
-    if (int rc = launch_nchw_to_blocked(st, input, in_blk, BG, HW)) return rc;
-    EBFI_CUDA_OK(cudaMemsetAsync(gin_blk, 0, n * (d.det ? sizeof(long long) : sizeof(float)), st));
+    // blocked copy of the input + zero fill of the grad_input accumulator (fp32, or int64 in deterministic mode) in one pass
+    if (int rc = launch_nchw_to_blocked(st, input, in_blk, BG, HW, gin_blk, d.det ? 4 : 2)) return rc;
     dim3 grid(S, d.dg);
     CUtensorMap tm_off{}, tm_mask{};
     if (pl.om_bytes > 0 && !(ebfi::aligned16(offset) && ebfi::aligned16(mask))) {   // TMA needs 16-byte aligned bases

@@ -150,6 +150,6 @@ __device__ __forceinline__ f8 ldg_f8(const float *p32B_aligned, bool ok)
 int launch_det_bound(cudaStream_t st, const DcnDims &d, const float *gout, const float *weight, const float *mask, float *bound);
 
 // NCHW (BG*8 planes of HW pixels) -> group-blocked (BG, HW, 8) copy (dcn_bwd_tc.cu)
-int launch_nchw_to_blocked(cudaStream_t st, const float *src, float *dst, int BG, int HW);
+int launch_nchw_to_blocked(cudaStream_t st, const float *src, float *dst, int BG, int HW, void *zero = nullptr, int zero_f4 = 0);
 
 }  // namespace ebfi_dcn
