@@ -178,7 +178,14 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL on a high-priority stream: its (tiny) all-reduce kernel is scheduled ahead of the queued FAC CTAs
+        # instead of waiting behind an HBM-saturating grid
+        opts = None
+        try:
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        except Exception:
+            pass
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
         _bind_to_gpu_numa_node(torch, dev)
     ebfi_be_b200._lib.load()
     host = make_inputs(torch, dev, 1234 + rank)
@@ -224,6 +231,7 @@ def run_ours(args):
         run("fac_fwd")
         mark()
         run("fac_bwd")
+        mark()                      # kernel intervals end here; the collective's completion is timed separately
         if pending is not None:
             pending.wait()
         mark()
@@ -260,9 +268,11 @@ def run_ours(args):
         ms_total = float(tt)
     ms_step = ms_total / args.steps
     op_ms = {n: 0.0 for n in op_names}
+    allreduce_wait_ms = 0.0
     for s in range(args.steps):
         for i, n in enumerate(op_names):
-            op_ms[n] += marks[5 * s + i].elapsed_time(marks[5 * s + i + 1]) / args.steps
+            op_ms[n] += marks[6 * s + i].elapsed_time(marks[6 * s + i + 1]) / args.steps
+        allreduce_wait_ms += marks[6 * s + 4].elapsed_time(marks[6 * s + 5]) / args.steps
 
     # ---- e2e: autograd Functions, pinned host buffers in and out, copies inside the timed region
     pin = {k: v.pin_memory() for k, v in host.items()}
@@ -386,6 +396,45 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.kernels_only:
         widen = widening_numbers(torch, dev, d, timed)
 
+    # ---- every rank encodes its own event window (no collective); aggregate = N windows / max time
+    enc_scaling = None
+    if not args.kernels_only:
+        from ebfi_be_b200 import encodings
+        g = torch.Generator(device="cpu").manual_seed(70 + rank)
+        NEV, EH, EW = 10_000_000, 720, 1280
+        exs = torch.randint(0, EW, (NEV,), generator=g).float().to(dev)
+        eys = torch.randint(0, EH, (NEV,), generator=g).float().to(dev)
+        ets = torch.sort(torch.rand(NEV, generator=g))[0].to(dev)
+        eps_ = (torch.randint(0, 2, (NEV,), generator=g) * 2 - 1).float().to(dev)
+        if world > 1:
+            dist.barrier()
+        t_v = timed(lambda: encodings.events_to_voxel(exs, eys, ets, eps_, 5, sensor_size=(EH, EW)), n=10)
+        t_s = timed(lambda: encodings.events_to_stack(exs, eys, ets, eps_, 16, sensor_size=(EH, EW)), n=10)
+        if world > 1:
+            tt = torch.tensor([t_v, t_s], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_v, t_s = float(tt[0]), float(tt[1])
+        enc_scaling = {"workload": "each rank encodes its own 10M-event window at 1280x720 (no collective); max time over ranks",
+                       "voxel_5bins_Gev_s": round(world * NEV / 1e9 / (t_v * 1e-3), 2),
+                       "stack_16bins_Gev_s": round(world * NEV / 1e9 / (t_s * 1e-3), 2), "n_gpus": world}
+        del exs, eys, ets, eps_
+
+    # ---- BASELINE configs[3] / configs[4]: the reference's own model on these kernels (tools/bench_model.py)
+    cfg4 = cfg5 = None
+    if not (args.kernels_only or args.no_model):
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_model
+        torch.cuda.empty_cache()
+        try:
+            if world == 1:
+                cfg4 = bench_model.cfg4_inference(torch, dev)
+            cfg5 = bench_model.cfg5_train_step(torch, dev, world)
+        except Exception as e:       # the legs are reported beside the headline; a failure there must not lose the line
+            import traceback
+            err = {"error": f"{type(e).__name__}: {e}", "trace": traceback.format_exc()[-800:]}
+            cfg4 = cfg4 or (err if world == 1 else None)
+            cfg5 = cfg5 or err
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -425,7 +474,11 @@ def run_ours(args):
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "api": "ebfi_be_b200.host_pipeline (dcn_v2_conv / KernelConv2DFunction autograd, pinned host in/out, "
                        "per-sample H2D | compute | D2H on three streams)"},
+        "allreduce_wait_ms": round(allreduce_wait_ms, 4) if world > 1 else None,
         "events": events,
+        "events_per_rank": enc_scaling,
+        "cfg4_inference_720p": cfg4,
+        "cfg5_train_step": cfg5,
         "widening": widen,
         "gpu_launches": LAUNCHES_PER_STEP * args.steps,
         "launch_mode": "eager" if args.no_graphs else "one CUDA graph per operator call (4 replays per step)",
@@ -680,6 +733,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="eager operator calls instead of CUDA-graph replays")
+    ap.add_argument("--no-model", action="store_true", help="skip the full-model legs (BASELINE configs[3], configs[4])")
     ap.add_argument("--kernels-only", action="store_true",
                     help="profiling runs: skip the e2e, cold-breakdown and CPU-baseline legs")
     args = ap.parse_args()

@@ -9,6 +9,7 @@ is absent.
 """
 import logging
 import math
+import threading
 
 import torch
 from torch import nn
@@ -150,27 +151,45 @@ class _OffsetWatch:
     def __init__(self):
         self._pending = []          # (event, pinned value, element count)
         self._free = []             # pinned 1-float buffers, reused (cudaHostAlloc is slow)
+        self._lock = threading.Lock()   # nn.DataParallel replicas share the module attribute across threads
+
+    # CUDA events and pinned buffers are per-process runtime state: copies (copy.deepcopy for EMA models,
+    # torch.save(model), DataParallel replicas) start with a fresh, empty watcher — pending warnings stay with the original
+    def __getstate__(self):
+        return {}
+
+    def __setstate__(self, state):
+        self.__init__()
+
+    def __deepcopy__(self, memo):
+        return _OffsetWatch()
 
     def submit(self, stat, count):
-        host = self._free.pop() if self._free else torch.empty(1, dtype=torch.float32, pin_memory=True)
+        with self._lock:
+            host = self._free.pop() if self._free else torch.empty(1, dtype=torch.float32, pin_memory=True)
         host.copy_(stat, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
-        self._pending.append((ev, host, count))
+        with self._lock:
+            self._pending.append((ev, host, count))
 
     def poll(self, wait=False):
+        with self._lock:
+            pending, self._pending = self._pending, []
         keep = []
-        for ev, host, count in self._pending:
+        for ev, host, count in pending:
             if wait:
                 ev.synchronize()
             if ev.query():
                 mean = float(host[0]) / count
                 if mean > 100:
                     logger.warning("Offset mean is {}, larger than 100.".format(mean))
-                self._free.append(host)
+                with self._lock:
+                    self._free.append(host)
             else:
                 keep.append((ev, host, count))
-        self._pending = keep
+        with self._lock:
+            self._pending = keep + self._pending
 
     def flush(self):
         self.poll(wait=True)

@@ -48,6 +48,12 @@ def kernelconv_fac_fused(event_feat, frame_feat, conv_weight, conv_bias, kernel_
     return out
 
 
+def kernelconv_fac_fused_supported(channels_event, channels_frame, kernel_size):
+    """Shapes `ebfi_kpn_fused_forward` accepts (csrc/kpn.cu `fill`): odd K <= 5, (Ce + Cf) a multiple of 32 and <= 128."""
+    K, cin = int(kernel_size), int(channels_event) + int(channels_frame)
+    return K >= 1 and K % 2 == 1 and K <= 5 and cin % 32 == 0 and cin <= 128
+
+
 class _ConvLayer(nn.Module):
     """ConvLayer(norm=None, activation='LeakyReLU') of models/model_misc/submodules.py:159-200: parameter names
     `conv2d.weight`, `conv2d.bias` as in the reference's checkpoints."""
@@ -63,7 +69,15 @@ class _ConvLayer(nn.Module):
 
 class KernelPrediction(nn.Module):
     """`KernelConv` + `KPN` of Modification (model_singleframe.py:145-146,161-162): forward(EventTensor, FrameTensor)
-    -> KPN(EventTensor, KernelConv(cat([EventTensor, FrameTensor], 1))). Fused when no gradient is needed."""
+    -> KPN(EventTensor, KernelConv(cat([EventTensor, FrameTensor], 1))).
+
+    `fused = True` (class or instance attribute, like `DCN.fused`): when no gradient is needed and the shape is one the
+    fused kernel supports, producer and consumer run as one kernel whose conv operands are rounded to bf16 — eval
+    outputs then differ from the training / reference path (cuDNN TF32 or fp32 conv) by up to 1e-2 of max|out|
+    (bound tested in tests/test_kpn_gpu.py; measured 1.5e-3). Set `fused = False` for the reference's op sequence
+    in every mode. Unsupported shapes (e.g. FrameBasech = 24 or 96, KernelSize = 7) always take that sequence."""
+
+    fused = True
 
     def __init__(self, FrameBasech=64, KernelSize=5):
         super().__init__()
@@ -75,7 +89,9 @@ class KernelPrediction(nn.Module):
         conv = self.KernelConv.conv2d
         needs_grad = torch.is_grad_enabled() and (EventTensor.requires_grad or FrameTensor.requires_grad
                                                   or conv.weight.requires_grad)
-        if EventTensor.is_cuda and EventTensor.dtype in (torch.float32, torch.bfloat16) and not needs_grad:
+        if self.fused and not needs_grad and EventTensor.is_cuda and EventTensor.dtype in (torch.float32, torch.bfloat16) \
+                and FrameTensor.dtype == EventTensor.dtype and conv.weight.dtype == EventTensor.dtype \
+                and kernelconv_fac_fused_supported(EventTensor.shape[1], FrameTensor.shape[1], self.kernel_size):
             return kernelconv_fac_fused(EventTensor, FrameTensor, conv.weight, conv.bias, self.kernel_size,
                                         self.KernelConv.activation.negative_slope)
         Kernel = self.KernelConv(torch.cat([EventTensor, FrameTensor], dim=1))
