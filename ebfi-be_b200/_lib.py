@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libebfi_b200.so")
+LIB_PATH = os.environ.get("EBFI_LIB_PATH") or os.path.join(_HERE, "lib", "libebfi_b200.so")   # override: A/B a debug build
 
 EBFI_F32, EBFI_F64 = 0, 1
 _lib = None

@@ -17,6 +17,8 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
          "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr",
          "-Xptxas", "-warn-spills"]
+if os.environ.get("EBFI_DEBUG_HANG"):       # debugging build: mbarrier waits trap with a location instead of hanging
+    FLAGS.append("-DEBFI_DEBUG_HANG")
 
 
 def sources():

@@ -39,6 +39,7 @@ namespace {
 using ebfi::ceil_div;
 
 constexpr int TM = 128, TH = 8, TW = 16, NR = 3;
+constexpr int KSTEPS = NR;                      // a stage's K = NR taps x 8 channels = NR tf32 MMA steps
 constexpr int BH = 24, BW = 30;                 // staged box: rows x pixels (8 channels each)
 constexpr int BOX_PITCH = BW * 32;              // bytes; 960 = 64 (mod 128)
 constexpr int BOX_BYTES = BH * BOX_PITCH;       // 23,040 (a multiple of 128)
@@ -57,6 +58,7 @@ struct BoxPlan {
     int a_bytes, b_bytes;
     int om_bytes, use_om_tma;
     int my, mx;          // rows / pixels of the box above / left of the tile's undeformed footprint
+    int unit_bytes;      // weight images of one (group, chunk) unit: TPR stages x (hi | lo)
     int off_w, off_box, off_om, smem;
 };
 
@@ -67,51 +69,55 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr)
     return v;
 }
 
-// One modulated bilinear sample of 8 channels. In-box: rotated conflict-free LDS.128 gather (see the file header).
-// `ibf` = the chunk's blocked global plane for the fallback.
-__device__ __forceinline__ void sample8(float y, float x, float m, int H, int W, uint32_t box_s, int by0, int bx0,
-                                        const float *__restrict__ ibf, int lane, float (&val)[8])
+// One modulated bilinear sample of 8 channels. In-box: rotated conflict-free LDS.128 gather (see the file header);
+// the two 16-byte halves (channels 0-3 / 4-7) come back in `ha` / `hb`, SWAPPED when the function returns true (the
+// caller swaps the store addresses instead of eight values). `ibf` = the chunk's blocked global plane for the fallback.
+__device__ __forceinline__ bool sample8(float y, float x, float m, int H, int W, uint32_t box_s, int by0, int bx0,
+                                        const float *__restrict__ ibf, int lane, float (&ha)[4], float (&hb)[4])
 {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) val[j] = 0.f;
+    for (int j = 0; j < 4; ++j) ha[j] = hb[j] = 0.f;
     // the sampling window of the reference (im2col_cuda.cu:180); NaN coordinates fail it like they do there
-    if (!(y > -1.f && x > -1.f && y < (float)H && x < (float)W)) return;
+    if (!(y > -1.f && x > -1.f && y < (float)H && x < (float)W)) return false;
     const float fy = floorf(y), fx = floorf(x);
     const int y0 = (int)fy, x0 = (int)fx;
     const float ly = y - fy, lx = x - fx, hy = 1.f - ly, hx = 1.f - lx;
+    const float my = m * hy, mly = m * ly;
     const int yb = y0 - by0, xb = x0 - bx0;
     if ((unsigned)yb <= (unsigned)(BH - 2) && (unsigned)xb <= (unsigned)(BW - 2)) {
-        const int cell = yb * BW + xb;
-        const uint32_t base = box_s + (uint32_t)cell * 32u;
-        const int c0 = (lane - (int)(base >> 4)) & 7;    // first chunk: bank group of (base + 16*c0) = lane (mod 8)
-        const bool odd = c0 & 1;
-        // corner weights rotated so that w[j] belongs to corner (c0/2 + j) mod 4; corners: 0 (y0,x0) 1 (y0,x0+1) 2 (y0+1,x0) 3 (y0+1,x0+1)
-        float w0 = hy * hx, w1 = hy * lx, w2 = ly * hx, w3 = ly * lx;
-        if (c0 & 2) { const float t = w0; w0 = w1; w1 = w2; w2 = w3; w3 = t; }
-        if (c0 & 4) { float t = w0; w0 = w2; w2 = t; t = w1; w1 = w3; w3 = t; }
+        const uint32_t base = box_s + (uint32_t)(yb * BW + xb) * 32u;
+        const uint32_t c0 = ((uint32_t)lane - (base >> 4)) & 7u;   // first chunk: bank group of (base + 16*c0) = lane (mod 8)
+        const bool odd = c0 & 1u;
+        // corner weights (mask folded in) rotated so that w[j] belongs to corner (c0/2 + j) mod 4;
+        // corners: 0 (y0,x0)  1 (y0,x0+1)  2 (y0+1,x0)  3 (y0+1,x0+1)
+        float w0 = my * hx, w1 = my * lx, w2 = mly * hx, w3 = mly * lx;
+        if (c0 & 2u) { const float t = w0; w0 = w1; w1 = w2; w2 = w3; w3 = t; }
+        if (c0 & 4u) { float t = w0; w0 = w2; w2 = t; t = w1; w1 = w3; w3 = t; }
         const float wr[5] = {w0, w1, w2, w3, w0};
-        float ae[4] = {0.f, 0.f, 0.f, 0.f}, ao[4] = {0.f, 0.f, 0.f, 0.f};      // even / odd steps = the two 16-byte halves
+        // byte table of chunk offsets / 16 = {0,1,2,3, 60,61,62,63} (second row = +BOX_PITCH), rotated by c0 bytes
+        constexpr uint32_t T_LO = 0x03020100u, T_HI = 0x03020100u + 0x01010101u * (BOX_PITCH / 16);
+        const uint32_t ta = (c0 & 4u) ? T_HI : T_LO, tb = (c0 & 4u) ? T_LO : T_HI, sh = (c0 & 3u) * 8u;
+        const uint32_t r_lo = __funnelshift_r(ta, tb, sh), r_hi = __funnelshift_r(tb, ta, sh);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int c = (c0 + i) & 7;
-            const float4 q = lds128(base + (uint32_t)((c & 3) * 16 + (c >> 2) * BOX_PITCH));
+            const uint32_t o16 = __byte_perm(i < 4 ? r_lo : r_hi, 0u, 0x4440u | (uint32_t)(i & 3));
+            const float4 q = lds128(base + (o16 << 4));
             const float wi = odd ? wr[(i + 1) >> 1] : wr[i >> 1];
-            float *a = (i & 1) ? ao : ae;
+            float *a = (i & 1) ? hb : ha;                      // even / odd steps = the two 16-byte halves
             a[0] += wi * q.x; a[1] += wi * q.y; a[2] += wi * q.z; a[3] += wi * q.w;
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            val[j] = (odd ? ao[j] : ae[j]) * m;          // channels 0..3 = first half of a pixel's 32 bytes
-            val[4 + j] = (odd ? ae[j] : ao[j]) * m;
-        }
-    } else {
-        const Tap tp = make_tap(y, x, H, W);
-        const float w1 = tp.hy * tp.hx, w2 = tp.hy * tp.lx, w3 = tp.ly * tp.hx, w4 = tp.ly * tp.lx;
-        const f8 a = ldg_f8(ibf + (size_t)tp.i00 * 8, tp.c00), bq = ldg_f8(ibf + (size_t)tp.i01 * 8, tp.c01);
-        const f8 c = ldg_f8(ibf + (size_t)tp.i10 * 8, tp.c10), e8 = ldg_f8(ibf + (size_t)tp.i11 * 8, tp.c11);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) val[j] = (w1 * a.v[j] + w2 * bq.v[j] + w3 * c.v[j] + w4 * e8.v[j]) * m;
+        return odd;
     }
+    const Tap tp = make_tap(y, x, H, W);
+    const float w1 = tp.hy * tp.hx * m, w2 = tp.hy * tp.lx * m, w3 = tp.ly * tp.hx * m, w4 = tp.ly * tp.lx * m;
+    const f8 a = ldg_f8(ibf + (size_t)tp.i00 * 8, tp.c00), bq = ldg_f8(ibf + (size_t)tp.i01 * 8, tp.c01);
+    const f8 c = ldg_f8(ibf + (size_t)tp.i10 * 8, tp.c10), e8 = ldg_f8(ibf + (size_t)tp.i11 * 8, tp.c11);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        ha[j] = w1 * a.v[j] + w2 * bq.v[j] + w3 * c.v[j] + w4 * e8.v[j];
+        hb[j] = w1 * a.v[4 + j] + w2 * bq.v[4 + j] + w3 * c.v[4 + j] + w4 * e8.v[4 + j];
+    }
+    return false;
 }
 
 template <int TPR, bool PACKED>
@@ -124,10 +130,10 @@ dcn_fwd_box_kernel(const float *__restrict__ in_blk, const float *__restrict__ b
 {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *aring = smem;                       // [NS][a_hi | a_lo]
-    unsigned char *wring = smem + pl.off_w;            // [NS][b_hi | b_lo]
+    unsigned char *wring = smem + pl.off_w;            // [2 units][TPR stages][b_hi | b_lo], one unit ahead of the samplers
     unsigned char *boxes = smem + pl.off_box;          // [2][BH][BW][8] fp32
     const float *oms = reinterpret_cast<const float *>(smem + pl.off_om);   // [2][3*KK planes][128 px]
-    __shared__ __align__(8) uint64_t slot_free[NS], a_full[NS], w_full[NS];
+    __shared__ __align__(8) uint64_t slot_free[NS], a_full[NS], wu_full[2], wu_free[2];
     __shared__ __align__(8) uint64_t box_full[2], box_free[2], om_full[2], om_free[2], acc_full[2], acc_free[2];
     __shared__ uint32_t tmem_slot;
 
@@ -136,18 +142,25 @@ dcn_fwd_box_kernel(const float *__restrict__ in_blk, const float *__restrict__ b
     const int stages = units * TPR;                    // operand stages per tile
     const int total_tiles = d.B * pl.ntiles;
     const uint32_t sbo = (uint32_t)pl.kch * 128u;
-    const uint32_t wb = 2u * (uint32_t)pl.b_bytes;
+    const uint32_t wb = 2u * (uint32_t)pl.b_bytes;       // one stage's weight image (hi | lo)
 
     if (warp == 0) umma::tmem_alloc<TMEM_COLS>(&tmem_slot);
     if (tid == 32) {
-        for (int i = 0; i < NS; ++i) { umma::mbar_init(&slot_free[i], 1); umma::mbar_init(&a_full[i], N_SAMP); umma::mbar_init(&w_full[i], 1); }
+        for (int i = 0; i < NS; ++i) { umma::mbar_init(&slot_free[i], 1); umma::mbar_init(&a_full[i], N_SAMP); }
         for (int i = 0; i < 2; ++i) {
+            umma::mbar_init(&wu_full[i], 1); umma::mbar_init(&wu_free[i], 1);
             umma::mbar_init(&box_full[i], 1); umma::mbar_init(&box_free[i], N_SAMP);
             umma::mbar_init(&om_full[i], 1); umma::mbar_init(&om_free[i], N_SAMP);
             umma::mbar_init(&acc_full[i], 1); umma::mbar_init(&acc_free[i], N_EPI);
         }
         umma::mbar_fence_init();
     }
+#ifdef EBFI_DEBUG_HANG_ADDR
+    if (tid == 0 && blockIdx.x == 0)
+        printf("fwd barriers: slot_free 0x%x a_full 0x%x wu_full 0x%x wu_free 0x%x box_full 0x%x box_free 0x%x om_full 0x%x om_free 0x%x acc_full 0x%x acc_free 0x%x\n",
+               umma::smem_u32(slot_free), umma::smem_u32(a_full), umma::smem_u32(wu_full), umma::smem_u32(wu_free), umma::smem_u32(box_full),
+               umma::smem_u32(box_free), umma::smem_u32(om_full), umma::smem_u32(om_free), umma::smem_u32(acc_full), umma::smem_u32(acc_free));
+#endif
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
@@ -164,7 +177,7 @@ dcn_fwd_box_kernel(const float *__restrict__ in_blk, const float *__restrict__ b
         const size_t plane = (size_t)d.Ho * d.Wo;
         const int p = warp * 32 + lane;
         const uint32_t lane_base = (uint32_t)warp * 32u;
-        const int total_steps = stages * (pl.Ksp / 8), nused = min(pl.nacc, total_steps);
+        const int total_steps = stages * KSTEPS, nused = min(pl.nacc, total_steps);
         int k = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++k) {
             const int ab = k & 1;
@@ -263,18 +276,22 @@ dcn_fwd_box_kernel(const float *__restrict__ in_blk, const float *__restrict__ b
 #pragma unroll
                         for (int q = 1; q < TPR; ++q)
                             if (s == q) { y = sy[q]; x = sx[q]; m = sm[q]; }
-                        float val[8], hi[8], lo[8];
-                        sample8(y, x, m, d.H, d.W, box_s, by0, bx0, ibf, lane, val);
+                        float ha[4], hb[4], hi[8], lo[8];
+                        const bool swapped = sample8(y, x, m, d.H, d.W, box_s, by0, bx0, ibf, lane, ha, hb);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) umma::split_tf32(val[j], hi[j], lo[j]);
+                        for (int j = 0; j < 4; ++j) {
+                            umma::split_tf32(ha[j], hi[j], lo[j]);
+                            umma::split_tf32(hb[j], hi[4 + j], lo[4 + j]);
+                        }
                         if (n >= NS) umma::mbar_wait(&slot_free[slot], sph ^ 1u);      // MMAs of stage n - NS are done
                         float *a_hi = reinterpret_cast<float *>(aring + slot * 2 * pl.a_bytes);
                         float *a_lo = reinterpret_cast<float *>(aring + slot * 2 * pl.a_bytes + pl.a_bytes);
-                        const int off = a_row + (r * 2) * 32;                           // K order: row r major, channel minor
-                        *reinterpret_cast<float4 *>(a_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                        *reinterpret_cast<float4 *>(a_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                        *reinterpret_cast<float4 *>(a_hi + off + 32) = make_float4(hi[4], hi[5], hi[6], hi[7]);
-                        *reinterpret_cast<float4 *>(a_lo + off + 32) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+                        // K order: row r major, channel minor; the two 16-byte K chunks of this tap trade places when swapped
+                        const int off_a = a_row + (r * 2 + (swapped ? 1 : 0)) * 32, off_b = a_row + (r * 2 + (swapped ? 0 : 1)) * 32;
+                        *reinterpret_cast<float4 *>(a_hi + off_a) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<float4 *>(a_lo + off_a) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                        *reinterpret_cast<float4 *>(a_hi + off_b) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+                        *reinterpret_cast<float4 *>(a_lo + off_b) = make_float4(lo[4], lo[5], lo[6], lo[7]);
                         umma::fence_smem_to_async();
                         __syncwarp();
                         if (lane == 0) umma::mbar_arrive(&a_full[slot]);
@@ -290,36 +307,47 @@ dcn_fwd_box_kernel(const float *__restrict__ in_blk, const float *__restrict__ b
         // ================= MMA issuer: all lanes run the loop with warp-uniform values, one elected lane issues =================
         const bool leader = umma::elect_one();
         const uint32_t idesc = umma::instr_desc_tf32(TM, d.Co, 0, 0);
-        const int ksteps = pl.Ksp / 8;
         int slot = 0; uint32_t sph = 0;
-        int k = 0;
+        int k = 0, U = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++k) {
             const int ab = k & 1;
             if (k >= 2) umma::mbar_wait(&acc_free[ab], (uint32_t)(((k >> 1) - 1) & 1));
             umma::fence_after_sync();
             const uint32_t tb = tmem + (uint32_t)(ab * ACC_COLS);
             int step = 0;
-            for (int s = 0; s < stages; ++s) {
-                umma::mbar_wait(&w_full[slot], sph);
-                umma::mbar_wait(&a_full[slot], sph);
-                umma::fence_after_sync();
-                const uint32_t ah = umma::smem_u32(aring + slot * 2 * pl.a_bytes), bh = umma::smem_u32(wring + slot * wb);
-                uint64_t dah = umma::smem_desc(ah, 128, sbo), dal = umma::smem_desc(ah + (uint32_t)pl.a_bytes, 128, sbo);
-                uint64_t dbh = umma::smem_desc(bh, 128, sbo), dbl = umma::smem_desc(bh + (uint32_t)pl.b_bytes, 128, sbo);
-                for (int ks = 0; ks < ksteps; ++ks, ++step, dah += 16, dal += 16, dbh += 16, dbl += 16) {
-                    const uint32_t d_x = tb + pl.nacc * d.Co, d_h = tb + (step % pl.nacc) * d.Co;
-                    if (leader) {
-                        umma::mma_tf32(d_x, dal, dbh, idesc, step > 0);
-                        umma::mma_tf32(d_x, dah, dbl, idesc, true);
-                        umma::mma_tf32(d_h, dah, dbh, idesc, step >= pl.nacc);
+            uint32_t hsel = 0;
+            const uint32_t d_x = tb + (uint32_t)(pl.nacc * d.Co);
+            for (int u = 0; u < units; ++u, ++U) {
+                const int ub = U & 1;
+                umma::mbar_wait(&wu_full[ub], (uint32_t)((U >> 1) & 1));
+                for (int s = 0; s < TPR; ++s) {
+                    umma::mbar_wait(&a_full[slot], sph);
+                    umma::fence_after_sync();
+                    const uint32_t ah = umma::smem_u32(aring + slot * 2 * pl.a_bytes);
+                    const uint32_t bh = umma::smem_u32(wring + ub * pl.unit_bytes) + (uint32_t)s * wb;
+                    uint64_t dah = umma::smem_desc(ah, 128, sbo), dal = umma::smem_desc(ah + (uint32_t)pl.a_bytes, 128, sbo);
+                    uint64_t dbh = umma::smem_desc(bh, 128, sbo), dbl = umma::smem_desc(bh + (uint32_t)pl.b_bytes, 128, sbo);
+                    // K steps of 8 (two 16-byte chunks = +256 B = +16 in the descriptor's address field); the hi*hi products
+                    // rotate over `nacc` accumulators (no division: hsel is carried), the cross terms share one
+#pragma unroll
+                    for (int ks = 0; ks < KSTEPS; ++ks) {
+                        const uint32_t d_h = tb + hsel * (uint32_t)d.Co;
+                        if (leader) {
+                            umma::mma_tf32(d_x, dal + 16 * ks, dbh + 16 * ks, idesc, step > 0);
+                            umma::mma_tf32(d_x, dah + 16 * ks, dbl + 16 * ks, idesc, true);
+                            umma::mma_tf32(d_h, dah + 16 * ks, dbh + 16 * ks, idesc, step >= pl.nacc);
+                        }
+                        ++step;
+                        if (++hsel == (uint32_t)pl.nacc) hsel = 0;
                     }
+                    if (leader) {
+                        umma::commit(&slot_free[slot]);
+                        if (s == TPR - 1) umma::commit(&wu_free[ub]);
+                        if (s == TPR - 1 && u == units - 1) umma::commit(&acc_full[ab]);
+                    }
+                    __syncwarp();
+                    if (++slot == NS) { slot = 0; sph ^= 1u; }
                 }
-                if (leader) {
-                    umma::commit(&slot_free[slot]);
-                    if (s == stages - 1) umma::commit(&acc_full[ab]);
-                }
-                __syncwarp();
-                if (++slot == NS) { slot = 0; sph ^= 1u; }
             }
         }
     } else if (warp == W_BOX) {
@@ -351,14 +379,13 @@ dcn_fwd_box_kernel(const float *__restrict__ in_blk, const float *__restrict__ b
     } else if (warp == W_WGT) {
         // ================= weight-image loader =================
         if (lane == 0) {
-            int slot = 0; uint32_t sph = 0;
-            int n = 0;
+            int U = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                for (int s = 0; s < stages; ++s, ++n) {
-                    if (n >= NS) umma::mbar_wait(&slot_free[slot], sph ^ 1u);
-                    umma::mbar_expect_tx(&w_full[slot], wb);
-                    umma::bulk_g2s(wring + slot * wb, wimg + (size_t)s * (wb / 4), wb, &w_full[slot]);
-                    if (++slot == NS) { slot = 0; sph ^= 1u; }
+                for (int u = 0; u < units; ++u, ++U) {
+                    const int ub = U & 1;
+                    if (U >= 2) umma::mbar_wait(&wu_free[ub], (uint32_t)(((U >> 1) - 1) & 1));
+                    umma::mbar_expect_tx(&wu_full[ub], (uint32_t)pl.unit_bytes);
+                    umma::bulk_g2s(wring + ub * pl.unit_bytes, wimg + (size_t)u * (pl.unit_bytes / 4), (uint32_t)pl.unit_bytes, &wu_full[ub]);
                 }
             }
         }
@@ -415,8 +442,9 @@ bool make_plan(const DcnDims &d, BoxPlan &pl)
     pl.mx = std::max(0, (BW - 1 - fw + 1) / 2);
     pl.om_bytes = 3 * d.KK * TM * 4;
     pl.use_om_tma = d.Wo % 4 == 0 && getenv("EBFI_DCN_NO_TMA") == nullptr;
+    pl.unit_bytes = pl.TPR * 2 * pl.b_bytes;
     pl.off_w = NS * 2 * pl.a_bytes;
-    pl.off_box = pl.off_w + NS * 2 * pl.b_bytes;
+    pl.off_box = pl.off_w + 2 * pl.unit_bytes;
     pl.off_om = pl.off_box + 2 * BOX_BYTES;
     pl.smem = pl.off_om + 2 * pl.om_bytes;
     return pl.smem <= 225 * 1024;

@@ -17,6 +17,7 @@
 // dropped lo*lo term and the truncation of lo to TF32 are both ~2^-22 relative.
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
@@ -127,6 +128,18 @@ __device__ __forceinline__ bool elect_one()
 }
 
 // ---- mbarrier -----------------------------------------------------------------------
+// -DEBFI_DEBUG_HANG: every wait loop reports (block, thread, shared address, parity) and traps after ~16 M polls, so a
+// protocol deadlock shows up as an error with a location instead of a hung GPU.
+#ifdef EBFI_DEBUG_HANG
+#define EBFI_HANG_CHECK(n, bar, parity)                                                                     \
+    if (++(n) > (1u << 24)) {                                                                               \
+        printf("mbarrier wait stuck: block %d thread %d bar 0x%x parity %u line %d\n", (int)blockIdx.x,     \
+               (int)threadIdx.x, smem_u32(bar), parity, __LINE__);                                          \
+        __trap();                                                                                           \
+    }
+#else
+#define EBFI_HANG_CHECK(n, bar, parity)
+#endif
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -146,7 +159,8 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 __device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity)
 {
     if ((threadIdx.x & 31) == 0) {
-        uint32_t done;
+        uint32_t done, polls = 0;
+        (void)polls;
         do {
             asm volatile(
                 "{\n\t.reg .pred p;\n\t"
@@ -155,14 +169,34 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity)
                 : "=r"(done)
                 : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
                 : "memory");
+            EBFI_HANG_CHECK(polls, bar, parity)
         } while (!done);
     }
     __syncwarp();
 }
 
+// Single-thread wait with a hardware suspend-time hint: for loader / controller lanes whose spinning would otherwise
+// take issue slots from the warps that do the work.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done, polls = 0;
+    (void)polls;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+            : "memory");
+        EBFI_HANG_CHECK(polls, bar, parity)
+    } while (!done);
+}
+
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
-    uint32_t done;
+    uint32_t done, polls = 0;
+    (void)polls;
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -171,6 +205,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
             : "=r"(done)
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
+        EBFI_HANG_CHECK(polls, bar, parity)
     } while (!done);
 }
 
