@@ -31,6 +31,11 @@ int forward_tc(cudaStream_t st, const DcnDims &d, const float *input, const floa
                const float *offset, const float *mask, float *output, void *workspace, size_t workspace_bytes);
 size_t forward_tc_workspace(const DcnDims &d);
 // tensor-core backward (dcn_bwd_tc.cu); splits == 0 when the shape is not eligible
+int backward_box_splits(const DcnDims &d);
+size_t backward_box_scratch_bytes(const DcnDims &d);
+int backward_box(cudaStream_t st, const DcnDims &d, const float *input, const float *weight, const float *offset,
+                 const float *mask, const float *gout, float *gin, float *goff, float *gmask, float *gw, float *gb,
+                 float *gw_part, float *gb_part, void *scratch);
 int backward_tc_splits(const DcnDims &d);
 size_t backward_tc_scratch_bytes(const DcnDims &d);
 int backward_tc(cudaStream_t st, const DcnDims &d, const float *input, const float *weight, const float *offset,
@@ -456,10 +461,10 @@ size_t ebfi_dcnv2_backward_workspace_bytes(const ebfi_dcn_geom *q)
 {
     DcnDims d{};
     if (fill_dims(q, d) != EBFI_OK) return 0;
-    const size_t S = (size_t)std::max(bwd_splits(d), backward_tc_splits(d));
+    const size_t S = (size_t)std::max({bwd_splits(d), backward_tc_splits(d), backward_box_splits(d)});
     const size_t det = d.det ? 256 + (size_t)d.B * d.C * d.H * d.W * sizeof(long long) : 0;   // bound + CUDA-core int64 copy
     return ebfi::round_up(S * ((size_t)d.Co * d.C * d.KK + d.Co) * sizeof(float), (size_t)256) +
-           std::max(backward_tc_scratch_bytes(d), det) + 512;
+           std::max({backward_tc_scratch_bytes(d), backward_box_scratch_bytes(d), det}) + 512;
 }
 
 size_t ebfi_dcnv2_forward_workspace_bytes(const ebfi_dcn_geom *q)
@@ -502,18 +507,23 @@ static int run_backward(void *stream, const DcnDims &d_in, const float *input, c
     DcnDims d = d_in;
     const char *impl = getenv("EBFI_DCN_IMPL");
     // the tensor-core backward stages grad_output with 128-bit loads: it needs a 16-byte aligned base
-    const int S_tc = ((impl && impl[0] == 's') || !ebfi::aligned16(grad_output)) ? 0 : backward_tc_splits(d);
+    const bool tc_ok = !(impl && impl[0] == 's') && ebfi::aligned16(grad_output);
+    // box kernel (dcn_bwd_box.cu) first; the group-specialised kernel (dcn_bwd_tc.cu) serves the deterministic flag
+    const int S_box = tc_ok ? backward_box_splits(d) : 0;
+    const int S_tc = S_box > 0 ? S_box : (tc_ok ? backward_tc_splits(d) : 0);
     const int S = S_tc > 0 ? S_tc : bwd_splits(d);
     const size_t n_w = (size_t)d.Co * d.C * d.KK, n_b = (size_t)d.Co;
     const size_t n_in = (size_t)d.B * d.C * d.H * d.W;
     // workspace: [grad_weight / grad_bias partials][scratch][deterministic mode: 3-float bound]
     const size_t part_bytes = ebfi::round_up((size_t)S * (n_w + n_b) * sizeof(float), (size_t)256);
     const size_t scratch_bytes = ebfi::round_up(
-        S_tc > 0 ? backward_tc_scratch_bytes(d) : (d.det ? n_in * sizeof(long long) : 0), (size_t)256);
+        S_box > 0 ? backward_box_scratch_bytes(d) : S_tc > 0 ? backward_tc_scratch_bytes(d) : (d.det ? n_in * sizeof(long long) : 0),
+        (size_t)256);
     const size_t need = part_bytes + scratch_bytes + (d.det ? 256 : 0);
     if (!workspace || workspace_bytes < need)
         return ebfi::fail(EBFI_ERR_WORKSPACE, "dcn_backward: workspace %zu < %zu bytes", workspace_bytes, need);
-    EBFI_REQUIRE(ebfi::aligned16(workspace), "dcn_backward: workspace must be 16-byte aligned");
+    // the blocked copies inside the workspace are read with 256-bit loads and by TMA
+    EBFI_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 31u) == 0, "dcn_backward: workspace must be 32-byte aligned");
     float *gw_part = static_cast<float *>(workspace);
     float *gb_part = gw_part + (size_t)S * n_w;
     char *scratch = static_cast<char *>(workspace) + part_bytes;
@@ -524,7 +534,11 @@ static int run_backward(void *stream, const DcnDims &d_in, const float *input, c
         EBFI_LAUNCH_OK("dcn_det_bound");
         d.det_bound = bound;
     }
-    if (S_tc > 0) {
+    if (S_box > 0) {
+        // writes all five gradients, including its own fixed-order reduction of the weight-gradient partials
+        return backward_box(st, d, input, weight, offset, mask, grad_output, grad_input, grad_offset, grad_mask,
+                            grad_weight, grad_bias, gw_part, gb_part, scratch);
+    } else if (S_tc > 0) {
         // tensor-core path (dcn_bwd_tc.cu): cpg == 8, Cout == 64
         if (int rc = backward_tc(st, d, input, weight, offset, mask, grad_output, grad_input, grad_offset, grad_mask,
                                  gw_part, gb_part, S, scratch))

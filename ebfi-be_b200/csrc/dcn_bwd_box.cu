@@ -1,0 +1,812 @@
+// dcn_bwd_box.cu — DCNv2 backward from TMA-staged boxes: shared-memory gather, shared-memory (integer) scatter, both weight
+// contractions on the sm_100a tensor cores, grad_input without global atomics for every sample inside the box.
+//
+// One persistent CTA per SM. CTA (s, h) owns the deformable groups [h*GPC, h*GPC + GPC) and walks the 8 x 16-pixel output
+// tiles s, s+S, ...; an "iteration" is one (tile, group). Per tile the grad_output tile is staged ONCE, as bf16 hi/lo pairs
+// in the layout Q[co][px]. The same bytes serve both contractions because kind::f16 accepts MN-major operands in the
+// no-swizzle core-matrix layout (probed: tests/test_tcgen05_gpu.py):
+//   GEMM1  colgrad[128 px x 72] = gO_tile . W_g        A = Q read MN-major (M = px, K = co), B = W_g^T image (bulk copy)
+//   GEMM3  gW_g[co x 72]      += gO_tile^T . col       A = [Q_hi ; Q_lo] stacked to M = 128 (K = px), B = col read MN-major
+// so the second grad_output copy of dcn_bwd_tc.cu is gone, a thread writes its 8 column values as ONE 16-byte chunk, and
+// two MMAs per K step yield all four hi/lo products (rows 0-63 and 64-127 of the accumulator are two partial sums).
+// GEMM3 accumulates in TMEM over all tiles of the CTA; an all-ones column gives grad_bias.
+// Per iteration (384 threads, thread = (pixel, tap row)):
+//   * input: a 24 x 30-pixel box of the group-blocked input arrives by one 3-D TMA copy (zeros outside the image = the
+//     reference's per-corner bounds tests, im2col_cuda.cu:38-48); the four corners of a sample are read with eight
+//     conflict-free LDS.128 in the rotated order of dcn_box.cuh. Offsets and masks of the tile arrive by two more copies.
+//     Everything is issued two iterations ahead.
+//   * grad_mask / grad_offset: one owner thread per element, no atomics (im2col_cuda.cu:280-330).
+//   * grad_input (im2col_cuda.cu:197-254): contributions are accumulated in a shared-memory box of the same geometry as
+//     32-bit FIXED POINT (native ATOMS.ADD; a float shared atomic is a CAS loop), with a power-of-two scale chosen per
+//     (tile, group) in a first pass over the samples: M = max |colgrad * mask| and W = the largest sum of bilinear
+//     weights any box cell receives (4 integer atomics per sample) bound every element by M * W, so scale = 2^30 / (M * W)
+//     cannot overflow and resolves a contribution to ~2^-26 of M (W is ~10). Integer addition is associative, so the box
+//     is bit-reproducible.
+//     The box is written — converted back to fp32 — as a dense partial to global memory with plain coalesced stores;
+//     dcn_gin_collect then sums, per input pixel, the <= 9 boxes that cover it in a fixed order and writes NCHW. No global
+//     atomics, no order dependence: grad_input is bit-identical run to run, by default.
+//   * samples whose corners leave the box (|offset| beyond ~7 pixels) fall back to 256-bit global loads and
+//     red.global.add.v4.f32 into a blocked fp32 buffer that dcn_gin_collect adds last (order-dependent only then, like
+//     the reference's atomicAdd, im2col_cuda.cu:249).
+// Non-finite gradients: a NaN/Inf anywhere in the (tile, group) makes the scale undefined; the box is then written as NaN
+// so that overflow checks on grad_input (AMP GradScaler) still fire.
+#include "dcn_box.cuh"
+#include "dcn_common.cuh"
+#include "tma.cuh"
+#include "umma.cuh"
+
+#include <algorithm>
+
+namespace ebfi_dcn {
+
+namespace {
+
+using ebfi::ceil_div;
+
+constexpr int TM = 128, TH = 8, TW = 16, NR = 3, NTHR = TM * NR;
+constexpr int CS = 8, CO = 64;                  // channels per group, output channels handled by this kernel
+constexpr int GPC_MAX = 4;                      // deformable groups per CTA (TMEM: 2 * N1 + GPC * N3 <= 512 columns)
+constexpr int TMEM_COLS = 512;
+constexpr int Q_PART = CO * TM * 2;             // one bf16 image of the grad_output tile
+constexpr int BOX_F = box::BYTES / 4;           // floats per box
+constexpr int CNT_BYTES = box::BH * box::BW * 4; // per-cell sums of bilinear weights (16.16 fixed point)
+
+struct BoxBwdPlan {
+    int TPR;             // taps per thread row
+    int Kc;              // CS * KK
+    int N1, N3;          // GEMM1 / GEMM3 N (multiples of 16)
+    int GPC, NH;         // groups per CTA, CTA rows
+    int tiles_x, tiles_y, ntiles;
+    int my, mx;          // box margins above / left of the tile's undeformed footprint
+    int wt_bytes;        // one group's W^T image, hi | lo
+    int col_part;        // one bf16 image of the column operand
+    int om_bytes, use_om_tma;
+    int off_q, off_col, off_box, off_acc, off_cnt, off_om, smem;
+};
+
+__device__ __forceinline__ void st_bf16x8(unsigned char *base, int off, const unsigned short (&v)[8])
+{
+    const uint32_t a = v[0] | ((uint32_t)v[1] << 16), b = v[2] | ((uint32_t)v[3] << 16);
+    const uint32_t c = v[4] | ((uint32_t)v[5] << 16), e = v[6] | ((uint32_t)v[7] << 16);
+    *reinterpret_cast<uint4 *>(base + off) = make_uint4(a, b, c, e);
+}
+
+__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float e)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(e) : "memory");
+}
+
+__device__ __forceinline__ void atoms_add(uint32_t saddr, int v)
+{
+    asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+
+// Where a sample lands in a box whose first cell is image pixel (by0, bx0).
+struct Geo {
+    bool inside;         // the sampling window of the reference (im2col_cuda.cu:180, :304); NaN coordinates fail it like they do there
+    bool inbox;          // all four corners are cells of the box
+    int yb, xb;          // box cell of corner (y0, x0)
+    float hy, hx, ly, lx;
+};
+__device__ __forceinline__ Geo make_geo(float y, float x, int H, int W, int by0, int bx0)
+{
+    Geo q;
+    q.inside = y > -1.f && x > -1.f && y < (float)H && x < (float)W;
+    const float fy = floorf(y), fx = floorf(x);
+    q.ly = y - fy; q.lx = x - fx; q.hy = 1.f - q.ly; q.hx = 1.f - q.lx;
+    q.yb = (int)fy - by0; q.xb = (int)fx - bx0;
+    q.inbox = q.inside && (unsigned)q.yb <= (unsigned)(box::BH - 2) && (unsigned)q.xb <= (unsigned)(box::BW - 2);
+    return q;
+}
+
+// v'[j] = v[(j + k) & 3], k in 0..3, without dynamic register indexing
+__device__ __forceinline__ void rot4(float (&v)[4], uint32_t k)
+{
+    if (k & 1u) { const float t = v[0]; v[0] = v[1]; v[1] = v[2]; v[2] = v[3]; v[3] = t; }
+    if (k & 2u) { float t = v[0]; v[0] = v[2]; v[2] = t; t = v[1]; v[1] = v[3]; v[3] = t; }
+}
+
+// One sample (pixel, tap) of the backward: gather the four corners, grad_mask / grad_offset, the grad_input scatter and
+// the recomputed column values (natural channel order). `gc` = colgrad of the tap's 8 channels.
+struct SampleCtx {
+    int ho, wo, by0, bx0, bxq0;
+    uint32_t box_s, acc_s;
+    const float *ib;     // blocked input plane of (sample, group): far-sample gathers
+    float *gb;           // blocked far-sample accumulator of (sample, group)
+    float scale;
+};
+template <bool PACKED>
+__device__ __forceinline__ void sample_bwd(const DcnDims &d, const SampleCtx &sc, const float (&gc)[8], float dy, float dx, float m,
+                                           int ti, int tj, int lane, uint32_t wrot, float (&colv)[8], float &g_y, float &g_x, float &g_m)
+{
+    const int ho = sc.ho, wo = sc.wo, by0 = sc.by0, bx0 = sc.bx0, bxq0 = sc.bxq0;
+    const uint32_t box_s = sc.box_s, acc_s = sc.acc_s;
+    const float *ib = sc.ib;
+    float *gb = sc.gb;
+    const float scale = sc.scale;
+    m = mask_act_t<PACKED>(m);
+    const float y = (float)(ho * d.sh - d.ph + ti * d.dh) + dy;
+    const float x = (float)(wo * d.sw - d.pw + tj * d.dw) + dx;
+    const Geo ge = make_geo(y, x, d.H, d.W, by0, bx0);
+    const bool inside = ge.inside, inbox = ge.inbox;
+    const float hy = ge.hy, hx = ge.hx, ly = ge.ly, lx = ge.lx;
+    const int yb = ge.yb, xb = ge.xb;
+    // A / B = the two 4-channel halves; in-box they are channels 0-3 / 4-7 unless `odd`, then swapped
+    float va[4], vb[4], ya[4], yb4[4], xa[4], xb4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) va[j] = vb[j] = ya[j] = yb4[j] = xa[j] = xb4[j] = 0.f;
+    bool odd = false;
+    box::Rot rt{};
+    if (inbox) {
+        rt = box::make_rot(box_s, yb, xb, lane);
+        odd = rt.odd;
+        float wv[5], wyv[5], wxv[5];
+        box::rot_corners(rt.c0, hy * hx, hy * lx, ly * hx, ly * lx, wv);       // bilinear weights
+        box::rot_corners(rt.c0, -hx, -lx, hx, lx, wyv);                         // d/dy (im2col_cuda.cu:99-120)
+        box::rot_corners(rt.c0, -hy, hy, -ly, ly, wxv);                         // d/dx
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 q = box::lds128(box::step_addr(rt, i));
+            const float cw = box::step_coef(wv, odd, i), cy = box::step_coef(wyv, odd, i), cx = box::step_coef(wxv, odd, i);
+            float *v = (i & 1) ? vb : va, *yy = (i & 1) ? yb4 : ya, *xx = (i & 1) ? xb4 : xa;
+            v[0] += cw * q.x; v[1] += cw * q.y; v[2] += cw * q.z; v[3] += cw * q.w;
+            yy[0] += cy * q.x; yy[1] += cy * q.y; yy[2] += cy * q.z; yy[3] += cy * q.w;
+            xx[0] += cx * q.x; xx[1] += cx * q.y; xx[2] += cx * q.z; xx[3] += cx * q.w;
+        }
+    } else if (inside) {
+        const Tap tp = make_tap(y, x, d.H, d.W);
+        const f8 a1 = ldg_f8(ib + (size_t)tp.i00 * CS, tp.c00), a2 = ldg_f8(ib + (size_t)tp.i01 * CS, tp.c01);
+        const f8 a3 = ldg_f8(ib + (size_t)tp.i10 * CS, tp.c10), a4 = ldg_f8(ib + (size_t)tp.i11 * CS, tp.c11);
+        const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            va[j] = w1 * a1.v[j] + w2 * a2.v[j] + w3 * a3.v[j] + w4 * a4.v[j];
+            vb[j] = w1 * a1.v[4 + j] + w2 * a2.v[4 + j] + w3 * a3.v[4 + j] + w4 * a4.v[4 + j];
+            ya[j] = -hx * a1.v[j] - lx * a2.v[j] + hx * a3.v[j] + lx * a4.v[j];
+            yb4[j] = -hx * a1.v[4 + j] - lx * a2.v[4 + j] + hx * a3.v[4 + j] + lx * a4.v[4 + j];
+            xa[j] = -hy * a1.v[j] + hy * a2.v[j] - ly * a3.v[j] + ly * a4.v[j];
+            xb4[j] = -hy * a1.v[4 + j] + hy * a2.v[4 + j] - ly * a3.v[4 + j] + ly * a4.v[4 + j];
+        }
+    }
+    float s_m = 0.f, s_y = 0.f, s_x = 0.f;
+    float ta[4], tb[4];                  // colgrad * mask of the A / B halves
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float ga = odd ? gc[4 + j] : gc[j], gb4 = odd ? gc[j] : gc[4 + j];
+        s_m += ga * va[j] + gb4 * vb[j];                      // grad_mask (im2col_cuda.cu:311)
+        ta[j] = ga * m; tb[j] = gb4 * m;
+        s_y += ya[j] * ta[j] + yb4[j] * tb[j];                // grad_offset
+        s_x += xa[j] * ta[j] + xb4[j] * tb[j];
+        colv[j] = (odd ? vb[j] : va[j]) * m;                  // recomputed column, natural channel order
+        colv[4 + j] = (odd ? va[j] : vb[j]) * m;
+    }
+    g_y = s_y; g_x = s_x; g_m = s_m * mask_act_grad_t<PACKED>(m);
+    // ---- grad_input (im2col_cuda.cu:236-251); the scatter's x uses pad_h (:368)
+    bool q_inside = inside, q_inbox = inbox, q_odd = odd;
+    float qhx = hx, qlx = lx;
+    float xs = x;
+    box::Rot rq = rt;
+    rq.base += acc_s - box_s;            // same cell of the accumulation box (both bases are 128-byte aligned)
+    if (d.ph != d.pw) {
+        xs = (float)(wo * d.sw - d.ph + tj * d.dw) + dx;
+        const Geo gq = make_geo(y, xs, d.H, d.W, by0, bxq0);
+        q_inside = gq.inside; q_inbox = gq.inbox;
+        qlx = gq.lx; qhx = gq.hx;
+        if (q_inbox) rq = box::make_rot(acc_s, gq.yb, gq.xb, lane);
+        q_odd = rq.odd;
+    }
+    if (q_inbox) {
+        if (q_odd != odd) {              // only when pad_h != pad_w moved the sample to a cell of the other parity
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const float tsw = ta[j]; ta[j] = tb[j]; tb[j] = tsw; }
+        }
+        // word rotation by the quarter-warp index on top of the chunk rotation: 32 lanes on 32 banks
+        rot4(ta, wrot); rot4(tb, wrot);
+        float qv[5];
+        box::rot_corners(rq.c0, hy * qhx * scale, hy * qlx * scale, ly * qhx * scale, ly * qlx * scale, qv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t a = box::step_addr(rq, i);
+            const float cf = box::step_coef(qv, q_odd, i);
+            const float *tt = (i & 1) ? tb : ta;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                atoms_add(a + ((((uint32_t)j + wrot) & 3u) << 2), __float2int_rn(cf * tt[j]));
+        }
+    } else if (q_inside) {
+        const Tap tq = make_tap(y, xs, d.H, d.W);
+        const float q1 = tq.hy * tq.hx, q2 = tq.hy * tq.lx, q3 = tq.ly * tq.hx, q4 = tq.ly * tq.lx;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const float *tt = (hf == (odd ? 1 : 0)) ? ta : tb;      // natural half hf
+            if (tq.c00) red_add_v4(gb + (size_t)tq.i00 * CS + 4 * hf, q1 * tt[0], q1 * tt[1], q1 * tt[2], q1 * tt[3]);
+            if (tq.c01) red_add_v4(gb + (size_t)tq.i01 * CS + 4 * hf, q2 * tt[0], q2 * tt[1], q2 * tt[2], q2 * tt[3]);
+            if (tq.c10) red_add_v4(gb + (size_t)tq.i10 * CS + 4 * hf, q3 * tt[0], q3 * tt[1], q3 * tt[2], q3 * tt[3]);
+            if (tq.c11) red_add_v4(gb + (size_t)tq.i11 * CS + 4 * hf, q4 * tt[0], q4 * tt[1], q4 * tt[2], q4 * tt[3]);
+        }
+    }
+}
+
+template <bool PACKED>
+__global__ void __launch_bounds__(NTHR, 1)
+dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__restrict__ wimg,
+                   const float *__restrict__ offset, const float *__restrict__ mask,
+                   const float *__restrict__ gout, float *__restrict__ gin_blk, float *__restrict__ pbox,
+                   float *__restrict__ goff, float *__restrict__ gmask,
+                   float *__restrict__ gw_part, float *__restrict__ gb_part, DcnDims d, BoxBwdPlan pl,
+                   const __grid_constant__ CUtensorMap tm_box, const __grid_constant__ CUtensorMap tm_off,
+                   const __grid_constant__ CUtensorMap tm_mask)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char *wring = smem;                                     // [2][hi | lo][N1 rows k'][CO], K-major
+    unsigned char *q_hi = smem + pl.off_q, *q_lo = q_hi + Q_PART;    // [co][px] bf16: K-major for GEMM3, MN-major for GEMM1
+    unsigned char *c_hi = smem + pl.off_col, *c_lo = c_hi + pl.col_part;   // [tap][px][8 ch] bf16: MN-major B of GEMM3
+    unsigned char *boxes = smem + pl.off_box;                        // [2][BH][BW][8] fp32 input boxes
+    int4 *acc4 = reinterpret_cast<int4 *>(smem + pl.off_acc);        // [BH][BW][8] fixed-point grad_input box
+    int *cnt = reinterpret_cast<int *>(smem + pl.off_cnt);           // [BH][BW] weight sums of the iteration in pass 1
+    const float *oms = reinterpret_cast<const float *>(smem + pl.off_om);   // [2][3*KK planes][128 px]
+    __shared__ __align__(8) uint64_t bar_w[2], bar_in[2], bar_d1[2], bar_g3;
+    __shared__ uint32_t tmem_slot;
+    __shared__ unsigned tile_max[2];
+    __shared__ int w_max[2];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int p = tid % TM, r = tid / TM;
+    const int S = gridDim.x, s = blockIdx.x;
+    const int g_begin = blockIdx.y * pl.GPC, ng = min(pl.GPC, d.dg - g_begin);
+    const int total_tiles = d.B * pl.ntiles;
+    const int NI = ((total_tiles - s + S - 1) / S) * ng;             // iterations (tile, group) of this CTA
+    const int npix = d.Ho * d.Wo, Kdim = d.C * d.KK;
+    const size_t plane = (size_t)npix, in_plane = (size_t)d.H * d.W;
+    const unsigned uplane = (unsigned)plane;
+    const bool use_tma = pl.use_om_tma != 0;
+    const int t_first = r * pl.TPR, ti_first = t_first / d.kw, tj_first = t_first - ti_first * d.kw;
+
+    if (warp == 0) umma::tmem_alloc<TMEM_COLS>(&tmem_slot);
+    if (tid == 32) {
+        for (int i = 0; i < 2; ++i) { umma::mbar_init(&bar_w[i], 1); umma::mbar_init(&bar_in[i], 1); umma::mbar_init(&bar_d1[i], 1); }
+        umma::mbar_init(&bar_g3, 1);
+        umma::mbar_fence_init();
+        tile_max[0] = tile_max[1] = 0u;
+        w_max[0] = w_max[1] = 0;
+    }
+    for (int c = tid; c < BOX_F / 4; c += NTHR) acc4[c] = make_int4(0, 0, 0, 0);
+    for (int c = tid; c < box::BH * box::BW; c += NTHR) cnt[c] = 0;
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t lane_base = (uint32_t)(warp & 3) * 32u;
+    const uint32_t idesc1 = umma::instr_desc_bf16(TM, pl.N1) | (1u << 15);     // A MN-major
+    const uint32_t idesc3 = umma::instr_desc_bf16(TM, pl.N3) | (1u << 16);     // B MN-major
+    const uint32_t q_s = umma::smem_u32(q_hi), c_s = umma::smem_u32(c_hi), w_s = umma::smem_u32(wring);
+    const uint32_t acc_s = umma::smem_u32(acc4), cnt_s = umma::smem_u32(cnt);
+    const uint32_t wrot = (uint32_t)lane >> 3;
+
+    // iteration n of this CTA = (tile s + (n / ng) * S, group g_begin + n % ng)
+    struct Iter { int n, b, ty0, tx0, g, gi, tl, ho, wo, pix; bool valid; };
+    auto decode = [&](int n) {
+        Iter it;
+        it.n = n;
+        const int k = n / ng;
+        it.gi = n - k * ng;
+        it.g = g_begin + it.gi;
+        const int tile = s + k * S;
+        it.b = tile / pl.ntiles;
+        it.tl = tile - it.b * pl.ntiles;
+        it.ty0 = (it.tl / pl.tiles_x) * TH;
+        it.tx0 = (it.tl % pl.tiles_x) * TW;
+        it.ho = it.ty0 + p / TW; it.wo = it.tx0 + p % TW;
+        it.valid = it.ho < d.Ho && it.wo < d.Wo;
+        it.pix = it.ho * d.Wo + it.wo;
+        return it;
+    };
+    // ---- single-thread issue helpers (tid 0)
+    auto issue_in = [&](int n) {                    // input box + offsets / masks of iteration n
+        const Iter it = decode(n);
+        const int bb = n & 1;
+        umma::mbar_expect_tx(&bar_in[bb], (uint32_t)(box::BYTES + (use_tma ? pl.om_bytes : 0)));
+        tma::load_3d(boxes + bb * box::BYTES, &tm_box, (it.tx0 * d.sw - d.pw - pl.mx) * 8, it.ty0 * d.sh - d.ph - pl.my, it.b * d.dg + it.g, &bar_in[bb]);
+        if (use_tma) {
+            unsigned char *dst = smem + pl.off_om + bb * pl.om_bytes;
+            tma::load_3d(dst, &tm_off, it.tx0, it.ty0, it.b * d.off_bp + it.g * 2 * d.KK, &bar_in[bb]);
+            tma::load_3d(dst + 2 * d.KK * TM * 4, &tm_mask, it.tx0, it.ty0, it.b * d.mask_bp + it.g * d.KK, &bar_in[bb]);
+        }
+    };
+    auto issue_w = [&](int n) {                     // W^T image of iteration n's group
+        const int g = g_begin + n % ng;
+        umma::mbar_expect_tx(&bar_w[n & 1], (uint32_t)pl.wt_bytes);
+        umma::bulk_g2s(wring + (n & 1) * pl.wt_bytes, wimg + (size_t)g * pl.wt_bytes, (uint32_t)pl.wt_bytes, &bar_w[n & 1]);
+    };
+    auto issue_gemm1 = [&](int n) {                 // D1[n & 1][px][k'] = Q^T . W^T   (K = co)
+        umma::mbar_wait(&bar_w[n & 1], (uint32_t)((n >> 1) & 1));
+        const uint32_t d1 = tmem + (uint32_t)((n & 1) * pl.N1);
+        const uint32_t wb = w_s + (uint32_t)((n & 1) * pl.wt_bytes), wlo = (uint32_t)(pl.N1 * CO * 2);
+        for (int ks = 0; ks < CO / 16; ++ks) {
+            // A: 16-byte chunks run along px (SBO 128 between chunks), 8-co groups 2048 B apart (LBO)
+            const uint64_t ah = umma::smem_desc(q_s + ks * 4096u, 2048, 128), al = umma::smem_desc(q_s + Q_PART + ks * 4096u, 2048, 128);
+            const uint64_t bh = umma::smem_desc(wb + ks * 256u, 128, (CO / 8) * 128), bl = umma::smem_desc(wb + wlo + ks * 256u, 128, (CO / 8) * 128);
+            umma::mma_f16(d1, al, bh, idesc1, ks > 0);
+            umma::mma_f16(d1, ah, bl, idesc1, true);
+            umma::mma_f16(d1, ah, bh, idesc1, true);
+        }
+        umma::commit(&bar_d1[n & 1]);
+    };
+    auto issue_gemm3 = [&](int gi, bool accumulate) {   // D3[gi][hi rows | lo rows][k'] += [Q_hi ; Q_lo] . col^T   (K = px)
+        const uint32_t d3 = tmem + (uint32_t)(2 * pl.N1 + gi * pl.N3);
+        for (int ks = 0; ks < TM / 16; ++ks) {
+            const uint64_t a = umma::smem_desc(q_s + ks * 256u, 128, (TM / 8) * 128);
+            // B: 16-byte chunks run along k' (one tap = one chunk, SBO 2048 between taps), 8-px groups 128 B apart (LBO)
+            const uint64_t bh = umma::smem_desc(c_s + ks * 256u, 128, TM * 16), bl = umma::smem_desc(c_s + pl.col_part + ks * 256u, 128, TM * 16);
+            umma::mma_f16(d3, a, bh, idesc3, accumulate || ks > 0);
+            umma::mma_f16(d3, a, bl, idesc3, true);
+        }
+        umma::commit(&bar_g3);
+    };
+
+    uint32_t ph_g3 = 0;
+    // ================= new tile: grad_output -> Q (bf16 hi / lo), once for all groups of the CTA =================
+    // item = (co, chunk of 8 consecutive tile pixels); lanes run over co % 8 first -> conflict-free 16-byte stores.
+    // All loads of a thread are issued before the wait for the previous tile's last GEMM3 (which still reads Q and col).
+    constexpr int QI = (CO * (TM / 8) + NTHR - 1) / NTHR;
+    auto tile_start = [&](const Iter &it, bool wait_g3) {
+        const float *go_b = gout + (size_t)it.b * d.Co * plane;
+        float4 va[QI], vb[QI];
+        const bool vec = (d.Wo & 3) == 0;
+#pragma unroll
+        for (int q = 0; q < QI; ++q) {
+            const int item = tid + q * NTHR;
+            va[q] = vb[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (item < CO * (TM / 8)) {
+                const int j = item & 7, pc = (item >> 3) & (TM / 8 - 1), co = (item >> 7) * 8 + j;
+                const int hh = it.ty0 + (pc * 8) / TW, ww = it.tx0 + (pc * 8) % TW;
+                const float *src = go_b + (size_t)co * plane + (size_t)hh * d.Wo + ww;
+                if (vec && hh < d.Ho && ww + 7 < d.Wo) {
+                    va[q] = __ldg(reinterpret_cast<const float4 *>(src));
+                    vb[q] = __ldg(reinterpret_cast<const float4 *>(src) + 1);
+                } else if (hh < d.Ho) {
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = (ww + i < d.Wo) ? __ldg(src + i) : 0.f;
+                    va[q] = make_float4(v[0], v[1], v[2], v[3]); vb[q] = make_float4(v[4], v[5], v[6], v[7]);
+                }
+            }
+        }
+        if (wait_g3) {
+            umma::mbar_wait(&bar_g3, ph_g3);
+            ph_g3 ^= 1u;
+        }
+#pragma unroll
+        for (int q = 0; q < QI; ++q) {
+            const int item = tid + q * NTHR;
+            if (item < CO * (TM / 8)) {
+                const int j = item & 7, pc = (item >> 3) & (TM / 8 - 1), co = (item >> 7) * 8 + j;
+                const float v[8] = {va[q].x, va[q].y, va[q].z, va[q].w, vb[q].x, vb[q].y, vb[q].z, vb[q].w};
+                unsigned short hi[8], lo[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) umma::split_bf16(v[i], hi[i], lo[i]);
+                const int off = (co >> 3) * ((TM / 8) * 128) + pc * 128 + j * 16;
+                st_bf16x8(q_hi, off, hi); st_bf16x8(q_lo, off, lo);
+            }
+        }
+        // column chunks past the taps: the ones column (grad_bias) and zero padding up to N3
+        for (int c = tid; c < (pl.N3 / 8 - d.KK) * TM; c += NTHR) {
+            const int pp = c % TM, ch = d.KK + c / TM;
+            const bool one = ch == d.KK && (it.ty0 + pp / TW) < d.Ho && (it.tx0 + pp % TW) < d.Wo;
+            *reinterpret_cast<uint4 *>(c_hi + ch * (TM * 16) + pp * 16) = make_uint4(one ? 0x3F80u : 0u, 0u, 0u, 0u);   // bf16(1.0)
+            *reinterpret_cast<uint4 *>(c_lo + ch * (TM * 16) + pp * 16) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        umma::fence_smem_to_async();
+        __syncthreads();
+        if (tid == 0) {
+            umma::fence_after_sync();
+            issue_gemm1(it.n);
+            if (ng > 1) issue_gemm1(it.n + 1);
+        }
+        // the next tile's grad_output -> L2, so that its staging pays an L2 hit instead of a DRAM miss
+        const int ntile = s + (it.n / ng + 1) * S;
+        if (ntile < total_tiles) {
+            const int nb = ntile / pl.ntiles, ntl = ntile - nb * pl.ntiles;
+            const int nty0 = (ntl / pl.tiles_x) * TH, ntx0 = (ntl % pl.tiles_x) * TW;
+            for (int c = tid; c < CO * TH; c += NTHR) {
+                const int co = c / TH, hh = nty0 + c % TH;
+                if (hh < d.Ho)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(gout + ((size_t)nb * d.Co + co) * plane + (size_t)hh * d.Wo + ntx0));
+            }
+        }
+    };
+    // ================= pass 1 of an iteration: M = max |colgrad * mask| (unsigned order of the float bits: NaN > Inf > finite,
+    // so a non-finite value anywhere is seen) and the per-cell sums of the scatter's bilinear weights (rounded up, 16.16) ======
+    auto pass1 = [&](const Iter &it) {
+        const int bb = it.n & 1;
+        const uint32_t par = (uint32_t)((it.n >> 1) & 1);
+        umma::mbar_wait(&bar_d1[bb], par);           // colgrad of this group is in TMEM
+        umma::fence_after_sync();
+        if (tid == 0 && it.n + 2 < NI) issue_w(it.n + 2);    // GEMM1(n) is complete: its weight slot is free
+        umma::mbar_wait(&bar_in[bb], par);           // box + offsets / masks have landed
+        const float *om = oms + bb * (pl.om_bytes / 4);
+        const float *off_g = offset + (size_t)it.b * d.off_bs + (size_t)it.g * 2 * d.KK * plane;
+        const float *mask_g = mask + (size_t)it.b * d.mask_bs + (size_t)it.g * d.KK * plane;
+        const uint32_t d1 = tmem + (uint32_t)(bb * pl.N1);
+        const int by0 = it.ty0 * d.sh - d.ph - pl.my, bxq0 = it.tx0 * d.sw - d.ph - pl.mx;
+        unsigned um = 0u;
+        int t = t_first, ti = ti_first, tj = tj_first;
+        for (int sidx = 0; sidx < pl.TPR && t < d.KK; ++sidx, ++t) {
+            float gc[8];
+            umma::tmem_ld8(umma::tmem_addr(d1, lane_base, t * 8), gc);
+            umma::tmem_ld_wait();
+            if (it.valid) {
+                float dy, dx, m;
+                if (use_tma) {
+                    dy = om[(2 * t) * TM + p];
+                    dx = om[(2 * t + 1) * TM + p];
+                    m = om[(2 * d.KK + t) * TM + p];
+                } else {
+                    tap_read(off_g, mask_g, uplane, (unsigned)t, (unsigned)it.pix, dy, dx, m);
+                }
+                m = mask_act_t<PACKED>(m);
+#pragma unroll
+                for (int cc = 0; cc < CS; ++cc) um = max(um, __float_as_uint(fabsf(gc[cc] * m)));
+                // the scatter's x uses pad_h (im2col_cuda.cu:368)
+                const Geo q = make_geo((float)(it.ho * d.sh - d.ph + ti * d.dh) + dy, (float)(it.wo * d.sw - d.ph + tj * d.dw) + dx,
+                                       d.H, d.W, by0, bxq0);
+                if (q.inbox) {
+                    const uint32_t a = cnt_s + (uint32_t)(q.yb * box::BW + q.xb) * 4u;
+                    atoms_add(a, __float2int_ru(q.hy * q.hx * 65536.f));
+                    atoms_add(a + 4u, __float2int_ru(q.hy * q.lx * 65536.f));
+                    atoms_add(a + box::BW * 4u, __float2int_ru(q.ly * q.hx * 65536.f));
+                    atoms_add(a + box::BW * 4u + 4u, __float2int_ru(q.ly * q.lx * 65536.f));
+                }
+            }
+            if (++tj == d.kw) { tj = 0; ++ti; }
+        }
+        um = __reduce_max_sync(0xffffffffu, um);
+        if (lane == 0 && um) atomicMax(&tile_max[bb], um);
+    };
+    // max over the cells of the weight sums pass 1 left in `cnt` (cleared for the next pass 1)
+    auto cell_max = [&](int bb) {
+        int wm = 0;
+        for (int c = tid; c < box::BH * box::BW; c += NTHR) { wm = max(wm, cnt[c]); cnt[c] = 0; }
+        wm = __reduce_max_sync(0xffffffffu, wm);
+        if (lane == 0 && wm) atomicMax(&w_max[bb], wm);
+    };
+
+    if (tid == 0) {
+        issue_w(0); issue_in(0);
+        if (NI > 1) { issue_w(1); issue_in(1); }
+    }
+    Iter cur = decode(0);
+    if (NI > 0) {
+        tile_start(cur, false);
+        pass1(cur);
+        __syncthreads();
+        cell_max(0);
+        __syncthreads();
+    }
+    for (int n = 0; n < NI; ++n) {
+        const int bb = n & 1;
+        const Iter nxt = decode(n + 1 < NI ? n + 1 : n);
+        const bool has_next = n + 1 < NI, next_same_tile = has_next && nxt.gi != 0;
+        // ---- fixed-point scale of this (tile, group): every element |sum| <= M * W * scale (+ one rounding per
+        //      contribution) <= 2^30 (+ 128 * taps)
+        const unsigned tmax = tile_max[bb];
+        const bool nonfinite = tmax >= 0x7F800000u;
+        int e2 = 0;
+        if (tmax && !nonfinite) frexpf(__uint_as_float(tmax), &e2);      // M < 2^e2
+        const int wbits = 32 - __clz(max(w_max[bb], 65536));             // W < 2^(wbits - 16), at least 1
+        const int k2 = max(-100, min(100, 46 - wbits - e2));
+        const float inv_scale = ldexpf(1.f, -k2);
+        if (cur.gi != 0) {                               // col is still read by GEMM3 of the previous iteration
+            umma::mbar_wait(&bar_g3, ph_g3);
+            ph_g3 ^= 1u;
+        }
+        // ================= pass 2: the samples =================
+        {
+            SampleCtx sc;
+            sc.ho = cur.ho; sc.wo = cur.wo;
+            sc.by0 = cur.ty0 * d.sh - d.ph - pl.my; sc.bx0 = cur.tx0 * d.sw - d.pw - pl.mx; sc.bxq0 = cur.tx0 * d.sw - d.ph - pl.mx;
+            sc.box_s = umma::smem_u32(boxes + bb * box::BYTES); sc.acc_s = acc_s;
+            sc.ib = in_blk + ((size_t)cur.b * d.dg + cur.g) * in_plane * CS;
+            sc.gb = gin_blk + ((size_t)cur.b * d.dg + cur.g) * in_plane * CS;
+            sc.scale = ldexpf(1.f, k2);
+            const float *om = oms + bb * (pl.om_bytes / 4);
+            const float *off_g = offset + (size_t)cur.b * d.off_bs + (size_t)cur.g * 2 * d.KK * plane;
+            const float *mask_g = mask + (size_t)cur.b * d.mask_bs + (size_t)cur.g * d.KK * plane;
+            float *goff_g = goff + (size_t)cur.b * d.off_bs + (size_t)cur.g * 2 * d.KK * plane;
+            float *gmask_g = gmask + (size_t)cur.b * d.mask_bs + (size_t)cur.g * d.KK * plane;
+            const uint32_t d1 = tmem + (uint32_t)(bb * pl.N1);
+            int t = t_first, ti = ti_first, tj = tj_first;
+#pragma unroll 1
+            for (int sidx = 0; sidx < pl.TPR && t < d.KK; ++sidx, ++t) {
+                float gc[8];
+                umma::tmem_ld8(umma::tmem_addr(d1, lane_base, t * 8), gc);     // colgrad[p][t*8 .. t*8+7]
+                umma::tmem_ld_wait();
+                float colv[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) colv[j] = 0.f;
+                if (cur.valid) {
+                    float dy, dx, m;
+                    if (use_tma) {
+                        dy = om[(2 * t) * TM + p];
+                        dx = om[(2 * t + 1) * TM + p];
+                        m = om[(2 * d.KK + t) * TM + p];
+                    } else {
+                        tap_read(off_g, mask_g, uplane, (unsigned)t, (unsigned)cur.pix, dy, dx, m);
+                    }
+                    float g_y, g_x, g_m;
+                    sample_bwd<PACKED>(d, sc, gc, dy, dx, m, ti, tj, lane, wrot, colv, g_y, g_x, g_m);
+                    float *gy = goff_g + (2u * (unsigned)t * uplane + (unsigned)cur.pix);
+                    gy[0] = g_y; gy[uplane] = g_x;
+                    gmask_g[(unsigned)t * uplane + (unsigned)cur.pix] = g_m;
+                }
+                // column operand: the 8 channels of (tap t, pixel p) are one 16-byte chunk
+                unsigned short hi[8], lo[8];
+#pragma unroll
+                for (int cc = 0; cc < CS; ++cc) umma::split_bf16(colv[cc], hi[cc], lo[cc]);
+                st_bf16x8(c_hi, t * (TM * 16) + p * 16, hi);
+                st_bf16x8(c_lo, t * (TM * 16) + p * 16, lo);
+                if (++tj == d.kw) { tj = 0; ++ti; }
+            }
+        }
+        // pass 1 of the next group of the same tile rides in the same barrier interval (its colgrad was issued two
+        // iterations ago); a new tile needs its Q first
+        if (next_same_tile) pass1(nxt);
+        umma::fence_smem_to_async();
+        umma::fence_before_sync();                       // orders this thread's tcgen05.ld of D1 before the sync
+        __syncthreads();
+        if (tid == 0) {
+            umma::fence_after_sync();
+            issue_gemm3(cur.gi, n >= ng);                // the first tile of the CTA starts the accumulation
+            if (n + 2 < NI) {
+                issue_in(n + 2);                         // box / offset buffers of this iteration are free
+                if (cur.gi + 2 < ng) issue_gemm1(n + 2); // same tile: Q is already staged (else: issued at the tile start)
+            }
+            tile_max[bb] = 0u;
+            w_max[bb] = 0;
+        }
+        // ---- the accumulation box -> dense fp32 partial (plain coalesced stores), cleared for the next iteration
+        {
+            float4 *dst = reinterpret_cast<float4 *>(pbox + (((size_t)cur.b * pl.ntiles + cur.tl) * d.dg + cur.g) * BOX_F);
+            const float qnan = __uint_as_float(0x7FC00000u);
+            for (int c = tid; c < BOX_F / 4; c += NTHR) {
+                const int4 v = acc4[c];
+                acc4[c] = make_int4(0, 0, 0, 0);
+                dst[c] = nonfinite ? make_float4(qnan, qnan, qnan, qnan)
+                                   : make_float4((float)v.x * inv_scale, (float)v.y * inv_scale, (float)v.z * inv_scale, (float)v.w * inv_scale);
+            }
+        }
+        if (next_same_tile) {
+            cell_max(bb ^ 1);
+        } else if (has_next) {
+            tile_start(nxt, true);
+            pass1(nxt);
+            __syncthreads();
+            cell_max(bb ^ 1);
+        }
+        __syncthreads();
+        cur = nxt;
+    }
+    // ---- partials of this CTA, [slot][k = (c0 + cc) * KK + tap][co] so that a warp writes 128 contiguous bytes:
+    //      rows 0-63 of D3 (Q_hi products) -> slot 2s, rows 64-127 (Q_lo products) -> slot 2s+1
+    if (NI > 0) {
+        umma::mbar_wait(&bar_g3, ph_g3);
+        umma::fence_after_sync();
+    }
+    {
+        const int row = (int)lane_base + lane, half = row >> 6, co = row & 63;
+        const size_t slot = (size_t)2 * s + half;
+        for (int gi = 0; gi < ng; ++gi) {
+            const int c0 = (g_begin + gi) * d.cpg;
+            for (int cb = r * 8; cb < pl.N3; cb += NR * 8) {
+                float v[8];
+                if (NI > 0) {
+                    umma::tmem_ld8(umma::tmem_addr(tmem, lane_base, 2 * pl.N1 + gi * pl.N3 + cb), v);
+                    umma::tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int kp = cb + i;
+                    if (kp < pl.Kc)
+                        gw_part[(slot * Kdim + (size_t)(c0 + (kp & 7)) * d.KK + (kp >> 3)) * CO + co] = v[i];
+                    else if (kp == pl.Kc && g_begin + gi == 0)
+                        gb_part[slot * CO + co] = v[i];
+                }
+            }
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc<TMEM_COLS>(tmem);
+}
+
+// grad_weight[co][k] = sum over the slots of part[slot][k][co], grad_bias likewise: fixed order (four interleaved slot
+// quarters per element, combined in a fixed order), coalesced reads along co.
+__global__ void dcn_box_reduce_partials(const float *__restrict__ gw_part, const float *__restrict__ gb_part,
+                                        float *__restrict__ gw, float *__restrict__ gb, int nslot, int Kdim)
+{
+    const int e = blockIdx.x * (blockDim.x / 4) + (threadIdx.x >> 2), q = threadIdx.x & 3;
+    const int n_w = Kdim * CO;
+    float a = 0.f;
+    if (e < n_w) {
+        for (int sl = q; sl < nslot; sl += 4) a += gw_part[(size_t)sl * n_w + e];
+    } else if (e < n_w + CO) {
+        for (int sl = q; sl < nslot; sl += 4) a += gb_part[(size_t)sl * CO + (e - n_w)];
+    }
+    const float b1 = __shfl_xor_sync(0xffffffffu, a, 1);
+    a = (q & 1) ? b1 + a : a + b1;           // (q0 + q1), (q2 + q3): the same operand order in both lanes
+    const float b2 = __shfl_xor_sync(0xffffffffu, a, 2);
+    a = (q & 2) ? b2 + a : a + b2;
+    if (q == 0) {
+        if (e < n_w) gw[(size_t)(e % CO) * Kdim + e / CO] = a;
+        else if (e < n_w + CO) gb[e - n_w] = a;
+    }
+}
+
+// W^T images for the bulk copies: [group][hi | lo][N1 rows k'][CO] bf16 in the K-major core-matrix order,
+// k' = tap * 8 + cc  <-  weight[co][(g * 8 + cc) * KK + tap]; zero rows past Kc.
+__global__ void dcn_bwd_prep_weights(const float *__restrict__ weight, unsigned short *__restrict__ wimg, DcnDims d, BoxBwdPlan pl)
+{
+    const int per = pl.N1 * CO, Kdim = d.C * d.KK;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.dg * per; i += gridDim.x * blockDim.x) {
+        const int g = i / per, e = i - g * per;
+        const int j = e & 7, rr = (e >> 3) & 7, rest = e >> 6;
+        const int kc = rest % (CO / 8), rg = rest / (CO / 8);
+        const int kp = rg * 8 + rr, co = kc * 8 + j;
+        unsigned short hi = 0, lo = 0;
+        if (kp < pl.Kc)
+            umma::split_bf16(__ldg(weight + (size_t)co * Kdim + (size_t)(g * CS + (kp & 7)) * d.KK + (kp >> 3)), hi, lo);
+        wimg[(size_t)g * 2 * per + e] = hi;
+        wimg[(size_t)g * 2 * per + per + e] = lo;
+    }
+}
+
+// grad_input[b][g*8 + c][y][x] = sum, in a fixed order, over the boxes that cover (y, x) + the far-sample buffer.
+// One thread per (b, g, y, x): 32 contiguous bytes per box, coalesced along x; NCHW plane stores.
+__global__ void dcn_gin_collect(const float *__restrict__ pbox, const float *__restrict__ gin_blk, float *__restrict__ gin,
+                                DcnDims d, BoxBwdPlan pl)
+{
+    const int HW = d.H * d.W;
+    const size_t n = (size_t)d.B * d.dg * HW;
+    const int sy = TH * d.sh, sx = TW * d.sw;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t bg = i / HW;
+        const int px = (int)(i - bg * HW), b = (int)(bg / d.dg), g = (int)(bg - (size_t)b * d.dg);
+        const int y = px / d.W, x = px - y * d.W;
+        const float4 *fp = reinterpret_cast<const float4 *>(gin_blk + i * CS);
+        float4 a0 = __ldg(fp), a1 = __ldg(fp + 1);
+        // box of tile (ty, tx): rows [ty*sy - ph - my, +BH), pixels [tx*sx - ph - mx, +BW)   (pad_h for x too, :368)
+        const int ny = y + d.ph + pl.my, nx = x + d.ph + pl.mx;
+        const int ty_hi = min(pl.tiles_y - 1, ny / sy), tx_hi = min(pl.tiles_x - 1, nx / sx);
+        const int ty_lo = ny - (box::BH - 1) <= 0 ? 0 : (ny - (box::BH - 1) + sy - 1) / sy;
+        const int tx_lo = nx - (box::BW - 1) <= 0 ? 0 : (nx - (box::BW - 1) + sx - 1) / sx;
+        for (int ty = ty_lo; ty <= ty_hi; ++ty)
+            for (int tx = tx_lo; tx <= tx_hi; ++tx) {
+                const size_t bx = ((size_t)b * pl.ntiles + (size_t)ty * pl.tiles_x + tx) * d.dg + g;
+                const int cell = (ny - ty * sy) * box::BW + (nx - tx * sx);
+                const float4 *bp = reinterpret_cast<const float4 *>(pbox + bx * BOX_F + (size_t)cell * CS);
+                const float4 u0 = __ldg(bp), u1 = __ldg(bp + 1);
+                a0.x += u0.x; a0.y += u0.y; a0.z += u0.z; a0.w += u0.w;
+                a1.x += u1.x; a1.y += u1.y; a1.z += u1.z; a1.w += u1.w;
+            }
+        float *dp = gin + bg * CS * HW + px;
+        dp[0] = a0.x; dp[(size_t)HW] = a0.y; dp[(size_t)2 * HW] = a0.z; dp[(size_t)3 * HW] = a0.w;
+        dp[(size_t)4 * HW] = a1.x; dp[(size_t)5 * HW] = a1.y; dp[(size_t)6 * HW] = a1.z; dp[(size_t)7 * HW] = a1.w;
+    }
+}
+
+bool make_plan(const DcnDims &d, BoxBwdPlan &pl)
+{
+    if (d.cpg != CS || d.Co != CO || d.det) return false;
+    if (getenv("EBFI_DCN_BWD_NO_BOX")) return false;
+    if ((long)2 * d.KK * d.Ho * d.Wo >= (1L << 31) || d.KK > 15) return false;       // 32-bit offsets; <= 2^11 contributions per element
+    if ((long)d.B * d.dg >= (1L << 31) || (long)d.W * 8 >= (1L << 31)) return false;
+    pl.TPR = ceil_div(d.KK, NR);
+    pl.Kc = CS * d.KK;
+    pl.N1 = ebfi::round_up(pl.Kc, 16);
+    pl.N3 = ebfi::round_up(pl.Kc + 1, 16);
+    pl.GPC = std::min({GPC_MAX, d.dg, (TMEM_COLS - 2 * pl.N1) / pl.N3});
+    if (pl.GPC < 1 || pl.N1 > 256 || pl.N3 > 256) return false;
+    pl.NH = ceil_div(d.dg, pl.GPC);
+    pl.tiles_x = ceil_div(d.Wo, TW);
+    pl.tiles_y = ceil_div(d.Ho, TH);
+    pl.ntiles = pl.tiles_x * pl.tiles_y;
+    // the undeformed footprint of a tile (+1 for the second bilinear row / pixel) must fit the box; margins centre it
+    const int fh = (TH - 1) * d.sh + (d.kh - 1) * d.dh + 1, fw = (TW - 1) * d.sw + (d.kw - 1) * d.dw + 1;
+    if (fh > box::BH - 1 || fw > box::BW - 1) return false;
+    pl.my = (box::BH - 1 - fh + 1) / 2;
+    pl.mx = (box::BW - 1 - fw + 1) / 2;
+    pl.wt_bytes = 2 * pl.N1 * CO * 2;
+    pl.col_part = (pl.N3 / 8) * TM * 16;
+    pl.om_bytes = 3 * d.KK * TM * 4;
+    pl.use_om_tma = d.Wo % 4 == 0 && getenv("EBFI_DCN_NO_TMA") == nullptr;
+    pl.off_q = 2 * pl.wt_bytes;
+    pl.off_col = pl.off_q + 2 * Q_PART;
+    pl.off_box = pl.off_col + 2 * pl.col_part;
+    pl.off_acc = pl.off_box + 2 * box::BYTES;
+    pl.off_cnt = pl.off_acc + box::BYTES;
+    pl.off_om = pl.off_cnt + ebfi::round_up(CNT_BYTES, 128);
+    pl.smem = pl.off_om + 2 * pl.om_bytes;
+    return pl.smem <= 226 * 1024;
+}
+
+int box_splits(const DcnDims &d, const BoxBwdPlan &pl)
+{
+    return std::max(1, std::min(d.B * pl.ntiles, ebfi::sm_count() / pl.NH));
+}
+
+}  // namespace
+
+// Number of [Co][C*KK] partial slots the box backward writes (two per CTA column), 0 when the shape is not covered.
+int backward_box_splits(const DcnDims &d)
+{
+    BoxBwdPlan pl{};
+    if (!make_plan(d, pl)) return 0;
+    return 2 * box_splits(d, pl);
+}
+
+// scratch: blocked input | blocked far-sample accumulator | W^T images | dense partial boxes
+size_t backward_box_scratch_bytes(const DcnDims &d)
+{
+    BoxBwdPlan pl{};
+    if (!make_plan(d, pl)) return 0;
+    const size_t n = (size_t)d.B * d.C * d.H * d.W;
+    return 2 * n * sizeof(float) + ebfi::round_up((size_t)d.dg * pl.wt_bytes, (size_t)256) +
+           (size_t)d.B * pl.ntiles * d.dg * box::BYTES;
+}
+
+int backward_box(cudaStream_t st, const DcnDims &d, const float *input, const float *weight, const float *offset,
+                 const float *mask, const float *gout, float *gin, float *goff, float *gmask, float *gw, float *gb,
+                 float *gw_part, float *gb_part, void *scratch)
+{
+    BoxBwdPlan pl{};
+    if (!make_plan(d, pl)) return EBFI_ERR_UNSUPPORTED;
+    const size_t n = (size_t)d.B * d.C * d.H * d.W;
+    float *in_blk = static_cast<float *>(scratch), *gin_blk = in_blk + n;
+    unsigned char *wimg = reinterpret_cast<unsigned char *>(gin_blk + n);
+    float *pbox = reinterpret_cast<float *>(wimg + ebfi::round_up((size_t)d.dg * pl.wt_bytes, (size_t)256));
+    const int BG = d.B * d.dg, HW = d.H * d.W;
+    // blocked copy of the input + zero fill of the far-sample accumulator in one pass
+    if (int rc = launch_nchw_to_blocked(st, input, in_blk, BG, HW, gin_blk, 2)) return rc;
+    dcn_bwd_prep_weights<<<ceil_div(d.dg * pl.N1 * CO, 256), 256, 0, st>>>(weight, reinterpret_cast<unsigned short *>(wimg), d, pl);
+    EBFI_LAUNCH_OK("dcn_bwd_prep_weights");
+
+    CUtensorMap tm_box{}, tm_off{}, tm_mask{};
+    {
+        const uint64_t dims[3] = {(uint64_t)d.W * 8, (uint64_t)d.H, (uint64_t)BG};
+        const uint64_t str[2] = {(uint64_t)d.W * 32, (uint64_t)HW * 32};
+        const uint32_t bx[3] = {box::BW * 8, box::BH, 1};
+        if (int rc = tma::encode_3d(tm_box, in_blk, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, dims, str, bx)) return rc;
+    }
+    if (pl.use_om_tma && !(ebfi::aligned16(offset) && ebfi::aligned16(mask))) pl.use_om_tma = 0;
+    if (pl.use_om_tma) {
+        const uint64_t str[2] = {(uint64_t)d.Wo * 4, (uint64_t)d.Ho * d.Wo * 4};
+        const uint64_t dims_o[3] = {(uint64_t)d.Wo, (uint64_t)d.Ho, (uint64_t)(d.B - 1) * d.off_bp + 2 * d.dg * d.KK};
+        const uint64_t dims_m[3] = {(uint64_t)d.Wo, (uint64_t)d.Ho, (uint64_t)(d.B - 1) * d.mask_bp + d.dg * d.KK};
+        const uint32_t box_o[3] = {TW, TH, (uint32_t)(2 * d.KK)}, box_m[3] = {TW, TH, (uint32_t)d.KK};
+        if (int rc = tma::encode_3d(tm_off, offset, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, dims_o, str, box_o)) return rc;
+        if (int rc = tma::encode_3d(tm_mask, mask, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, dims_m, str, box_m)) return rc;
+    }
+    dim3 grid(box_splits(d, pl), pl.NH);
+    if (d.packed) {
+        EBFI_CUDA_OK(cudaFuncSetAttribute(dcn_bwd_box_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
+        dcn_bwd_box_kernel<true><<<grid, NTHR, pl.smem, st>>>(in_blk, wimg, offset, mask, gout, gin_blk, pbox, goff, gmask,
+                                                               gw_part, gb_part, d, pl, tm_box, tm_off, tm_mask);
+    } else {
+        EBFI_CUDA_OK(cudaFuncSetAttribute(dcn_bwd_box_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
+        dcn_bwd_box_kernel<false><<<grid, NTHR, pl.smem, st>>>(in_blk, wimg, offset, mask, gout, gin_blk, pbox, goff, gmask,
+                                                                gw_part, gb_part, d, pl, tm_box, tm_off, tm_mask);
+    }
+    EBFI_LAUNCH_OK("dcn_bwd_box_kernel");
+    const unsigned cgrid = (unsigned)std::min<size_t>(ceil_div((size_t)BG * HW, (size_t)256), (size_t)ebfi::sm_count() * 16);
+    dcn_gin_collect<<<cgrid, 256, 0, st>>>(pbox, gin_blk, gin, d, pl);
+    EBFI_LAUNCH_OK("dcn_gin_collect");
+    const int Kdim = d.C * d.KK;
+    dcn_box_reduce_partials<<<ceil_div(Kdim * CO + CO, 64), 256, 0, st>>>(gw_part, gb_part, gw, gb, 2 * (int)grid.x, Kdim);
+    EBFI_LAUNCH_OK("dcn_box_reduce_partials");
+    return EBFI_OK;
+}
+
+}  // namespace ebfi_dcn

@@ -143,7 +143,7 @@ extern "C" int ebfi_selftest_gemm_tf32x3(void *stream, const float *A, const flo
 namespace {
 __global__ void __launch_bounds__(128)
 tc_gemm_bf16_selftest_kernel(const float *__restrict__ A, const float *__restrict__ B, float *__restrict__ C,
-                             int M, int N, int K, int b_lbo)
+                             int M, int N, int K, int b_lbo, int a_mn)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     // A: [M/8][K/8 chunks][8][8] bf16, LBO 128; B: [N/8][K/8 chunks at b_lbo][8 rows x 16 B]
@@ -160,7 +160,10 @@ tc_gemm_bf16_selftest_kernel(const float *__restrict__ A, const float *__restric
         const int r = e / K, k = e % K;
         unsigned short hi, lo;
         umma::split_bf16(A[(size_t)r * K + k], hi, lo);
-        const int off = (r / 8) * (kch * 64) + (k / 8) * 64 + (r % 8) * 8 + (k % 8);
+        // K-major: 16-byte chunks run along K. MN-major (a_mn): the same 128-byte core matrices hold 8 k-rows of
+        // 8 consecutive m: addr = (m/8)*SBO + (k/8)*LBO + (k%8)*16 + (m%8)*2 with SBO = 128, LBO = 16 * 128
+        const int off = a_mn ? (r / 8) * 64 + (k / 8) * (16 * 64) + (k % 8) * 8 + (r % 8)
+                             : (r / 8) * (kch * 64) + (k / 8) * 64 + (r % 8) * 8 + (k % 8);
         a_hi[off] = hi; a_lo[off] = lo;
     }
     for (int e = tid; e < N * K; e += blockDim.x) {
@@ -177,11 +180,12 @@ tc_gemm_bf16_selftest_kernel(const float *__restrict__ A, const float *__restric
     umma::fence_after_sync();
     const uint32_t tmem = tmem_slot;
     if (tid == 0) {
-        const uint32_t idesc = umma::instr_desc_bf16(M, N);
+        const uint32_t idesc = umma::instr_desc_bf16(M, N) | ((uint32_t)a_mn << 15);
         for (int ks = 0; ks < K / 16; ++ks) {
-            const uint32_t ao = ks * 256, bo = ks * 2 * b_lbo;
-            const uint64_t dah = umma::smem_desc(umma::smem_u32(a_hi) + ao, 128, kch * 128);
-            const uint64_t dal = umma::smem_desc(umma::smem_u32(a_lo) + ao, 128, kch * 128);
+            const uint32_t ao = a_mn ? ks * 2 * (16 * 128) : ks * 256, bo = ks * 2 * b_lbo;
+            const uint32_t a_lbo = a_mn ? 16 * 128 : 128, a_sbo = a_mn ? 128 : kch * 128;
+            const uint64_t dah = umma::smem_desc(umma::smem_u32(a_hi) + ao, a_lbo, a_sbo);
+            const uint64_t dal = umma::smem_desc(umma::smem_u32(a_lo) + ao, a_lbo, a_sbo);
             const uint64_t dbh = umma::smem_desc(umma::smem_u32(b_hi) + bo, b_lbo, b_sbo);
             const uint64_t dbl = umma::smem_desc(umma::smem_u32(b_lo) + bo, b_lbo, b_sbo);
             umma::mma_f16(tmem + N, dal, dbh, idesc, ks > 0);
@@ -210,6 +214,8 @@ tc_gemm_bf16_selftest_kernel(const float *__restrict__ A, const float *__restric
 extern "C" int ebfi_selftest_gemm_bf16x3(void *stream, const float *A, const float *B, float *C, int M, int N,
                                          int K, int b_lbo_bytes)
 {
+    const int a_mn = (b_lbo_bytes >> 16) & 1;      // bit 16: A operand stored MN-major (test-only switch)
+    b_lbo_bytes &= 0xFFFF;
     EBFI_REQUIRE(A && B && C, "selftest_gemm_bf16: null pointer");
     EBFI_REQUIRE(M == 128 || M == 64, "selftest_gemm_bf16: M must be 64 or 128");
     EBFI_REQUIRE(N >= 8 && N <= 128 && N % (M == 128 ? 16 : 8) == 0, "selftest_gemm_bf16: bad N");
@@ -217,7 +223,7 @@ extern "C" int ebfi_selftest_gemm_bf16x3(void *stream, const float *A, const flo
     EBFI_REQUIRE(b_lbo_bytes >= 128 && b_lbo_bytes % 16 == 0 && b_lbo_bytes <= 256, "selftest_gemm_bf16: bad LBO");
     const int smem = 2 * 128 * K * 2 + 2 * 16 * (K / 8) * b_lbo_bytes;
     EBFI_CUDA_OK(cudaFuncSetAttribute(tc_gemm_bf16_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    tc_gemm_bf16_selftest_kernel<<<1, 128, smem, ebfi::as_stream(stream)>>>(A, B, C, M, N, K, b_lbo_bytes);
+    tc_gemm_bf16_selftest_kernel<<<1, 128, smem, ebfi::as_stream(stream)>>>(A, B, C, M, N, K, b_lbo_bytes, a_mn);
     EBFI_LAUNCH_OK("tc_gemm_bf16_selftest_kernel");
     return EBFI_OK;
 }
