@@ -43,7 +43,9 @@ namespace {
 
 using ebfi::ceil_div;
 
-constexpr int TM = 128, TH = 8, TW = 16, NR = 3, NTHR = TM * NR;
+constexpr int TM = 128, TH = 8, TW = 16, NR = 3;
+constexpr int NSAMP = TM * NR, NSW = NSAMP / 32;        // sampler threads / warps
+constexpr int NTHR = NSAMP + 32;                       // + the issuer warp (tensor core, TMA)
 constexpr int CS = 8, CO = 64;                  // channels per group, output channels handled by this kernel
 constexpr int GPC_MAX = 4;                      // deformable groups per CTA (TMEM: 2 * N1 + GPC * N3 <= 512 columns)
 constexpr int TMEM_COLS = 512;
@@ -70,6 +72,25 @@ __device__ __forceinline__ void st_bf16x8(unsigned char *base, int off, const un
     const uint32_t c = v[4] | ((uint32_t)v[5] << 16), e = v[6] | ((uint32_t)v[7] << 16);
     *reinterpret_cast<uint4 *>(base + off) = make_uint4(a, b, c, e);
 }
+
+// (a, b) -> packed bf16 pairs hi = {bf16(a), bf16(b)}, lo = {bf16(a - hi_a), bf16(b - hi_b)}; a in the low half
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t &hi, uint32_t &lo)
+{
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+    const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xFFFF0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
+}
+// eight floats -> one 16-byte chunk of bf16 hi parts and one of lo parts
+__device__ __forceinline__ void st_split8(unsigned char *hi_base, unsigned char *lo_base, int off, const float (&v)[8])
+{
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_bf16x2(v[2 * i], v[2 * i + 1], h[i], l[i]);
+    *reinterpret_cast<uint4 *>(hi_base + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4 *>(lo_base + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__device__ __forceinline__ void sampler_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NSAMP) : "memory"); }
 
 __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float e)
 {
@@ -245,13 +266,15 @@ dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__rest
     int4 *acc4 = reinterpret_cast<int4 *>(smem + pl.off_acc);        // [BH][BW][8] fixed-point grad_input box
     int *cnt = reinterpret_cast<int *>(smem + pl.off_cnt);           // [BH][BW] weight sums of the iteration in pass 1
     const float *oms = reinterpret_cast<const float *>(smem + pl.off_om);   // [2][3*KK planes][128 px]
-    __shared__ __align__(8) uint64_t bar_w[2], bar_in[2], bar_d1[2], bar_g3;
+    // bar_w / bar_in: bulk copies landed; bar_d1: GEMM1 complete; bar_g3: GEMM3 complete (Q, col free);
+    // q_full / col_full: the sampler warps have written Q / the column operand (one arrival per warp)
+    __shared__ __align__(8) uint64_t bar_w[2], bar_in[2], bar_d1[2], bar_g3, q_full, col_full;
     __shared__ uint32_t tmem_slot;
     __shared__ unsigned tile_max[2];
     __shared__ int w_max[2];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int p = tid % TM, r = tid / TM;
+    const int p = tid % TM, r = tid / TM;             // samplers: thread (pixel p, tap row r)
     const int S = gridDim.x, s = blockIdx.x;
     const int g_begin = blockIdx.y * pl.GPC, ng = min(pl.GPC, d.dg - g_begin);
     const int total_tiles = d.B * pl.ntiles;
@@ -265,7 +288,7 @@ dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__rest
     if (warp == 0) umma::tmem_alloc<TMEM_COLS>(&tmem_slot);
     if (tid == 32) {
         for (int i = 0; i < 2; ++i) { umma::mbar_init(&bar_w[i], 1); umma::mbar_init(&bar_in[i], 1); umma::mbar_init(&bar_d1[i], 1); }
-        umma::mbar_init(&bar_g3, 1);
+        umma::mbar_init(&bar_g3, 1); umma::mbar_init(&q_full, NSW); umma::mbar_init(&col_full, NSW);
         umma::mbar_fence_init();
         tile_max[0] = tile_max[1] = 0u;
         w_max[0] = w_max[1] = 0;
@@ -285,26 +308,41 @@ dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__rest
 
     // iteration n of this CTA = (tile s + (n / ng) * S, group g_begin + n % ng)
     struct Iter { int n, b, ty0, tx0, g, gi, tl, ho, wo, pix; bool valid; };
+    auto set_tile = [&](Iter &it, int tile) {       // divisions once per tile
+        it.b = tile / pl.ntiles;
+        it.tl = tile - it.b * pl.ntiles;
+        const int tyi = it.tl / pl.tiles_x;
+        it.ty0 = tyi * TH;
+        it.tx0 = (it.tl - tyi * pl.tiles_x) * TW;
+        it.ho = it.ty0 + p / TW; it.wo = it.tx0 + p % TW;
+        it.valid = it.ho < d.Ho && it.wo < d.Wo;
+        it.pix = it.ho * d.Wo + it.wo;
+    };
     auto decode = [&](int n) {
         Iter it;
         it.n = n;
         const int k = n / ng;
         it.gi = n - k * ng;
         it.g = g_begin + it.gi;
-        const int tile = s + k * S;
-        it.b = tile / pl.ntiles;
-        it.tl = tile - it.b * pl.ntiles;
-        it.ty0 = (it.tl / pl.tiles_x) * TH;
-        it.tx0 = (it.tl % pl.tiles_x) * TW;
-        it.ho = it.ty0 + p / TW; it.wo = it.tx0 + p % TW;
-        it.valid = it.ho < d.Ho && it.wo < d.Wo;
-        it.pix = it.ho * d.Wo + it.wo;
+        set_tile(it, s + k * S);
         return it;
     };
-    // ---- single-thread issue helpers (tid 0)
+    auto next_iter = [&](const Iter &c) {           // iteration c.n + 1
+        Iter it = c;
+        ++it.n;
+        if (++it.gi == ng) {
+            it.gi = 0;
+            set_tile(it, s + (it.n / ng) * S);
+        }
+        it.g = g_begin + it.gi;
+        return it;
+    };
+    // ---- issue helpers: run by all lanes of the issuer warp (warp-uniform arithmetic), the elected lane issues
+    const bool leader = warp == NSW && umma::elect_one();
     auto issue_in = [&](int n) {                    // input box + offsets / masks of iteration n
         const Iter it = decode(n);
         const int bb = n & 1;
+        if (!leader) return;
         umma::mbar_expect_tx(&bar_in[bb], (uint32_t)(box::BYTES + (use_tma ? pl.om_bytes : 0)));
         tma::load_3d(boxes + bb * box::BYTES, &tm_box, (it.tx0 * d.sw - d.pw - pl.mx) * 8, it.ty0 * d.sh - d.ph - pl.my, it.b * d.dg + it.g, &bar_in[bb]);
         if (use_tma) {
@@ -315,6 +353,7 @@ dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__rest
     };
     auto issue_w = [&](int n) {                     // W^T image of iteration n's group
         const int g = g_begin + n % ng;
+        if (!leader) return;
         umma::mbar_expect_tx(&bar_w[n & 1], (uint32_t)pl.wt_bytes);
         umma::bulk_g2s(wring + (n & 1) * pl.wt_bytes, wimg + (size_t)g * pl.wt_bytes, (uint32_t)pl.wt_bytes, &bar_w[n & 1]);
     };
@@ -326,11 +365,14 @@ dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__rest
             // A: 16-byte chunks run along px (SBO 128 between chunks), 8-co groups 2048 B apart (LBO)
             const uint64_t ah = umma::smem_desc(q_s + ks * 4096u, 2048, 128), al = umma::smem_desc(q_s + Q_PART + ks * 4096u, 2048, 128);
             const uint64_t bh = umma::smem_desc(wb + ks * 256u, 128, (CO / 8) * 128), bl = umma::smem_desc(wb + wlo + ks * 256u, 128, (CO / 8) * 128);
-            umma::mma_f16(d1, al, bh, idesc1, ks > 0);
-            umma::mma_f16(d1, ah, bl, idesc1, true);
-            umma::mma_f16(d1, ah, bh, idesc1, true);
+            if (leader) {
+                umma::mma_f16(d1, al, bh, idesc1, ks > 0);
+                umma::mma_f16(d1, ah, bl, idesc1, true);
+                umma::mma_f16(d1, ah, bh, idesc1, true);
+            }
         }
-        umma::commit(&bar_d1[n & 1]);
+        if (leader) umma::commit(&bar_d1[n & 1]);
+        __syncwarp();
     };
     auto issue_gemm3 = [&](int gi, bool accumulate) {   // D3[gi][hi rows | lo rows][k'] += [Q_hi ; Q_lo] . col^T   (K = px)
         const uint32_t d3 = tmem + (uint32_t)(2 * pl.N1 + gi * pl.N3);
@@ -338,24 +380,27 @@ dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__rest
             const uint64_t a = umma::smem_desc(q_s + ks * 256u, 128, (TM / 8) * 128);
             // B: 16-byte chunks run along k' (one tap = one chunk, SBO 2048 between taps), 8-px groups 128 B apart (LBO)
             const uint64_t bh = umma::smem_desc(c_s + ks * 256u, 128, TM * 16), bl = umma::smem_desc(c_s + pl.col_part + ks * 256u, 128, TM * 16);
-            umma::mma_f16(d3, a, bh, idesc3, accumulate || ks > 0);
-            umma::mma_f16(d3, a, bl, idesc3, true);
+            if (leader) {
+                umma::mma_f16(d3, a, bh, idesc3, accumulate || ks > 0);
+                umma::mma_f16(d3, a, bl, idesc3, true);
+            }
         }
-        umma::commit(&bar_g3);
+        if (leader) umma::commit(&bar_g3);
+        __syncwarp();
     };
 
     uint32_t ph_g3 = 0;
     // ================= new tile: grad_output -> Q (bf16 hi / lo), once for all groups of the CTA =================
     // item = (co, chunk of 8 consecutive tile pixels); lanes run over co % 8 first -> conflict-free 16-byte stores.
     // All loads of a thread are issued before the wait for the previous tile's last GEMM3 (which still reads Q and col).
-    constexpr int QI = (CO * (TM / 8) + NTHR - 1) / NTHR;
+    constexpr int QI = (CO * (TM / 8) + NSAMP - 1) / NSAMP;
     auto tile_start = [&](const Iter &it, bool wait_g3) {
         const float *go_b = gout + (size_t)it.b * d.Co * plane;
         float4 va[QI], vb[QI];
         const bool vec = (d.Wo & 3) == 0;
 #pragma unroll
         for (int q = 0; q < QI; ++q) {
-            const int item = tid + q * NTHR;
+            const int item = tid + q * NSAMP;
             va[q] = vb[q] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (item < CO * (TM / 8)) {
                 const int j = item & 7, pc = (item >> 3) & (TM / 8 - 1), co = (item >> 7) * 8 + j;
@@ -378,42 +423,23 @@ dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__rest
         }
 #pragma unroll
         for (int q = 0; q < QI; ++q) {
-            const int item = tid + q * NTHR;
+            const int item = tid + q * NSAMP;
             if (item < CO * (TM / 8)) {
                 const int j = item & 7, pc = (item >> 3) & (TM / 8 - 1), co = (item >> 7) * 8 + j;
                 const float v[8] = {va[q].x, va[q].y, va[q].z, va[q].w, vb[q].x, vb[q].y, vb[q].z, vb[q].w};
-                unsigned short hi[8], lo[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) umma::split_bf16(v[i], hi[i], lo[i]);
-                const int off = (co >> 3) * ((TM / 8) * 128) + pc * 128 + j * 16;
-                st_bf16x8(q_hi, off, hi); st_bf16x8(q_lo, off, lo);
+                st_split8(q_hi, q_lo, (co >> 3) * ((TM / 8) * 128) + pc * 128 + j * 16, v);
             }
         }
         // column chunks past the taps: the ones column (grad_bias) and zero padding up to N3
-        for (int c = tid; c < (pl.N3 / 8 - d.KK) * TM; c += NTHR) {
+        for (int c = tid; c < (pl.N3 / 8 - d.KK) * TM; c += NSAMP) {
             const int pp = c % TM, ch = d.KK + c / TM;
             const bool one = ch == d.KK && (it.ty0 + pp / TW) < d.Ho && (it.tx0 + pp % TW) < d.Wo;
             *reinterpret_cast<uint4 *>(c_hi + ch * (TM * 16) + pp * 16) = make_uint4(one ? 0x3F80u : 0u, 0u, 0u, 0u);   // bf16(1.0)
             *reinterpret_cast<uint4 *>(c_lo + ch * (TM * 16) + pp * 16) = make_uint4(0u, 0u, 0u, 0u);
         }
         umma::fence_smem_to_async();
-        __syncthreads();
-        if (tid == 0) {
-            umma::fence_after_sync();
-            issue_gemm1(it.n);
-            if (ng > 1) issue_gemm1(it.n + 1);
-        }
-        // the next tile's grad_output -> L2, so that its staging pays an L2 hit instead of a DRAM miss
-        const int ntile = s + (it.n / ng + 1) * S;
-        if (ntile < total_tiles) {
-            const int nb = ntile / pl.ntiles, ntl = ntile - nb * pl.ntiles;
-            const int nty0 = (ntl / pl.tiles_x) * TH, ntx0 = (ntl % pl.tiles_x) * TW;
-            for (int c = tid; c < CO * TH; c += NTHR) {
-                const int co = c / TH, hh = nty0 + c % TH;
-                if (hh < d.Ho)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(gout + ((size_t)nb * d.Co + co) * plane + (size_t)hh * d.Wo + ntx0));
-            }
-        }
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(&q_full);
     };
     // ================= pass 1 of an iteration: M = max |colgrad * mask| (unsigned order of the float bits: NaN > Inf > finite,
     // so a non-finite value anywhere is seen) and the per-cell sums of the scatter's bilinear weights (rounded up, 16.16) ======
@@ -422,7 +448,6 @@ dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__rest
         const uint32_t par = (uint32_t)((it.n >> 1) & 1);
         umma::mbar_wait(&bar_d1[bb], par);           // colgrad of this group is in TMEM
         umma::fence_after_sync();
-        if (tid == 0 && it.n + 2 < NI) issue_w(it.n + 2);    // GEMM1(n) is complete: its weight slot is free
         umma::mbar_wait(&bar_in[bb], par);           // box + offsets / masks have landed
         const float *om = oms + bb * (pl.om_bytes / 4);
         const float *off_g = offset + (size_t)it.b * d.off_bs + (size_t)it.g * 2 * d.KK * plane;
@@ -466,26 +491,58 @@ dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__rest
     // max over the cells of the weight sums pass 1 left in `cnt` (cleared for the next pass 1)
     auto cell_max = [&](int bb) {
         int wm = 0;
-        for (int c = tid; c < box::BH * box::BW; c += NTHR) { wm = max(wm, cnt[c]); cnt[c] = 0; }
+        for (int c = tid; c < box::BH * box::BW; c += NSAMP) { wm = max(wm, cnt[c]); cnt[c] = 0; }
         wm = __reduce_max_sync(0xffffffffu, wm);
         if (lane == 0 && wm) atomicMax(&w_max[bb], wm);
     };
 
-    if (tid == 0) {
+    if (warp == NSW) {
+        // ================= issuer warp: tensor-core and copy-engine work, off the samplers' critical path =================
         issue_w(0); issue_in(0);
         if (NI > 1) { issue_w(1); issue_in(1); }
-    }
+        int gi = 0, k = 0;
+        for (int n = 0; n < NI; ++n) {
+            if (gi == 0) {
+                umma::mbar_wait(&q_full, (uint32_t)(k & 1));         // Q of this tile is staged
+                umma::fence_after_sync();
+                issue_gemm1(n);
+                if (ng > 1) issue_gemm1(n + 1);
+                // the next tile's grad_output -> L2, so that its staging pays an L2 hit instead of a DRAM miss
+                const int ntile = s + (k + 1) * S;
+                if (ntile < total_tiles) {
+                    const int nb = ntile / pl.ntiles, ntl = ntile - nb * pl.ntiles;
+                    const int nty0 = (ntl / pl.tiles_x) * TH, ntx0 = (ntl % pl.tiles_x) * TW;
+                    for (int c = lane; c < CO * TH; c += 32) {
+                        const int co = c / TH, hh = nty0 + c % TH;
+                        if (hh < d.Ho)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(gout + ((size_t)nb * d.Co + co) * plane + (size_t)hh * d.Wo + ntx0));
+                    }
+                }
+            }
+            umma::mbar_wait(&bar_d1[n & 1], (uint32_t)((n >> 1) & 1));
+            if (n + 2 < NI) issue_w(n + 2);                          // GEMM1(n) is complete: its weight slot is free
+            umma::mbar_wait(&col_full, (uint32_t)(n & 1));           // pass 2 of iteration n is done in every sampler warp
+            umma::fence_after_sync();
+            issue_gemm3(gi, n >= ng);                                // the first tile of the CTA starts the accumulation
+            if (n + 2 < NI) {
+                issue_in(n + 2);                                     // box / offset buffers of this iteration are free
+                if (gi + 2 < ng) issue_gemm1(n + 2);                 // same tile: Q is staged (else: at the tile start), D1 slot is free
+            }
+            if (++gi == ng) { gi = 0; ++k; }
+        }
+    } else {
+    // ================= sampler warps =================
     Iter cur = decode(0);
     if (NI > 0) {
         tile_start(cur, false);
         pass1(cur);
-        __syncthreads();
+        sampler_sync();
         cell_max(0);
-        __syncthreads();
+        sampler_sync();
     }
     for (int n = 0; n < NI; ++n) {
         const int bb = n & 1;
-        const Iter nxt = decode(n + 1 < NI ? n + 1 : n);
+        const Iter nxt = n + 1 < NI ? next_iter(cur) : cur;
         const bool has_next = n + 1 < NI, next_same_tile = has_next && nxt.gi != 0;
         // ---- fixed-point scale of this (tile, group): every element |sum| <= M * W * scale (+ one rounding per
         //      contribution) <= 2^30 (+ 128 * taps)
@@ -540,11 +597,7 @@ dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__rest
                     gmask_g[(unsigned)t * uplane + (unsigned)cur.pix] = g_m;
                 }
                 // column operand: the 8 channels of (tap t, pixel p) are one 16-byte chunk
-                unsigned short hi[8], lo[8];
-#pragma unroll
-                for (int cc = 0; cc < CS; ++cc) umma::split_bf16(colv[cc], hi[cc], lo[cc]);
-                st_bf16x8(c_hi, t * (TM * 16) + p * 16, hi);
-                st_bf16x8(c_lo, t * (TM * 16) + p * 16, lo);
+                st_split8(c_hi, c_lo, t * (TM * 16) + p * 16, colv);
                 if (++tj == d.kw) { tj = 0; ++ti; }
             }
         }
@@ -552,23 +605,16 @@ dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__rest
         // iterations ago); a new tile needs its Q first
         if (next_same_tile) pass1(nxt);
         umma::fence_smem_to_async();
-        umma::fence_before_sync();                       // orders this thread's tcgen05.ld of D1 before the sync
-        __syncthreads();
-        if (tid == 0) {
-            umma::fence_after_sync();
-            issue_gemm3(cur.gi, n >= ng);                // the first tile of the CTA starts the accumulation
-            if (n + 2 < NI) {
-                issue_in(n + 2);                         // box / offset buffers of this iteration are free
-                if (cur.gi + 2 < ng) issue_gemm1(n + 2); // same tile: Q is already staged (else: issued at the tile start)
-            }
-            tile_max[bb] = 0u;
-            w_max[bb] = 0;
-        }
+        umma::fence_before_sync();                       // orders this thread's tcgen05.ld of D1 before the arrival
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(&col_full);
+        sampler_sync();                                  // the accumulation box is complete
+        if (tid == 0) { tile_max[bb] = 0u; w_max[bb] = 0; }
         // ---- the accumulation box -> dense fp32 partial (plain coalesced stores), cleared for the next iteration
         {
             float4 *dst = reinterpret_cast<float4 *>(pbox + (((size_t)cur.b * pl.ntiles + cur.tl) * d.dg + cur.g) * BOX_F);
             const float qnan = __uint_as_float(0x7FC00000u);
-            for (int c = tid; c < BOX_F / 4; c += NTHR) {
+            for (int c = tid; c < BOX_F / 4; c += NSAMP) {
                 const int4 v = acc4[c];
                 acc4[c] = make_int4(0, 0, 0, 0);
                 dst[c] = nonfinite ? make_float4(qnan, qnan, qnan, qnan)
@@ -580,10 +626,10 @@ dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__rest
         } else if (has_next) {
             tile_start(nxt, true);
             pass1(nxt);
-            __syncthreads();
+            sampler_sync();
             cell_max(bb ^ 1);
         }
-        __syncthreads();
+        sampler_sync();
         cur = nxt;
     }
     // ---- partials of this CTA, [slot][k = (c0 + cc) * KK + tap][co] so that a warp writes 128 contiguous bytes:
@@ -617,6 +663,7 @@ dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__rest
             }
         }
     }
+    }   // sampler warps
     umma::fence_before_sync();
     __syncthreads();
     if (warp == 0) umma::tmem_dealloc<TMEM_COLS>(tmem);
