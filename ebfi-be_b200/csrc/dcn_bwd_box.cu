@@ -18,10 +18,10 @@
 //   * grad_mask / grad_offset: one owner thread per element, no atomics (im2col_cuda.cu:280-330).
 //   * grad_input (im2col_cuda.cu:197-254): contributions are accumulated in a shared-memory box of the same geometry as
 //     32-bit FIXED POINT (native ATOMS.ADD; a float shared atomic is a CAS loop), with a power-of-two scale chosen per
-//     (tile, group) in a first pass over the samples: M = max |colgrad * mask| and W = the largest sum of bilinear
-//     weights any box cell receives (4 integer atomics per sample) bound every element by M * W, so scale = 2^30 / (M * W)
-//     cannot overflow and resolves a contribution to ~2^-26 of M (W is ~10). Integer addition is associative, so the box
-//     is bit-reproducible.
+//     (tile, group) in a first pass over the samples: M = max |colgrad * mask| and n = the largest number of contributions
+//     any box cell receives (one integer atomic per sample into a count box) bound every element by n * M, so
+//     scale = 2^30 / (n * M) cannot overflow and resolves a contribution to ~2^-24 of M (n is ~40). Integer addition is
+//     associative, so the box is bit-reproducible.
 //     The box is written — converted back to fp32 — as a dense partial to global memory with plain coalesced stores;
 //     dcn_gin_collect then sums, per input pixel, the <= 9 boxes that cover it in a fixed order and writes NCHW. No global
 //     atomics, no order dependence: grad_input is bit-identical run to run, by default.
@@ -51,7 +51,8 @@ constexpr int GPC_MAX = 4;                      // deformable groups per CTA (TM
 constexpr int TMEM_COLS = 512;
 constexpr int Q_PART = CO * TM * 2;             // one bf16 image of the grad_output tile
 constexpr int BOX_F = box::BYTES / 4;           // floats per box
-constexpr int CNT_BYTES = box::BH * box::BW * 4; // per-cell sums of bilinear weights (16.16 fixed point)
+constexpr int CNT_BYTES = box::BH * box::BW * 4; // per-cell sample counts of one iteration
+constexpr int CNT_PAD = (CNT_BYTES + 127) / 128 * 128;
 
 struct BoxBwdPlan {
     int TPR;             // taps per thread row
@@ -248,7 +249,7 @@ __device__ __forceinline__ void sample_bwd(const DcnDims &d, const SampleCtx &sc
     }
 }
 
-template <bool PACKED>
+template <bool PACKED, int TPRT>
 __global__ void __launch_bounds__(NTHR, 1)
 dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__restrict__ wimg,
                    const float *__restrict__ offset, const float *__restrict__ mask,
@@ -264,7 +265,7 @@ dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__rest
     unsigned char *c_hi = smem + pl.off_col, *c_lo = c_hi + pl.col_part;   // [tap][px][8 ch] bf16: MN-major B of GEMM3
     unsigned char *boxes = smem + pl.off_box;                        // [2][BH][BW][8] fp32 input boxes
     int4 *acc4 = reinterpret_cast<int4 *>(smem + pl.off_acc);        // [BH][BW][8] fixed-point grad_input box
-    int *cnt = reinterpret_cast<int *>(smem + pl.off_cnt);           // [BH][BW] weight sums of the iteration in pass 1
+    int *cnt = reinterpret_cast<int *>(smem + pl.off_cnt);           // [2][BH][BW] samples per cell (first corner), by iteration parity
     const float *oms = reinterpret_cast<const float *>(smem + pl.off_om);   // [2][3*KK planes][128 px]
     // bar_w / bar_in: bulk copies landed; bar_d1: GEMM1 complete; bar_g3: GEMM3 complete (Q, col free);
     // q_full / col_full: the sampler warps have written Q / the column operand (one arrival per warp)
@@ -294,7 +295,7 @@ dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__rest
         w_max[0] = w_max[1] = 0;
     }
     for (int c = tid; c < BOX_F / 4; c += NTHR) acc4[c] = make_int4(0, 0, 0, 0);
-    for (int c = tid; c < box::BH * box::BW; c += NTHR) cnt[c] = 0;
+    for (int c = tid; c < 2 * CNT_PAD / 4; c += NTHR) cnt[c] = 0;
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
@@ -443,55 +444,70 @@ dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__rest
     };
     // ================= pass 1 of an iteration: M = max |colgrad * mask| (unsigned order of the float bits: NaN > Inf > finite,
     // so a non-finite value anywhere is seen) and the per-cell sums of the scatter's bilinear weights (rounded up, 16.16) ======
-    auto pass1 = [&](const Iter &it) {
+    struct P1 { const float *om, *off_g, *mask_g; uint32_t d1, cnt_s; int by0, bxq0; };
+    auto pass1_begin = [&](const Iter &it) {
         const int bb = it.n & 1;
         const uint32_t par = (uint32_t)((it.n >> 1) & 1);
         umma::mbar_wait(&bar_d1[bb], par);           // colgrad of this group is in TMEM
         umma::fence_after_sync();
         umma::mbar_wait(&bar_in[bb], par);           // box + offsets / masks have landed
-        const float *om = oms + bb * (pl.om_bytes / 4);
-        const float *off_g = offset + (size_t)it.b * d.off_bs + (size_t)it.g * 2 * d.KK * plane;
-        const float *mask_g = mask + (size_t)it.b * d.mask_bs + (size_t)it.g * d.KK * plane;
-        const uint32_t d1 = tmem + (uint32_t)(bb * pl.N1);
-        const int by0 = it.ty0 * d.sh - d.ph - pl.my, bxq0 = it.tx0 * d.sw - d.ph - pl.mx;
-        unsigned um = 0u;
-        int t = t_first, ti = ti_first, tj = tj_first;
-        for (int sidx = 0; sidx < pl.TPR && t < d.KK; ++sidx, ++t) {
-            float gc[8];
-            umma::tmem_ld8(umma::tmem_addr(d1, lane_base, t * 8), gc);
-            umma::tmem_ld_wait();
-            if (it.valid) {
-                float dy, dx, m;
-                if (use_tma) {
-                    dy = om[(2 * t) * TM + p];
-                    dx = om[(2 * t + 1) * TM + p];
-                    m = om[(2 * d.KK + t) * TM + p];
-                } else {
-                    tap_read(off_g, mask_g, uplane, (unsigned)t, (unsigned)it.pix, dy, dx, m);
-                }
-                m = mask_act_t<PACKED>(m);
-#pragma unroll
-                for (int cc = 0; cc < CS; ++cc) um = max(um, __float_as_uint(fabsf(gc[cc] * m)));
-                // the scatter's x uses pad_h (im2col_cuda.cu:368)
-                const Geo q = make_geo((float)(it.ho * d.sh - d.ph + ti * d.dh) + dy, (float)(it.wo * d.sw - d.ph + tj * d.dw) + dx,
-                                       d.H, d.W, by0, bxq0);
-                if (q.inbox) {
-                    const uint32_t a = cnt_s + (uint32_t)(q.yb * box::BW + q.xb) * 4u;
-                    atoms_add(a, __float2int_ru(q.hy * q.hx * 65536.f));
-                    atoms_add(a + 4u, __float2int_ru(q.hy * q.lx * 65536.f));
-                    atoms_add(a + box::BW * 4u, __float2int_ru(q.ly * q.hx * 65536.f));
-                    atoms_add(a + box::BW * 4u + 4u, __float2int_ru(q.ly * q.lx * 65536.f));
-                }
+        P1 q;
+        q.om = oms + bb * (pl.om_bytes / 4);
+        q.off_g = offset + (size_t)it.b * d.off_bs + (size_t)it.g * 2 * d.KK * plane;
+        q.mask_g = mask + (size_t)it.b * d.mask_bs + (size_t)it.g * d.KK * plane;
+        q.d1 = tmem + (uint32_t)(bb * pl.N1);
+        q.cnt_s = cnt_s + (uint32_t)(bb * CNT_PAD);
+        q.by0 = it.ty0 * d.sh - d.ph - pl.my; q.bxq0 = it.tx0 * d.sw - d.ph - pl.mx;
+        return q;
+    };
+    auto pass1_tap = [&](const Iter &it, const P1 &q, int t, int ti, int tj, unsigned &um) {
+        float gc[8];
+        umma::tmem_ld8(umma::tmem_addr(q.d1, lane_base, t * 8), gc);
+        umma::tmem_ld_wait();
+        if (it.valid) {
+            float dy, dx, m;
+            if (use_tma) {
+                dy = q.om[(2 * t) * TM + p];
+                dx = q.om[(2 * t + 1) * TM + p];
+                m = q.om[(2 * d.KK + t) * TM + p];
+            } else {
+                tap_read(q.off_g, q.mask_g, uplane, (unsigned)t, (unsigned)it.pix, dy, dx, m);
             }
-            if (++tj == d.kw) { tj = 0; ++ti; }
+            m = mask_act_t<PACKED>(m);
+#pragma unroll
+            for (int cc = 0; cc < CS; ++cc) um = max(um, __float_as_uint(fabsf(gc[cc] * m)));
+            // the scatter's x uses pad_h (im2col_cuda.cu:368)
+            const Geo ge = make_geo((float)(it.ho * d.sh - d.ph + ti * d.dh) + dy, (float)(it.wo * d.sw - d.ph + tj * d.dw) + dx,
+                                    d.H, d.W, q.by0, q.bxq0);
+            if (ge.inbox) atoms_add(q.cnt_s + (uint32_t)(ge.yb * box::BW + ge.xb) * 4u, 1);
         }
+    };
+    auto pass1_end = [&](int bb, unsigned um) {
         um = __reduce_max_sync(0xffffffffu, um);
         if (lane == 0 && um) atomicMax(&tile_max[bb], um);
     };
-    // max over the cells of the weight sums pass 1 left in `cnt` (cleared for the next pass 1)
+    auto pass1 = [&](const Iter &it) {
+        const P1 q = pass1_begin(it);
+        unsigned um = 0u;
+        int t = t_first, ti = ti_first, tj = tj_first;
+        for (int sidx = 0; sidx < pl.TPR && t < d.KK; ++sidx, ++t) {
+            pass1_tap(it, q, t, ti, tj, um);
+            if (++tj == d.kw) { tj = 0; ++ti; }
+        }
+        pass1_end(it.n & 1, um);
+    };
+    // n_max = the largest number of contributions any box cell receives = max over cells (Y, X) of the samples whose first
+    // corner is (Y, X), (Y, X-1), (Y-1, X) or (Y-1, X-1), from the counts pass 1 left in cnt[bb]
     auto cell_max = [&](int bb) {
+        const int *cb = cnt + bb * (CNT_PAD / 4);
         int wm = 0;
-        for (int c = tid; c < box::BH * box::BW; c += NSAMP) { wm = max(wm, cnt[c]); cnt[c] = 0; }
+        for (int c = tid; c < box::BH * box::BW; c += NSAMP) {
+            const int yy = c / box::BW, xx = c - yy * box::BW;
+            int v = cb[c];
+            if (xx > 0) v += cb[c - 1];
+            if (yy > 0) { v += cb[c - box::BW]; if (xx > 0) v += cb[c - box::BW - 1]; }
+            wm = max(wm, v);
+        }
         wm = __reduce_max_sync(0xffffffffu, wm);
         if (lane == 0 && wm) atomicMax(&w_max[bb], wm);
     };
@@ -544,14 +560,13 @@ dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__rest
         const int bb = n & 1;
         const Iter nxt = n + 1 < NI ? next_iter(cur) : cur;
         const bool has_next = n + 1 < NI, next_same_tile = has_next && nxt.gi != 0;
-        // ---- fixed-point scale of this (tile, group): every element |sum| <= M * W * scale (+ one rounding per
-        //      contribution) <= 2^30 (+ 128 * taps)
+        // ---- fixed-point scale of this (tile, group): every element |sum| <= n_max * (M * scale + 1/2) <= 2^30 + 2^10
         const unsigned tmax = tile_max[bb];
         const bool nonfinite = tmax >= 0x7F800000u;
         int e2 = 0;
         if (tmax && !nonfinite) frexpf(__uint_as_float(tmax), &e2);      // M < 2^e2
-        const int wbits = 32 - __clz(max(w_max[bb], 65536));             // W < 2^(wbits - 16), at least 1
-        const int k2 = max(-100, min(100, 46 - wbits - e2));
+        const int wbits = 32 - __clz(max(w_max[bb], 1));                 // contributions per element < 2^wbits
+        const int k2 = max(-100, min(100, 30 - wbits - e2));
         const float inv_scale = ldexpf(1.f, -k2);
         if (cur.gi != 0) {                               // col is still read by GEMM3 of the previous iteration
             umma::mbar_wait(&bar_g3, ph_g3);
@@ -572,9 +587,15 @@ dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__rest
             float *goff_g = goff + (size_t)cur.b * d.off_bs + (size_t)cur.g * 2 * d.KK * plane;
             float *gmask_g = gmask + (size_t)cur.b * d.mask_bs + (size_t)cur.g * d.KK * plane;
             const uint32_t d1 = tmem + (uint32_t)(bb * pl.N1);
+            // pass 1 of the next group of the same tile is interleaved tap by tap (its colgrad was issued two iterations
+            // ago): two independent instruction streams per warp; a new tile needs its Q first
+            P1 q1{};
+            unsigned um = 0u;
+            if (next_same_tile) q1 = pass1_begin(nxt);
             int t = t_first, ti = ti_first, tj = tj_first;
-#pragma unroll 1
-            for (int sidx = 0; sidx < pl.TPR && t < d.KK; ++sidx, ++t) {
+#pragma unroll (TPRT > 0 ? TPRT : 1)
+            for (int sidx = 0; sidx < (TPRT > 0 ? TPRT : pl.TPR) && t < d.KK; ++sidx, ++t) {
+                if (next_same_tile) pass1_tap(nxt, q1, t, ti, tj, um);
                 float gc[8];
                 umma::tmem_ld8(umma::tmem_addr(d1, lane_base, t * 8), gc);     // colgrad[p][t*8 .. t*8+7]
                 umma::tmem_ld_wait();
@@ -600,10 +621,8 @@ dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__rest
                 st_split8(c_hi, c_lo, t * (TM * 16) + p * 16, colv);
                 if (++tj == d.kw) { tj = 0; ++ti; }
             }
+            if (next_same_tile) pass1_end(bb ^ 1, um);
         }
-        // pass 1 of the next group of the same tile rides in the same barrier interval (its colgrad was issued two
-        // iterations ago); a new tile needs its Q first
-        if (next_same_tile) pass1(nxt);
         umma::fence_smem_to_async();
         umma::fence_before_sync();                       // orders this thread's tcgen05.ld of D1 before the arrival
         __syncwarp();
@@ -614,6 +633,7 @@ dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__rest
         {
             float4 *dst = reinterpret_cast<float4 *>(pbox + (((size_t)cur.b * pl.ntiles + cur.tl) * d.dg + cur.g) * BOX_F);
             const float qnan = __uint_as_float(0x7FC00000u);
+            for (int c = tid; c < box::BH * box::BW; c += NSAMP) cnt[bb * (CNT_PAD / 4) + c] = 0;    // read by cell_max an interval ago
             for (int c = tid; c < BOX_F / 4; c += NSAMP) {
                 const int4 v = acc4[c];
                 acc4[c] = make_int4(0, 0, 0, 0);
@@ -774,7 +794,7 @@ bool make_plan(const DcnDims &d, BoxBwdPlan &pl)
     pl.off_box = pl.off_col + 2 * pl.col_part;
     pl.off_acc = pl.off_box + 2 * box::BYTES;
     pl.off_cnt = pl.off_acc + box::BYTES;
-    pl.off_om = pl.off_cnt + ebfi::round_up(CNT_BYTES, 128);
+    pl.off_om = pl.off_cnt + 2 * CNT_PAD;
     pl.smem = pl.off_om + 2 * pl.om_bytes;
     return pl.smem <= 226 * 1024;
 }
@@ -837,15 +857,16 @@ int backward_box(cudaStream_t st, const DcnDims &d, const float *input, const fl
         if (int rc = tma::encode_3d(tm_mask, mask, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, dims_m, str, box_m)) return rc;
     }
     dim3 grid(box_splits(d, pl), pl.NH);
-    if (d.packed) {
-        EBFI_CUDA_OK(cudaFuncSetAttribute(dcn_bwd_box_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
-        dcn_bwd_box_kernel<true><<<grid, NTHR, pl.smem, st>>>(in_blk, wimg, offset, mask, gout, gin_blk, pbox, goff, gmask,
-                                                               gw_part, gb_part, d, pl, tm_box, tm_off, tm_mask);
-    } else {
-        EBFI_CUDA_OK(cudaFuncSetAttribute(dcn_bwd_box_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
-        dcn_bwd_box_kernel<false><<<grid, NTHR, pl.smem, st>>>(in_blk, wimg, offset, mask, gout, gin_blk, pbox, goff, gmask,
-                                                                gw_part, gb_part, d, pl, tm_box, tm_off, tm_mask);
-    }
+#define EBFI_BWD_BOX(P, T)                                                                                             \
+    do {                                                                                                               \
+        EBFI_CUDA_OK(cudaFuncSetAttribute(dcn_bwd_box_kernel<P, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem)); \
+        dcn_bwd_box_kernel<P, T><<<grid, NTHR, pl.smem, st>>>(in_blk, wimg, offset, mask, gout, gin_blk, pbox, goff, gmask, \
+                                                              gw_part, gb_part, d, pl, tm_box, tm_off, tm_mask);       \
+    } while (0)
+    // TPRT > 0 unrolls the tap loop (several samples in flight per thread); measured slower on B200 at 3 taps (238 vs
+    // 230 us: register pressure), so the rolled loop serves every shape
+    if (d.packed) EBFI_BWD_BOX(true, 0); else EBFI_BWD_BOX(false, 0);
+#undef EBFI_BWD_BOX
     EBFI_LAUNCH_OK("dcn_bwd_box_kernel");
     const unsigned cgrid = (unsigned)std::min<size_t>(ceil_div((size_t)BG * HW, (size_t)256), (size_t)ebfi::sm_count() * 16);
     dcn_gin_collect<<<cgrid, 256, 0, st>>>(pbox, gin_blk, gin, d, pl);
