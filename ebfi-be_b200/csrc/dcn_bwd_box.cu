@@ -749,15 +749,28 @@ __global__ void dcn_gin_collect(const float *__restrict__ pbox, const float *__r
         const int ty_hi = min(pl.tiles_y - 1, ny / sy), tx_hi = min(pl.tiles_x - 1, nx / sx);
         const int ty_lo = ny - (box::BH - 1) <= 0 ? 0 : (ny - (box::BH - 1) + sy - 1) / sy;
         const int tx_lo = nx - (box::BW - 1) <= 0 ? 0 : (nx - (box::BW - 1) + sx - 1) / sx;
-        for (int ty = ty_lo; ty <= ty_hi; ++ty)
-            for (int tx = tx_lo; tx <= tx_hi; ++tx) {
-                const size_t bx = ((size_t)b * pl.ntiles + (size_t)ty * pl.tiles_x + tx) * d.dg + g;
-                const int cell = (ny - ty * sy) * box::BW + (nx - tx * sx);
-                const float4 *bp = reinterpret_cast<const float4 *>(pbox + bx * BOX_F + (size_t)cell * CS);
-                const float4 u0 = __ldg(bp), u1 = __ldg(bp + 1);
-                a0.x += u0.x; a0.y += u0.y; a0.z += u0.z; a0.w += u0.w;
-                a1.x += u1.x; a1.y += u1.y; a1.z += u1.z; a1.w += u1.w;
+        // at most ceil(BH / 8) x ceil(BW / 16) = 3 x 2 boxes cover a pixel: all loads are issued before the first add,
+        // the additions keep the fixed (ty, tx) order
+        constexpr int NY = (box::BH + TH - 1) / TH, NX = (box::BW + TW - 1) / TW;
+        float4 u0[NY * NX], u1[NY * NX];
+#pragma unroll
+        for (int a = 0; a < NY; ++a)
+#pragma unroll
+            for (int c = 0; c < NX; ++c) {
+                const int ty = ty_lo + a, tx = tx_lo + c;
+                u0[a * NX + c] = u1[a * NX + c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ty <= ty_hi && tx <= tx_hi) {
+                    const size_t bx = ((size_t)b * pl.ntiles + (size_t)ty * pl.tiles_x + tx) * d.dg + g;
+                    const int cell = (ny - ty * sy) * box::BW + (nx - tx * sx);
+                    const float4 *bp = reinterpret_cast<const float4 *>(pbox + bx * BOX_F + (size_t)cell * CS);
+                    u0[a * NX + c] = __ldg(bp); u1[a * NX + c] = __ldg(bp + 1);
+                }
             }
+#pragma unroll
+        for (int q = 0; q < NY * NX; ++q) {
+            a0.x += u0[q].x; a0.y += u0[q].y; a0.z += u0[q].z; a0.w += u0[q].w;
+            a1.x += u1[q].x; a1.y += u1[q].y; a1.z += u1[q].z; a1.w += u1[q].w;
+        }
         float *dp = gin + bg * CS * HW + px;
         dp[0] = a0.x; dp[(size_t)HW] = a0.y; dp[(size_t)2 * HW] = a0.z; dp[(size_t)3 * HW] = a0.w;
         dp[(size_t)4 * HW] = a1.x; dp[(size_t)5 * HW] = a1.y; dp[(size_t)6 * HW] = a1.z; dp[(size_t)7 * HW] = a1.w;

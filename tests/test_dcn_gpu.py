@@ -96,6 +96,99 @@ def test_window_edges_match_oracle(dcn, oracle):
         assert rel_err(got, ref) < GRAD_TOL, name
 
 
+# (B, C=Co=64, H, W, pad_h, pad_w, offset sigma): shapes of the box backward (dcn_bwd_box.cu: 8 channels per group, 64 outputs)
+BOX_SHAPES = [(1, 40, 56, 1, 1, 2.0),        # ragged tiles (40 = 5 x 8 rows, 56 = 3.5 x 16 pixels)
+              (2, 33, 47, 1, 1, 1.0),        # odd sizes: offsets / masks read without TMA (row stride not 16-byte)
+              (1, 48, 64, 1, 1, 12.0),       # most samples leave the 24 x 30 box: global gather / red.add fall-back
+              (1, 32, 48, 2, 1, 2.0),        # pad_h != pad_w: the scatter's x uses pad_h (im2col_cuda.cu:368)
+              (3, 24, 16, 1, 1, 3.0)]        # one tile column, three samples
+
+
+@pytest.mark.parametrize("shape", BOX_SHAPES)
+def test_box_backward_against_oracle(dcn, oracle, shape):
+    B, H, W, ph, pw, osc = shape
+    C = Co = 64; dg = 8; k = 3
+    rng = np.random.default_rng(abs(hash(shape)) % (2 ** 32))
+    Ho, Wo = H + 2 * ph - 2, W + 2 * pw - 2
+    x = rng.standard_normal((B, C, H, W), dtype=np.float32)
+    w = (rng.random((Co, C, k, k), dtype=np.float32) * 2 - 1) / 24
+    b = rng.standard_normal(Co, dtype=np.float32)
+    # offsets on the grid k/64 + 1/128: sampling coordinates are exact in fp32 and never integers, where grad_offset jumps
+    # (a coordinate that rounds to an integer in fp32 but not in the oracle's fp64 would compare two different branches)
+    off = (np.round(rng.standard_normal((B, 2 * dg * k * k, Ho, Wo)) * osc * 64) / 64 + 1 / 128).astype(np.float32)
+    msk = (1 / (1 + np.exp(-rng.standard_normal((B, dg * k * k, Ho, Wo))))).astype(np.float32)
+    go = rng.standard_normal((B, Co, Ho, Wo), dtype=np.float32)
+    out, grads = _run(dcn, x, off, msk, w, b, go, 1, (ph, pw), 1, dg)
+    assert rel_err(out, oracle.dcn_forward(x, off, msk, w, b, 1, (ph, pw), 1, dg)) < FWD_TOL
+    for name, got, ref in zip(GRADS, grads, oracle.dcn_backward(x, off, msk, w, b, go, 1, (ph, pw), 1, dg)):
+        assert rel_err(got, ref) < GRAD_TOL, name
+
+
+def test_grad_input_is_bit_reproducible_by_default(dcn):
+    """Default mode, no flag: samples inside the staged box accumulate in shared-memory fixed point and the per-tile boxes
+    are summed in a fixed order, so ALL five gradients are bit-identical run to run (512 tiles: 7 per CTA)."""
+    from gpu_util import dev
+    torch.manual_seed(4)
+    B, C, H, W, dg = 1, 64, 256, 256, 8
+    x = torch.randn(B, C, H, W, device=dev())
+    off = 2 * torch.randn(B, 2 * dg * 9, H, W, device=dev())
+    msk = torch.sigmoid(torch.randn(B, dg * 9, H, W, device=dev()))
+    w = torch.randn(64, C, 3, 3, device=dev()) / 24
+    b = torch.randn(64, device=dev())
+    go = torch.randn(B, 64, H, W, device=dev())
+    runs = []
+    for i in range(3):
+        ts = [v.clone().requires_grad_() for v in (x, off, msk, w, b)]
+        dcn.dcn_v2_conv(*ts, 1, 1, 1, dg).backward(go)
+        runs.append([v.grad.clone() for v in ts])
+        torch.zeros(64 << 20, device=dev())                  # perturb the cache / timing state between runs
+    for r in runs[1:]:
+        for i in range(5):
+            assert torch.equal(r[i], runs[0][i]), GRADS[i]
+
+
+def test_grad_input_scale_invariance(dcn):
+    """The fixed-point scale follows the data: gradients 1e-12 .. 1e12 keep the same relative accuracy."""
+    from gpu_util import dev
+    torch.manual_seed(6)
+    B, C, H, W, dg = 1, 64, 32, 48, 8
+    x = torch.randn(B, C, H, W, device=dev())
+    off = 2 * torch.randn(B, 2 * dg * 9, H, W, device=dev())
+    msk = torch.sigmoid(torch.randn(B, dg * 9, H, W, device=dev()))
+    w = torch.randn(64, C, 3, 3, device=dev()) / 24
+    b = torch.randn(64, device=dev())
+    go = torch.randn(B, 64, H, W, device=dev())
+    ref = None
+    for sc in (1.0, 1e-12, 1e12, 2.0 ** -100):
+        xi = x.clone().requires_grad_()
+        dcn.dcn_v2_conv(xi, off, msk, w, b, 1, 1, 1, dg).backward(go * sc)
+        g = xi.grad.double() / sc
+        if ref is None:
+            ref = g
+        else:
+            assert float((g - ref).abs().max() / ref.abs().max()) < 2e-6, sc
+
+
+def test_nonfinite_grad_output_reaches_grad_input(dcn):
+    """An Inf / NaN in grad_output must surface in grad_input (AMP GradScaler's overflow check), not vanish in the
+    fixed-point conversion."""
+    from gpu_util import dev
+    torch.manual_seed(7)
+    B, C, H, W, dg = 1, 64, 24, 32, 8
+    x = torch.randn(B, C, H, W, device=dev())
+    off = torch.randn(B, 2 * dg * 9, H, W, device=dev())
+    msk = torch.sigmoid(torch.randn(B, dg * 9, H, W, device=dev()))
+    w = torch.randn(64, C, 3, 3, device=dev()) / 24
+    b = torch.randn(64, device=dev())
+    for bad in (float("inf"), float("nan")):
+        go = torch.randn(B, 64, H, W, device=dev())
+        go[0, 3, 10, 17] = bad
+        xi = x.clone().requires_grad_()
+        dcn.dcn_v2_conv(xi, off, msk, w, b, 1, 1, 1, dg).backward(go)
+        assert not bool(torch.isfinite(xi.grad).all()), bad
+        assert bool(torch.isfinite(xi.grad[0, :, 20:, :8]).all())      # far from the bad pixel: untouched
+
+
 def test_reductions_are_bit_reproducible(dcn):
     """grad_offset / grad_mask / grad_weight / grad_bias use fixed-order reductions."""
     from gpu_util import dev
