@@ -26,6 +26,12 @@ class DcnGeom(ctypes.Structure):
 
 EBFI_DCN_DETERMINISTIC = 1
 
+
+class DpComm(ctypes.Structure):
+    """`ebfi_dp_comm`: peer mappings of the symmetric all-reduce buffers (parallel.GradComm fills it)."""
+    _fields_ = [("world", c_int), ("rank", c_int), ("peer_base", c_void * 8), ("bytes", c_size)]
+
+
 # name -> (restype, argtypes); must list every symbol include/ebfi_b200.h declares
 _GEOM_P = ctypes.POINTER(DcnGeom)
 SIGNATURES = {
@@ -37,6 +43,9 @@ SIGNATURES = {
     "ebfi_dcnv2_forward_workspace_bytes": (c_size, [_GEOM_P]),
     "ebfi_dcnv2_forward": (c_int, [c_void, _GEOM_P] + [c_void] * 6 + [c_void, c_size]),
     "ebfi_dcnv2_backward": (c_int, [c_void, _GEOM_P] + [c_void] * 11 + [c_void, c_size]),
+    "ebfi_dcnv2_backward_dp": (c_int, [c_void, _GEOM_P] + [c_void] * 11 + [c_void, c_size, ctypes.POINTER(DpComm)]),
+    "ebfi_dp_comm_bytes": (c_size, [c_size]),
+    "ebfi_dp_allreduce_sum": (c_int, [c_void, ctypes.POINTER(DpComm), c_void, c_size, c_void, c_size]),
     "ebfi_dcnv2_forward_packed": (c_int, [c_void, _GEOM_P] + [c_void] * 6 + [c_void, c_size]),
     "ebfi_dcnv2_backward_packed": (c_int, [c_void, _GEOM_P] + [c_void] * 9 + [c_void, c_size]),
     "ebfi_fac_forward": (c_int, [c_void] * 4 + [c_int] * 5),
@@ -73,7 +82,7 @@ def load():
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)      # AttributeError here = header/library mismatch
         fn.restype, fn.argtypes = res, args
-    if lib.ebfi_abi_version() != 2:
+    if lib.ebfi_abi_version() != 3:
         raise RuntimeError("libebfi_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -22,6 +22,7 @@
 // sampling window (im2col_cuda.cu:180), per-corner bounds (:38-48), the coordinate weights
 // (:82-123), and the pad_h-for-both-paddings quirk of the grad_input scatter (:368).
 #include "dcn_common.cuh"
+#include "dp_comm.cuh"
 
 #include <algorithm>
 
@@ -35,7 +36,7 @@ int backward_box_splits(const DcnDims &d);
 size_t backward_box_scratch_bytes(const DcnDims &d);
 int backward_box(cudaStream_t st, const DcnDims &d, const float *input, const float *weight, const float *offset,
                  const float *mask, const float *gout, float *gin, float *goff, float *gmask, float *gw, float *gb,
-                 float *gw_part, float *gb_part, void *scratch);
+                 float *gw_part, float *gb_part, void *scratch, const ebfi_dp::View *dp);
 int backward_tc_splits(const DcnDims &d);
 size_t backward_tc_scratch_bytes(const DcnDims &d);
 int backward_tc(cudaStream_t st, const DcnDims &d, const float *input, const float *weight, const float *offset,
@@ -499,10 +500,14 @@ static int run_backward(void *stream, const DcnDims &d_in, const float *input, c
                         const float *offset, const float *mask,
                         const float *grad_output, float *grad_input, float *grad_offset,
                         float *grad_mask, float *grad_weight, float *grad_bias,
-                        void *workspace, size_t workspace_bytes)
+                        void *workspace, size_t workspace_bytes, const ebfi_dp_comm *comm = nullptr)
 {
     EBFI_REQUIRE(input && weight && offset && mask && grad_output && grad_input && grad_offset &&
                  grad_mask && grad_weight && grad_bias, "dcn_backward: null pointer");
+    ebfi_dp::View dpv{};
+    if (comm)
+        if (int rc = ebfi_dp::make_view(comm, (size_t)d_in.Co * d_in.C * d_in.KK + d_in.Co, dpv)) return rc;
+    const ebfi_dp::View *dp = comm ? &dpv : nullptr;
     cudaStream_t st = ebfi::as_stream(stream);
     DcnDims d = d_in;
     const char *impl = getenv("EBFI_DCN_IMPL");
@@ -537,7 +542,7 @@ static int run_backward(void *stream, const DcnDims &d_in, const float *input, c
     if (S_box > 0) {
         // writes all five gradients, including its own fixed-order reduction of the weight-gradient partials
         return backward_box(st, d, input, weight, offset, mask, grad_output, grad_input, grad_offset, grad_mask,
-                            grad_weight, grad_bias, gw_part, gb_part, scratch);
+                            grad_weight, grad_bias, gw_part, gb_part, scratch, dp);
     } else if (S_tc > 0) {
         // tensor-core path (dcn_bwd_tc.cu): cpg == 8, Cout == 64
         if (int rc = backward_tc(st, d, input, weight, offset, mask, grad_output, grad_input, grad_offset, grad_mask,
@@ -571,6 +576,7 @@ static int run_backward(void *stream, const DcnDims &d_in, const float *input, c
     const int n = (int)(n_w + n_b);
     dcn_reduce_partials<<<ceil_div(n, 256), 256, 0, st>>>(gw_part, gb_part, grad_weight, grad_bias, S, (int)n_w, (int)n_b);
     EBFI_LAUNCH_OK("dcn_reduce_partials");
+    if (dp) return ebfi_dp::allreduce_sum(st, *dp, grad_weight, n_w, grad_bias, n_b);
     return EBFI_OK;
 }
 
@@ -594,6 +600,20 @@ int ebfi_dcnv2_backward(void *stream, const ebfi_dcn_geom *q, const float *input
     if (int rc = fill_dims(q, d)) return rc;
     return run_backward(stream, d, input, weight, offset, mask, grad_output, grad_input, grad_offset, grad_mask,
                         grad_weight, grad_bias, workspace, workspace_bytes);
+}
+
+int ebfi_dcnv2_backward_dp(void *stream, const ebfi_dcn_geom *q, const float *input, const float *weight,
+                           const float *bias, const float *offset, const float *mask,
+                           const float *grad_output, float *grad_input, float *grad_offset,
+                           float *grad_mask, float *grad_weight, float *grad_bias,
+                           void *workspace, size_t workspace_bytes, const ebfi_dp_comm *comm)
+{
+    (void)bias;
+    DcnDims d{};
+    if (int rc = fill_dims(q, d)) return rc;
+    EBFI_REQUIRE(comm != nullptr, "dcn_backward_dp: null communicator");
+    return run_backward(stream, d, input, weight, offset, mask, grad_output, grad_input, grad_offset, grad_mask,
+                        grad_weight, grad_bias, workspace, workspace_bytes, comm);
 }
 
 int ebfi_dcnv2_forward_packed(void *stream, const ebfi_dcn_geom *q, const float *input, const float *weight,

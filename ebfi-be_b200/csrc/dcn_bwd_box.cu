@@ -32,6 +32,7 @@
 // so that overflow checks on grad_input (AMP GradScaler) still fire.
 #include "dcn_box.cuh"
 #include "dcn_common.cuh"
+#include "dp_comm.cuh"
 #include "tma.cuh"
 #include "umma.cuh"
 
@@ -691,8 +692,13 @@ dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__rest
 
 // grad_weight[co][k] = sum over the slots of part[slot][k][co], grad_bias likewise: fixed order (four interleaved slot
 // quarters per element, combined in a fixed order), coalesced reads along co.
-__global__ void dcn_box_reduce_partials(const float *__restrict__ gw_part, const float *__restrict__ gb_part,
-                                        float *__restrict__ gw, float *__restrict__ gb, int nslot, int Kdim)
+// DP: the data-parallel all-reduce of the two gradients is part of this kernel — the local sums go to the rank's
+// symmetric buffer, the block exchanges flags with the same block of every peer over NVLink and adds the peers' sums in
+// rank order (dp_comm.cuh). No NCCL call, no bucket copies, one launch.
+template <bool DP>
+__global__ void __launch_bounds__(256)
+dcn_box_reduce_partials(const float *__restrict__ gw_part, const float *__restrict__ gb_part,
+                        float *__restrict__ gw, float *__restrict__ gb, int nslot, int Kdim, ebfi_dp::View v)
 {
     const int e = blockIdx.x * (blockDim.x / 4) + (threadIdx.x >> 2), q = threadIdx.x & 3;
     const int n_w = Kdim * CO;
@@ -706,10 +712,18 @@ __global__ void dcn_box_reduce_partials(const float *__restrict__ gw_part, const
     a = (q & 1) ? b1 + a : a + b1;           // (q0 + q1), (q2 + q3): the same operand order in both lanes
     const float b2 = __shfl_xor_sync(0xffffffffu, a, 2);
     a = (q & 2) ? b2 + a : a + b2;
+    unsigned epoch = 0;
+    if (DP) {
+        epoch = ebfi_dp::epoch_of_launch(v);
+        if (q == 0 && e < n_w + CO) ebfi_dp::data(v, v.rank, epoch & 1u)[e] = a;
+        ebfi_dp::publish_and_wait(v, epoch, (int)blockIdx.x);
+        if (q == 0 && e < n_w + CO) a = ebfi_dp::gather_sum(v, epoch, (size_t)e);
+    }
     if (q == 0) {
         if (e < n_w) gw[(size_t)(e % CO) * Kdim + e / CO] = a;
         else if (e < n_w + CO) gb[e - n_w] = a;
     }
+    if (DP) ebfi_dp::finish_launch(v, epoch);
 }
 
 // W^T images for the bulk copies: [group][hi | lo][N1 rows k'][CO] bf16 in the K-major core-matrix order,
@@ -839,7 +853,7 @@ size_t backward_box_scratch_bytes(const DcnDims &d)
 
 int backward_box(cudaStream_t st, const DcnDims &d, const float *input, const float *weight, const float *offset,
                  const float *mask, const float *gout, float *gin, float *goff, float *gmask, float *gw, float *gb,
-                 float *gw_part, float *gb_part, void *scratch)
+                 float *gw_part, float *gb_part, void *scratch, const ebfi_dp::View *dp)
 {
     BoxBwdPlan pl{};
     if (!make_plan(d, pl)) return EBFI_ERR_UNSUPPORTED;
@@ -885,8 +899,15 @@ int backward_box(cudaStream_t st, const DcnDims &d, const float *input, const fl
     dcn_gin_collect<<<cgrid, 256, 0, st>>>(pbox, gin_blk, gin, d, pl);
     EBFI_LAUNCH_OK("dcn_gin_collect");
     const int Kdim = d.C * d.KK;
-    dcn_box_reduce_partials<<<ceil_div(Kdim * CO + CO, 64), 256, 0, st>>>(gw_part, gb_part, gw, gb, 2 * (int)grid.x, Kdim);
+    const int rblocks = ceil_div(Kdim * CO + CO, 64);
+    const bool fused = dp && rblocks <= ebfi_dp::MAX_BLOCKS;      // world == 1 runs the same kernel (no peers to wait for)
+    if (fused)
+        dcn_box_reduce_partials<true><<<rblocks, 256, 0, st>>>(gw_part, gb_part, gw, gb, 2 * (int)grid.x, Kdim, *dp);
+    else
+        dcn_box_reduce_partials<false><<<rblocks, 256, 0, st>>>(gw_part, gb_part, gw, gb, 2 * (int)grid.x, Kdim, ebfi_dp::View{});
     EBFI_LAUNCH_OK("dcn_box_reduce_partials");
+    if (dp && !fused)                           // more reduction blocks than flag slots: separate exchange kernel
+        return ebfi_dp::allreduce_sum(st, *dp, gw, (size_t)Kdim * CO, gb, (size_t)CO);
     return EBFI_OK;
 }
 

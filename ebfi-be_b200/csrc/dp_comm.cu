@@ -1,0 +1,70 @@
+// dp_comm.cu — host side of the peer-memory all-reduce (dp_comm.cuh) and its stand-alone kernel: the data-parallel
+// weight-gradient sum of SURVEY §8e for the paths that do not fuse it into their own reduction kernel.
+#include "dp_comm.cuh"
+
+#include <algorithm>
+
+namespace ebfi_dp {
+
+int make_view(const ebfi_dp_comm *c, size_t n_floats, View &v)
+{
+    EBFI_REQUIRE(c != nullptr, "dp: null communicator");
+    EBFI_REQUIRE(c->world >= 1 && c->world <= MAX_WORLD && c->rank >= 0 && c->rank < c->world,
+                 "dp: bad world / rank (%d / %d; at most %d ranks)", c->world, c->rank, MAX_WORLD);
+    EBFI_REQUIRE(c->bytes >= bytes_for(n_floats), "dp: symmetric allocation of %zu bytes < %zu needed for %zu floats",
+                 c->bytes, bytes_for(n_floats), n_floats);
+    v.world = c->world; v.rank = c->rank;
+    for (int q = 0; q < MAX_WORLD; ++q) {
+        v.base[q] = static_cast<unsigned char *>(q < c->world ? c->peer_base[q] : nullptr);
+        EBFI_REQUIRE(q >= c->world || (v.base[q] && (reinterpret_cast<uintptr_t>(v.base[q]) & 255u) == 0),
+                     "dp: peer_base[%d] is null or not 256-byte aligned", q);
+    }
+    v.cap = (c->bytes - HDR_BYTES) / (2 * sizeof(float));
+    return EBFI_OK;
+}
+
+namespace {
+
+// a[0, na) and b[0, nb) (logically concatenated) <- sum over ranks, in place
+__global__ void __launch_bounds__(256) dp_allreduce_kernel(View v, float *a, size_t na, float *b, size_t nb, size_t chunk)
+{
+    const unsigned epoch = epoch_of_launch(v);
+    const size_t n = na + nb, e0 = (size_t)blockIdx.x * chunk, e1 = e0 + chunk < n ? e0 + chunk : n;
+    float *mine = data(v, v.rank, epoch & 1u);
+    for (size_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) mine[e] = e < na ? a[e] : b[e - na];
+    publish_and_wait(v, epoch, (int)blockIdx.x);
+    for (size_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+        const float s = gather_sum(v, epoch, e);
+        if (e < na) a[e] = s; else b[e - na] = s;
+    }
+    finish_launch(v, epoch);
+}
+
+}  // namespace
+
+int allreduce_sum(cudaStream_t st, const View &v, float *a, size_t na, float *b, size_t nb)
+{
+    const size_t n = na + nb;
+    if (n == 0) return EBFI_OK;
+    const size_t nblk = std::min<size_t>(MAX_BLOCKS, ebfi::ceil_div(n, (size_t)256));
+    const size_t chunk = ebfi::ceil_div(n, nblk);
+    dp_allreduce_kernel<<<(unsigned)ebfi::ceil_div(n, chunk), 256, 0, st>>>(v, a, na, b, nb, chunk);
+    EBFI_LAUNCH_OK("dp_allreduce_kernel");
+    return EBFI_OK;
+}
+
+}  // namespace ebfi_dp
+
+extern "C" {
+
+size_t ebfi_dp_comm_bytes(size_t n_floats) { return ebfi_dp::bytes_for(n_floats); }
+
+int ebfi_dp_allreduce_sum(void *stream, const ebfi_dp_comm *comm, float *a, size_t na, float *b, size_t nb)
+{
+    EBFI_REQUIRE((a || na == 0) && (b || nb == 0), "dp_allreduce: null pointer");
+    ebfi_dp::View v{};
+    if (int rc = ebfi_dp::make_view(comm, na + nb, v)) return rc;
+    return ebfi_dp::allreduce_sum(ebfi::as_stream(stream), v, a, na, b, nb);
+}
+
+}  // extern "C"

@@ -76,11 +76,54 @@ def allreduce_weight_grads(grads, group=None, average=False, async_op=False):
     return handle if async_op else handle.wait()
 
 
-def dcn_backward_data_parallel(backward_fn, input, weight, bias, offset, mask, grad_output, *geom, group=None):
+class GradComm:
+    """Peer-memory communicator for the fused weight-gradient all-reduce (include/ebfi_b200.h `ebfi_dp_comm`,
+    csrc/dp_comm.cuh): one symmetric allocation per rank, mapped into every peer by torch's symmetric memory
+    (plumbing only — the exchange itself runs inside this repo's kernels over NVLink, no NCCL call per step).
+    `n_floats` = the largest number of values all-reduced by one call (DCNv2: weight.numel() + bias.numel()).
+    Collective constructor: every rank of `group` must create it at the same point. CUDA + NCCL group only."""
+
+    def __init__(self, n_floats, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib as L
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise RuntimeError("GradComm: at most 8 ranks (one NVSwitch domain)")
+        nbytes = int(L.load().ebfi_dp_comm_bytes(int(n_floats)))
+        self.n_floats = int(n_floats)
+        self.buf = symm.empty((nbytes + 3) // 4, dtype=torch.float32, device=device)
+        self.buf.zero_()                                    # epoch counter and flags start at 0
+        self.handle = symm.rendezvous(self.buf, group.group_name if hasattr(group, "group_name") else group)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                                 # every rank's zero fill is done before anyone signals
+        ptrs = list(self.handle.buffer_ptrs)
+        self.struct = L.DpComm(self.world, self.rank, (L.c_void * 8)(*(ptrs + [None] * (8 - len(ptrs)))), nbytes)
+
+    def allreduce_(self, a, b=None):
+        """In place: `a` (and `b`) become the sums over all ranks — one kernel of this repo, on the current stream."""
+        from . import _lib as L
+        n = a.numel() + (b.numel() if b is not None else 0)
+        if n > self.n_floats:
+            raise RuntimeError(f"GradComm: {n} values > capacity {self.n_floats}")
+        for t in (a, b):
+            if t is not None and not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise RuntimeError("GradComm.allreduce_: contiguous float32 CUDA tensors only")
+        L.check(L.load().ebfi_dp_allreduce_sum(L.stream_ptr(a.device), self.struct, L.ptr(a), a.numel(),
+                                               L.ptr(b) if b is not None else None, b.numel() if b is not None else 0),
+                "dp_allreduce_sum")
+        return a, b
+
+
+def dcn_backward_data_parallel(backward_fn, input, weight, bias, offset, mask, grad_output, *geom, group=None, comm=None):
     """Run `backward_fn` (signature of `_ext.dcn_v2_backward`) on this rank's batch shard and
     all-reduce grad_weight / grad_bias. Returns the shard's grad_input / grad_offset / grad_mask
-    and the GLOBAL grad_weight / grad_bias."""
+    and the GLOBAL grad_weight / grad_bias. With `comm` (a GradComm) the all-reduce happens inside the backward's own
+    reduction kernel over NVLink peer memory; without it, one flat-bucket collective of torch.distributed follows."""
     x, off, msk, go = shard_batch(input, offset, mask, grad_output)
+    if comm is not None:
+        return tuple(backward_fn(x.contiguous(), weight, bias, off.contiguous(), msk.contiguous(), go.contiguous(),
+                                 *geom, comm=comm))
     g_in, g_off, g_msk, g_w, g_b = backward_fn(x.contiguous(), weight, bias, off.contiguous(),
                                                 msk.contiguous(), go.contiguous(), *geom)
     allreduce_weight_grads([g_w, g_b], group=group)

@@ -43,7 +43,7 @@ extern "C" {
 #define EBFI_ERR_WORKSPACE   -3   /* workspace too small (query the *_workspace_bytes fn) */
 #define EBFI_ERR_UNSUPPORTED -4   /* valid request this build does not implement */
 
-#define EBFI_ABI_VERSION 2
+#define EBFI_ABI_VERSION 3
 
 /* ---- library ---------------------------------------------------------------- */
 
@@ -259,6 +259,38 @@ int ebfi_frame_to_lap(void *stream, const float *frames, float *lap, int batch, 
  * dark (B, 1, H, W); scratch (B, H, W) fp32. Bit-identical to OpenCV. */
 int ebfi_frame_to_dcp(void *stream, const float *frames, float *dark, float *scratch,
                       int batch, int height, int width, int window);
+
+/* ---- data-parallel weight-gradient all-reduce over NVLink peer memory -------------------------------------------
+ * batch-sharded training has exactly one exchange on this path, the sum of DCNv2's grad_weight /
+ * grad_bias over the ranks (dcn_v2_cuda.cu:203-208 produces them per rank; the reference never reduces them,
+ * train_ours.py:250-272 runs every backward under no_sync). Instead of a separate NCCL call the reduction is done by
+ * the kernel that produces the gradients: every rank maps one symmetric allocation of each peer (torch symmetric
+ * memory, cudaIpc, ... — the host's plumbing), the kernel publishes its local sums there, exchanges per-block flags
+ * and adds the peers' values in rank order (identical bits on every rank and run to run). See csrc/dp_comm.cuh.
+ *
+ * peer_base[q]: this process's mapping of rank q's allocation (peer_base[rank] = the local one), 256-byte aligned,
+ * `bytes` >= ebfi_dp_comm_bytes(n) each, zero-filled ONCE before the first call (and a host barrier after the fill).
+ * Every rank must issue the same sequence of calls on the communicator. world <= 8; world == 1 is a plain copy. */
+typedef struct ebfi_dp_comm {
+    int world, rank;
+    void *peer_base[8];
+    size_t bytes;
+} ebfi_dp_comm;
+
+/* Symmetric bytes per rank for all-reducing up to n_floats values per call. */
+size_t ebfi_dp_comm_bytes(size_t n_floats);
+
+/* In place: a[0, na) and b[0, nb) become the sums over all ranks (one kernel, no NCCL). */
+int ebfi_dp_allreduce_sum(void *stream, const ebfi_dp_comm *comm, float *a, size_t na, float *b, size_t nb);
+
+/* ebfi_dcnv2_backward whose grad_weight / grad_bias are the sums over all ranks of `comm`; on the tensor-core box path
+ * the exchange is fused into the kernel that reduces the per-CTA partials. The other three gradients are per rank. */
+int ebfi_dcnv2_backward_dp(void *stream, const ebfi_dcn_geom *g,
+                           const float *input, const float *weight, const float *bias,
+                           const float *offset, const float *mask, const float *grad_output,
+                           float *grad_input, float *grad_offset, float *grad_mask,
+                           float *grad_weight, float *grad_bias,
+                           void *workspace, size_t workspace_bytes, const ebfi_dp_comm *comm);
 
 /* ---- self test --------------------------------------------------------------- */
 
