@@ -188,6 +188,19 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev, pg_options=opts)
         _bind_to_gpu_numa_node(torch, dev)
     ebfi_be_b200._lib.load()
+    # Data-parallel weight-gradient sum (the only exchange on the path): fused into the DCN backward's own reduction
+    # kernel over NVLink peer memory (parallel.GradComm / csrc/dp_comm.cuh); `--nccl-allreduce` keeps the separate
+    # flat-bucket NCCL collective of round 1 for comparison.
+    comm, comm_err = None, None
+    if world > 1 and not args.nccl_allreduce:
+        try:
+            comm = parallel.GradComm(C * C * 9 + C, dev)
+        except Exception as e:      # no peer mapping on this box: say so in the line and use NCCL
+            comm_err = f"{type(e).__name__}: {e}"[:200]
+        ok = torch.tensor([0 if comm is None else 1], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok) == 0:
+            comm = None
     host = make_inputs(torch, dev, 1234 + rank)
     d = {k: v.to(dev) for k, v in host.items()}
     geom = (3, 3, 1, 1, 1, 1, 1, 1, DG)
@@ -203,7 +216,7 @@ def run_ours(args):
     # the eager calls.
     ops = {
         "dcn_fwd": lambda: _ext.dcn_v2_forward(d["x"], d["w"], d["b"], d["off"], d["msk"], *geom),
-        "dcn_bwd": lambda: _ext.dcn_v2_backward(d["x"], d["w"], d["b"], d["off"], d["msk"], d["go_d"], *geom),
+        "dcn_bwd": lambda: _ext.dcn_v2_backward(d["x"], d["w"], d["b"], d["off"], d["msk"], d["go_d"], *geom, comm=comm, defer=comm is not None),
         "fac_fwd": lambda: kc.forward(d["xi"], d["ker"], K_FAC, out_f),
         "fac_bwd": lambda: kc.backward(d["xi"], d["ker"], K_FAC, d["go_f"], gi_f, gk_f),
     }
@@ -226,13 +239,17 @@ def run_ours(args):
         grads = run("dcn_bwd")
         # data-parallel weight-gradient all-reduce (the only collective on the path): ONE flat bucket, issued
         # asynchronously so that its latency hides under the FAC kernels; completed before the step ends
-        pending = parallel.allreduce_weight_grads(grads[3:5], async_op=True) if world > 1 else None
+        pending = parallel.allreduce_weight_grads(grads[3:5], async_op=True) if (world > 1 and comm is None) else None
         mark()
         run("fac_fwd")
         mark()
         run("fac_bwd")
         mark()                      # kernel intervals end here; the collective's completion is timed separately
-        if pending is not None:
+        if comm is not None:
+            # second half of the fused exchange: the backward's reduction kernel published this rank's sums ~0.9 ms ago;
+            # one tiny kernel waits for the peers' flags and adds their values in rank order
+            comm.complete(grads[3], grads[4])
+        elif pending is not None:
             pending.wait()
         mark()
 
@@ -293,7 +310,10 @@ def run_ours(args):
                                                 1, 1, 1, DG, dcn_res)
         if world > 1:   # weight-gradient all-reduce; the reduced values are what a trainer would read
             gw, gb = keep[1][3].grad, keep[1][4].grad
-            dist.all_reduce(gw); dist.all_reduce(gb)
+            if comm is not None:
+                comm.allreduce_(gw, gb)
+            else:
+                dist.all_reduce(gw); dist.all_reduce(gb)
         pipe.fac_forward_backward(pin["xi"], pin["ker"], pin["go_f"], K_FAC,
                                   pin_out["out_f"], pin_out["g_xi"], pin_out["g_ker"])
         s_out.synchronize()
@@ -458,7 +478,11 @@ def run_ours(args):
                    "pixels_per_step_per_gpu": int(MPIX_PER_STEP * 1e6), "parallelism": f"dp{world} (batch-sharded)",
                    "l2": "inputs larger than L2: each step streams 5.4 GB of FAC tensors (>> 126 MB L2) "
                          "between consecutive DCN calls; breakdown.cold_ms flushes L2 explicitly",
-                   "collective": "one flat-bucket NCCL all-reduce of DCN grad_weight+grad_bias per step, overlapped with the FAC kernels" if world > 1 else "none"},
+                   "collective": ("none" if world == 1 else
+                                  "DCN grad_weight+grad_bias all-reduce fused into dcn_box_reduce_partials: the kernel publishes the rank's "
+                                  "sums to NVLink peer memory, a tiny kernel after the FAC calls adds the peers' (no NCCL call)" if comm is not None else
+                                  "one flat-bucket NCCL all-reduce of DCN grad_weight+grad_bias per step, overlapped with the FAC kernels"
+                                  + (f" (peer-memory communicator unavailable: {comm_err})" if comm_err else ""))},
         "roofline": {"bound": "hbm", "kernel": "fac_bwd_march<5,4,ring> (FAC fused backward)",
                      "achieved": round(gbs(op_bytes[dom], op_ms[dom]), 1), "peak": peak, "unit": "GB/s",
                      "frac": round(gbs(op_bytes[dom], op_ms[dom]) / peak, 4), "traffic": traffic,
@@ -733,6 +757,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="eager operator calls instead of CUDA-graph replays")
+    ap.add_argument("--nccl-allreduce", action="store_true",
+                    help="N > 1: all-reduce the weight gradients with a separate NCCL collective instead of the fused peer-memory exchange")
     ap.add_argument("--no-model", action="store_true", help="skip the full-model legs (BASELINE configs[3], configs[4])")
     ap.add_argument("--kernels-only", action="store_true",
                     help="profiling runs: skip the e2e, cold-breakdown and CPU-baseline legs")

@@ -43,9 +43,11 @@ SIGNATURES = {
     "ebfi_dcnv2_forward_workspace_bytes": (c_size, [_GEOM_P]),
     "ebfi_dcnv2_forward": (c_int, [c_void, _GEOM_P] + [c_void] * 6 + [c_void, c_size]),
     "ebfi_dcnv2_backward": (c_int, [c_void, _GEOM_P] + [c_void] * 11 + [c_void, c_size]),
-    "ebfi_dcnv2_backward_dp": (c_int, [c_void, _GEOM_P] + [c_void] * 11 + [c_void, c_size, ctypes.POINTER(DpComm)]),
+    "ebfi_dcnv2_backward_dp": (c_int, [c_void, _GEOM_P] + [c_void] * 11 + [c_void, c_size, ctypes.POINTER(DpComm), c_int]),
     "ebfi_dp_comm_bytes": (c_size, [c_size]),
     "ebfi_dp_allreduce_sum": (c_int, [c_void, ctypes.POINTER(DpComm), c_void, c_size, c_void, c_size]),
+    "ebfi_dp_publish": (c_int, [c_void, ctypes.POINTER(DpComm), c_void, c_size, c_void, c_size]),
+    "ebfi_dp_complete": (c_int, [c_void, ctypes.POINTER(DpComm), c_void, c_size, c_void, c_size]),
     "ebfi_dcnv2_forward_packed": (c_int, [c_void, _GEOM_P] + [c_void] * 6 + [c_void, c_size]),
     "ebfi_dcnv2_backward_packed": (c_int, [c_void, _GEOM_P] + [c_void] * 9 + [c_void, c_size]),
     "ebfi_fac_forward": (c_int, [c_void] * 4 + [c_int] * 5),

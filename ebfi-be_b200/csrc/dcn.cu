@@ -36,7 +36,7 @@ int backward_box_splits(const DcnDims &d);
 size_t backward_box_scratch_bytes(const DcnDims &d);
 int backward_box(cudaStream_t st, const DcnDims &d, const float *input, const float *weight, const float *offset,
                  const float *mask, const float *gout, float *gin, float *goff, float *gmask, float *gw, float *gb,
-                 float *gw_part, float *gb_part, void *scratch, const ebfi_dp::View *dp);
+                 float *gw_part, float *gb_part, void *scratch, const ebfi_dp::View *dp, bool dp_defer);
 int backward_tc_splits(const DcnDims &d);
 size_t backward_tc_scratch_bytes(const DcnDims &d);
 int backward_tc(cudaStream_t st, const DcnDims &d, const float *input, const float *weight, const float *offset,
@@ -500,7 +500,7 @@ static int run_backward(void *stream, const DcnDims &d_in, const float *input, c
                         const float *offset, const float *mask,
                         const float *grad_output, float *grad_input, float *grad_offset,
                         float *grad_mask, float *grad_weight, float *grad_bias,
-                        void *workspace, size_t workspace_bytes, const ebfi_dp_comm *comm = nullptr)
+                        void *workspace, size_t workspace_bytes, const ebfi_dp_comm *comm = nullptr, bool dp_defer = false)
 {
     EBFI_REQUIRE(input && weight && offset && mask && grad_output && grad_input && grad_offset &&
                  grad_mask && grad_weight && grad_bias, "dcn_backward: null pointer");
@@ -542,7 +542,7 @@ static int run_backward(void *stream, const DcnDims &d_in, const float *input, c
     if (S_box > 0) {
         // writes all five gradients, including its own fixed-order reduction of the weight-gradient partials
         return backward_box(st, d, input, weight, offset, mask, grad_output, grad_input, grad_offset, grad_mask,
-                            grad_weight, grad_bias, gw_part, gb_part, scratch, dp);
+                            grad_weight, grad_bias, gw_part, gb_part, scratch, dp, dp_defer);
     } else if (S_tc > 0) {
         // tensor-core path (dcn_bwd_tc.cu): cpg == 8, Cout == 64
         if (int rc = backward_tc(st, d, input, weight, offset, mask, grad_output, grad_input, grad_offset, grad_mask,
@@ -576,7 +576,7 @@ static int run_backward(void *stream, const DcnDims &d_in, const float *input, c
     const int n = (int)(n_w + n_b);
     dcn_reduce_partials<<<ceil_div(n, 256), 256, 0, st>>>(gw_part, gb_part, grad_weight, grad_bias, S, (int)n_w, (int)n_b);
     EBFI_LAUNCH_OK("dcn_reduce_partials");
-    if (dp) return ebfi_dp::allreduce_sum(st, *dp, grad_weight, n_w, grad_bias, n_b);
+    if (dp) return ebfi_dp::allreduce_sum(st, *dp, grad_weight, n_w, grad_bias, n_b, dp_defer ? 1 : 0);
     return EBFI_OK;
 }
 
@@ -606,14 +606,14 @@ int ebfi_dcnv2_backward_dp(void *stream, const ebfi_dcn_geom *q, const float *in
                            const float *bias, const float *offset, const float *mask,
                            const float *grad_output, float *grad_input, float *grad_offset,
                            float *grad_mask, float *grad_weight, float *grad_bias,
-                           void *workspace, size_t workspace_bytes, const ebfi_dp_comm *comm)
+                           void *workspace, size_t workspace_bytes, const ebfi_dp_comm *comm, int defer)
 {
     (void)bias;
     DcnDims d{};
     if (int rc = fill_dims(q, d)) return rc;
     EBFI_REQUIRE(comm != nullptr, "dcn_backward_dp: null communicator");
     return run_backward(stream, d, input, weight, offset, mask, grad_output, grad_input, grad_offset, grad_mask,
-                        grad_weight, grad_bias, workspace, workspace_bytes, comm);
+                        grad_weight, grad_bias, workspace, workspace_bytes, comm, defer != 0);
 }
 
 int ebfi_dcnv2_forward_packed(void *stream, const ebfi_dcn_geom *q, const float *input, const float *weight,

@@ -692,10 +692,10 @@ dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__rest
 
 // grad_weight[co][k] = sum over the slots of part[slot][k][co], grad_bias likewise: fixed order (four interleaved slot
 // quarters per element, combined in a fixed order), coalesced reads along co.
-// DP: the data-parallel all-reduce of the two gradients is part of this kernel — the local sums go to the rank's
-// symmetric buffer, the block exchanges flags with the same block of every peer over NVLink and adds the peers' sums in
-// rank order (dp_comm.cuh). No NCCL call, no bucket copies, one launch.
-template <bool DP>
+// DP: the first half of the data-parallel all-reduce of the two gradients is part of this kernel — the local sums also
+// go to the rank's symmetric buffer and the last block hands them to the peers over NVLink (dp_comm.cuh: no NCCL
+// call, no bucket copies). The outputs hold the local sums until ebfi_dp_complete adds the peers' in rank order.
+template <int DP>
 __global__ void __launch_bounds__(256)
 dcn_box_reduce_partials(const float *__restrict__ gw_part, const float *__restrict__ gb_part,
                         float *__restrict__ gw, float *__restrict__ gb, int nslot, int Kdim, ebfi_dp::View v)
@@ -715,15 +715,14 @@ dcn_box_reduce_partials(const float *__restrict__ gw_part, const float *__restri
     unsigned epoch = 0;
     if (DP) {
         epoch = ebfi_dp::epoch_of_launch(v);
-        if (q == 0 && e < n_w + CO) ebfi_dp::data(v, v.rank, epoch & 1u)[e] = a;
-        ebfi_dp::publish_and_wait(v, epoch, (int)blockIdx.x);
-        if (q == 0 && e < n_w + CO) a = ebfi_dp::gather_sum(v, epoch, (size_t)e);
+        // in the order of the outputs (grad_weight | grad_bias): ebfi_dp_complete works on those two tensors
+        if (q == 0 && e < n_w + CO) ebfi_dp::data(v, v.rank, epoch & 1u)[e < n_w ? (size_t)(e % CO) * Kdim + e / CO : (size_t)e] = a;
     }
     if (q == 0) {
         if (e < n_w) gw[(size_t)(e % CO) * Kdim + e / CO] = a;
         else if (e < n_w + CO) gb[e - n_w] = a;
     }
-    if (DP) ebfi_dp::finish_launch(v, epoch);
+    if (DP) ebfi_dp::publish(v, epoch);
 }
 
 // W^T images for the bulk copies: [group][hi | lo][N1 rows k'][CO] bf16 in the K-major core-matrix order,
@@ -853,7 +852,7 @@ size_t backward_box_scratch_bytes(const DcnDims &d)
 
 int backward_box(cudaStream_t st, const DcnDims &d, const float *input, const float *weight, const float *offset,
                  const float *mask, const float *gout, float *gin, float *goff, float *gmask, float *gw, float *gb,
-                 float *gw_part, float *gb_part, void *scratch, const ebfi_dp::View *dp)
+                 float *gw_part, float *gb_part, void *scratch, const ebfi_dp::View *dp, bool dp_defer)
 {
     BoxBwdPlan pl{};
     if (!make_plan(d, pl)) return EBFI_ERR_UNSUPPORTED;
@@ -900,14 +899,12 @@ int backward_box(cudaStream_t st, const DcnDims &d, const float *input, const fl
     EBFI_LAUNCH_OK("dcn_gin_collect");
     const int Kdim = d.C * d.KK;
     const int rblocks = ceil_div(Kdim * CO + CO, 64);
-    const bool fused = dp && rblocks <= ebfi_dp::MAX_BLOCKS;      // world == 1 runs the same kernel (no peers to wait for)
-    if (fused)
-        dcn_box_reduce_partials<true><<<rblocks, 256, 0, st>>>(gw_part, gb_part, gw, gb, 2 * (int)grid.x, Kdim, *dp);
+    if (dp)
+        dcn_box_reduce_partials<1><<<rblocks, 256, 0, st>>>(gw_part, gb_part, gw, gb, 2 * (int)grid.x, Kdim, *dp);
     else
-        dcn_box_reduce_partials<false><<<rblocks, 256, 0, st>>>(gw_part, gb_part, gw, gb, 2 * (int)grid.x, Kdim, ebfi_dp::View{});
+        dcn_box_reduce_partials<0><<<rblocks, 256, 0, st>>>(gw_part, gb_part, gw, gb, 2 * (int)grid.x, Kdim, ebfi_dp::View{});
     EBFI_LAUNCH_OK("dcn_box_reduce_partials");
-    if (dp && !fused)                           // more reduction blocks than flag slots: separate exchange kernel
-        return ebfi_dp::allreduce_sum(st, *dp, gw, (size_t)Kdim * CO, gb, (size_t)CO);
+    if (dp && !dp_defer) return ebfi_dp::allreduce_sum(st, *dp, gw, (size_t)Kdim * CO, gb, (size_t)CO, 2);
     return EBFI_OK;
 }
 

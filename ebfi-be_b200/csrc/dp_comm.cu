@@ -25,31 +25,42 @@ int make_view(const ebfi_dp_comm *c, size_t n_floats, View &v)
 
 namespace {
 
-// a[0, na) and b[0, nb) (logically concatenated) <- sum over ranks, in place
-__global__ void __launch_bounds__(256) dp_allreduce_kernel(View v, float *a, size_t na, float *b, size_t nb, size_t chunk)
+// a | b (logically concatenated) -> this rank's symmetric buffer, handed to the peers
+__global__ void __launch_bounds__(256) dp_publish_kernel(View v, const float *a, size_t na, const float *b, size_t nb)
 {
     const unsigned epoch = epoch_of_launch(v);
-    const size_t n = na + nb, e0 = (size_t)blockIdx.x * chunk, e1 = e0 + chunk < n ? e0 + chunk : n;
     float *mine = data(v, v.rank, epoch & 1u);
-    for (size_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) mine[e] = e < na ? a[e] : b[e - na];
-    publish_and_wait(v, epoch, (int)blockIdx.x);
-    for (size_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < na + nb; e += (size_t)gridDim.x * blockDim.x)
+        mine[e] = e < na ? a[e] : b[e - na];
+    publish(v, epoch);
+}
+
+// a | b <- rank-ordered sums of the epoch published last
+__global__ void __launch_bounds__(256) dp_complete_kernel(View v, float *a, size_t na, float *b, size_t nb)
+{
+    const unsigned epoch = epoch_of_launch(v) - 1u;
+    wait_peers(v, epoch);
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < na + nb; e += (size_t)gridDim.x * blockDim.x) {
         const float s = gather_sum(v, epoch, e);
         if (e < na) a[e] = s; else b[e - na] = s;
     }
-    finish_launch(v, epoch);
 }
 
 }  // namespace
 
-int allreduce_sum(cudaStream_t st, const View &v, float *a, size_t na, float *b, size_t nb)
+int allreduce_sum(cudaStream_t st, const View &v, float *a, size_t na, float *b, size_t nb, int mode)
 {
     const size_t n = na + nb;
     if (n == 0) return EBFI_OK;
-    const size_t nblk = std::min<size_t>(MAX_BLOCKS, ebfi::ceil_div(n, (size_t)256));
-    const size_t chunk = ebfi::ceil_div(n, nblk);
-    dp_allreduce_kernel<<<(unsigned)ebfi::ceil_div(n, chunk), 256, 0, st>>>(v, a, na, b, nb, chunk);
-    EBFI_LAUNCH_OK("dp_allreduce_kernel");
+    const unsigned grid = (unsigned)std::min<size_t>(ebfi::ceil_div(n, (size_t)256), (size_t)ebfi::sm_count() * 4);
+    if (mode != 2) {
+        dp_publish_kernel<<<grid, 256, 0, st>>>(v, a, na, b, nb);
+        EBFI_LAUNCH_OK("dp_publish_kernel");
+    }
+    if (mode != 1) {
+        dp_complete_kernel<<<grid, 256, 0, st>>>(v, a, na, b, nb);
+        EBFI_LAUNCH_OK("dp_complete_kernel");
+    }
     return EBFI_OK;
 }
 
@@ -59,12 +70,27 @@ extern "C" {
 
 size_t ebfi_dp_comm_bytes(size_t n_floats) { return ebfi_dp::bytes_for(n_floats); }
 
-int ebfi_dp_allreduce_sum(void *stream, const ebfi_dp_comm *comm, float *a, size_t na, float *b, size_t nb)
+static int dp_call(void *stream, const ebfi_dp_comm *comm, float *a, size_t na, float *b, size_t nb, int mode)
 {
     EBFI_REQUIRE((a || na == 0) && (b || nb == 0), "dp_allreduce: null pointer");
     ebfi_dp::View v{};
     if (int rc = ebfi_dp::make_view(comm, na + nb, v)) return rc;
-    return ebfi_dp::allreduce_sum(ebfi::as_stream(stream), v, a, na, b, nb);
+    return ebfi_dp::allreduce_sum(ebfi::as_stream(stream), v, a, na, b, nb, mode);
+}
+
+int ebfi_dp_allreduce_sum(void *stream, const ebfi_dp_comm *comm, float *a, size_t na, float *b, size_t nb)
+{
+    return dp_call(stream, comm, a, na, b, nb, 0);
+}
+
+int ebfi_dp_publish(void *stream, const ebfi_dp_comm *comm, const float *a, size_t na, const float *b, size_t nb)
+{
+    return dp_call(stream, comm, const_cast<float *>(a), na, const_cast<float *>(b), nb, 1);
+}
+
+int ebfi_dp_complete(void *stream, const ebfi_dp_comm *comm, float *a, size_t na, float *b, size_t nb)
+{
+    return dp_call(stream, comm, a, na, b, nb, 2);
 }
 
 }  // extern "C"

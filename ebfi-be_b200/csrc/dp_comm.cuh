@@ -1,20 +1,22 @@
-// dp_comm.cuh — one-shot all-reduce over NVLink peer memory, usable INSIDE a producing kernel.
+// dp_comm.cuh — all-reduce over NVLink peer memory whose first half runs INSIDE the producing kernel.
 //
 // Every rank owns one symmetric allocation (same layout on all ranks, mapped into every peer's address space by the
 // host: torch symmetric memory / cudaIpc — plumbing, include/ebfi_b200.h `ebfi_dp_comm`):
-//     [0, 256)                     : epoch counter + block ticket (used by the owner only)
-//     [256, 256 + 8*1024*4)        : flags[src rank][block] (uint32), written by the peers
-//     [.., + 2 * capacity * 4)     : data[parity][capacity] (fp32), written by the owner, read by the peers
-// Protocol per kernel launch (all ranks launch the same grid): epoch = counter + 1; a block writes its slice of the
-// local values into data[epoch & 1], fences, stores `epoch` into flags[my rank][block] of every peer (st.release.sys
-// over NVLink), spins until its own flags[q][block] reached `epoch` for every peer q (ld.acquire.sys, local memory),
-// then reads the same slice from every rank's data (ld.relaxed.sys — never from a stale L1 line) and adds them in rank
-// order: the sum is identical on all ranks and run to run. The last block to finish bumps the counter (device side, so
-// the launch can sit in a CUDA graph). Double-buffered data: a rank can run at most one launch ahead of a peer, because
-// launch e+1 needs every peer's flags of e+1, which a peer only sets after its launch e has finished reading.
-// A block only waits for blocks that signal BEFORE they wait, and blocks are dispatched in index order on every GPU:
-// the lowest unfinished block index always completes, so the exchange cannot deadlock; a dead peer trips the
-// watchdog (~4 s) into a trap instead of hanging the GPU.
+//     [0, 256)        : epoch counter + block ticket (used by the owner only)
+//     [256, 512)      : flags[src rank] (uint32), written by the peers
+//     [512, ...)      : data[parity][capacity] (fp32), written by the owner, read by the peers
+// publish (any kernel that produces the values; all ranks issue the same sequence): epoch = counter + 1; every block
+// stores its share of the local values into data[epoch & 1], fences and takes a ticket; the LAST block of the grid
+// issues one system-scope fence (cumulative over the other blocks' stores, which it observed through the ticket), stores
+// `epoch` into flags[my rank] of every peer (st.release.sys over NVLink) and advances the counter — device side, so
+// the launch can sit in a CUDA graph. It never waits.
+// complete (a tiny kernel at the point of use): waits until flags[q] reached the current epoch for every peer q
+// (ld.acquire.sys on local memory), then reads every rank's data (ld.relaxed.sys — never from a stale L1 line) and adds
+// them in rank order: the sums are identical on all ranks and run to run. Between the two halves the NVLink latency and
+// the skew between the ranks hide behind whatever the stream runs (at most one publish outstanding per communicator).
+// Double-buffered data: a rank can be at most one publish ahead of a peer, because its complete(e+1) needs the peer's
+// flag e+1, which the peer only sets after its own complete(e) has been issued. Nothing that waits holds up a
+// publish, so the exchange cannot deadlock; a dead peer trips the watchdog (~4 s) into a trap instead of a hang.
 #pragma once
 #include <cstdint>
 #include <cstdio>
@@ -23,8 +25,8 @@
 
 namespace ebfi_dp {
 
-constexpr int MAX_WORLD = 8, MAX_BLOCKS = 1024;
-constexpr size_t CTR_BYTES = 256, FLAG_BYTES = (size_t)MAX_WORLD * MAX_BLOCKS * 4, HDR_BYTES = CTR_BYTES + FLAG_BYTES;
+constexpr int MAX_WORLD = 8;
+constexpr size_t CTR_BYTES = 256, FLAG_BYTES = 256, HDR_BYTES = CTR_BYTES + FLAG_BYTES;
 
 struct View {
     int world, rank;
@@ -36,8 +38,9 @@ inline size_t bytes_for(size_t n_floats) { return HDR_BYTES + 2 * ebfi::round_up
 
 // host: validate and convert the C struct; world == 1 is allowed (no peers: the exchange degenerates to a copy)
 int make_view(const ebfi_dp_comm *c, size_t n_floats, View &v);
-// host: a[0, na) | b[0, nb) <- sum over ranks, in place (stand-alone exchange kernel, dp_comm.cu)
-int allreduce_sum(cudaStream_t st, const View &v, float *a, size_t na, float *b, size_t nb);
+// host: a[0, na) | b[0, nb) <- sum over ranks, in place. mode 0: publish kernel + complete kernel; mode 1: publish only
+// (the values stay local); mode 2: complete the last publish (dp_comm.cu)
+int allreduce_sum(cudaStream_t st, const View &v, float *a, size_t na, float *b, size_t nb, int mode = 0);
 
 #ifdef __CUDACC__
 __device__ __forceinline__ unsigned *ctr(const View &v) { return reinterpret_cast<unsigned *>(v.base[v.rank]); }
@@ -65,20 +68,41 @@ __device__ __forceinline__ float ld_relaxed_sys(const float *p)
     return x;
 }
 
-// Called by ALL threads of the block after their stores into data(v, rank, epoch & 1): publish the block's slice to
-// the peers and wait for theirs. blockDim.x >= world.
-__device__ __forceinline__ void publish_and_wait(const View &v, unsigned epoch, int blk)
+// Called by ALL threads of EVERY block of the publishing grid after their stores into data(v, rank, epoch & 1): the last
+// block to arrive hands the whole epoch to the peers and advances the counter. blockDim.x >= world.
+__device__ __forceinline__ void publish(const View &v, unsigned epoch)
 {
+    __shared__ int last;
     __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();                                          // this block's data stores before its ticket
+        unsigned *c = ctr(v);
+        const unsigned nblk = gridDim.x * gridDim.y * gridDim.z;
+        last = atomicAdd(c + 1, 1u) == nblk - 1;
+        if (last) c[1] = 0u;
+    }
+    __syncthreads();
+    if (last) {
+        const int q = (int)threadIdx.x;
+        if (q < v.world && q != v.rank) {
+            __threadfence_system();                               // every block's data stores, system-wide
+            st_release_sys(flags(v, q) + v.rank, epoch);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned *>(ctr(v)) = epoch;
+    }
+}
+
+// Called by ALL threads of the block: wait until every peer has published `epoch`.
+__device__ __forceinline__ void wait_peers(const View &v, unsigned epoch)
+{
     const int q = (int)threadIdx.x;
     if (q < v.world && q != v.rank) {
-        __threadfence_system();                                   // the block's data stores, system-wide
-        st_release_sys(flags(v, q) + v.rank * MAX_BLOCKS + blk, epoch);
-        const unsigned *mine = flags(v, v.rank) + q * MAX_BLOCKS + blk;
+        const unsigned *mine = flags(v, v.rank) + q;
         const long long t0 = clock64();
         while ((int)(ld_acquire_sys(mine) - epoch) < 0) {
             if (clock64() - t0 > (8LL << 30)) {                   // ~4 s at 2 GHz: a peer never arrived
-                printf("ebfi_dp: rank %d block %d waited for rank %d epoch %u\n", v.rank, blk, q, epoch);
+                printf("ebfi_dp: rank %d waited for rank %d epoch %u\n", v.rank, q, epoch);
                 __trap();
             }
         }
@@ -94,20 +118,6 @@ __device__ __forceinline__ float gather_sum(const View &v, unsigned epoch, size_
     return a;
 }
 
-// Called by all threads of the block at the very end: the last block of the grid advances the epoch counter.
-__device__ __forceinline__ void finish_launch(const View &v, unsigned epoch)
-{
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned *c = ctr(v);
-        const unsigned nblk = gridDim.x * gridDim.y * gridDim.z;
-        if (atomicAdd(c + 1, 1u) == nblk - 1) {
-            c[1] = 0u;
-            __threadfence();
-            *reinterpret_cast<volatile unsigned *>(c) = epoch;
-        }
-    }
-}
 #endif
 
 }  // namespace ebfi_dp

@@ -100,8 +100,7 @@ class GradComm:
         ptrs = list(self.handle.buffer_ptrs)
         self.struct = L.DpComm(self.world, self.rank, (L.c_void * 8)(*(ptrs + [None] * (8 - len(ptrs)))), nbytes)
 
-    def allreduce_(self, a, b=None):
-        """In place: `a` (and `b`) become the sums over all ranks — one kernel of this repo, on the current stream."""
+    def _call(self, fn, what, a, b):
         from . import _lib as L
         n = a.numel() + (b.numel() if b is not None else 0)
         if n > self.n_floats:
@@ -109,10 +108,22 @@ class GradComm:
         for t in (a, b):
             if t is not None and not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
                 raise RuntimeError("GradComm.allreduce_: contiguous float32 CUDA tensors only")
-        L.check(L.load().ebfi_dp_allreduce_sum(L.stream_ptr(a.device), self.struct, L.ptr(a), a.numel(),
-                                               L.ptr(b) if b is not None else None, b.numel() if b is not None else 0),
-                "dp_allreduce_sum")
+        L.check(getattr(L.load(), fn)(L.stream_ptr(a.device), self.struct, L.ptr(a), a.numel(),
+                                      L.ptr(b) if b is not None else None, b.numel() if b is not None else 0), what)
         return a, b
+
+    def allreduce_(self, a, b=None):
+        """In place: `a` (and `b`) become the sums over all ranks — one kernel of this repo, on the current stream."""
+        return self._call("ebfi_dp_allreduce_sum", "dp_allreduce_sum", a, b)
+
+    def publish(self, a, b=None):
+        """First half of the exchange: hand this rank's values to the peers, do not wait."""
+        return self._call("ebfi_dp_publish", "dp_publish", a, b)
+
+    def complete(self, a, b=None):
+        """Second half: wait for every peer's values of the last publish (this class's, or a deferred
+        `_ext.dcn_v2_backward(..., comm=, defer=True)`); `a` / `b` become the rank-ordered sums."""
+        return self._call("ebfi_dp_complete", "dp_complete", a, b)
 
 
 def dcn_backward_data_parallel(backward_fn, input, weight, bias, offset, mask, grad_output, *geom, group=None, comm=None):

@@ -99,11 +99,12 @@ def dcn_v2_forward(input, weight, bias, offset, mask, kernel_h, kernel_w, stride
 
 
 def dcn_v2_backward(input, weight, bias, offset, mask, grad_output, kernel_h, kernel_w, stride_h,
-                    stride_w, pad_h, pad_w, dilation_h, dilation_w, deformable_group, comm=None):
+                    stride_w, pad_h, pad_w, dilation_h, dilation_w, deformable_group, comm=None, defer=False):
     """dcn_v2_cuda_backward (dcn_v2_cuda.cu:97-216).
     Returns [grad_input, grad_offset, grad_mask, grad_weight, grad_bias].
     comm (new, optional): a parallel.GradComm — grad_weight / grad_bias then come back summed over its ranks, the
-    exchange fused into the kernel that reduces them (ebfi_dcnv2_backward_dp)."""
+    exchange fused into the kernel that reduces them (ebfi_dcnv2_backward_dp). defer=True: the kernel only publishes
+    this rank's sums; `comm.complete(grad_weight, grad_bias)` finishes the exchange where the sums are needed."""
     # THArgCheck(input.is_contiguous()) / (weight.is_contiguous()), dcn_v2_cuda.cu:110-111
     if not input.is_contiguous():
         raise RuntimeError("input tensor has to be contiguous")
@@ -112,7 +113,7 @@ def dcn_v2_backward(input, weight, bias, offset, mask, grad_output, kernel_h, ke
     if _check_cuda(input=input, weight=weight, bias=bias, offset=offset, mask=mask,
                    grad_output=grad_output) == torch.bfloat16:
         return _bf16_via_fp32(dcn_v2_backward, (input, weight, bias, offset, mask, grad_output),
-                              (kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w, deformable_group, comm))
+                              (kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w, deformable_group, comm, defer))
     g, ho, wo = _geom(input, weight, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w,
                       dilation_h, dilation_w, deformable_group, _deterministic())
     _check_offset_mask(g, ho, wo, offset, mask)
@@ -129,15 +130,15 @@ def dcn_v2_backward(input, weight, bias, offset, mask, grad_output, kernel_h, ke
         if comm is None:
             L.check(lib.ebfi_dcnv2_backward(*args), "dcn_v2_backward")
         else:
-            L.check(lib.ebfi_dcnv2_backward_dp(*args, comm.struct), "dcn_v2_backward_dp")
+            L.check(lib.ebfi_dcnv2_backward_dp(*args, comm.struct, 1 if defer else 0), "dcn_v2_backward_dp")
     return grads
 
 
 def dcn_v2_backward_dp(input, weight, bias, offset, mask, grad_output, kernel_h, kernel_w, stride_h,
-                       stride_w, pad_h, pad_w, dilation_h, dilation_w, deformable_group, comm):
+                       stride_w, pad_h, pad_w, dilation_h, dilation_w, deformable_group, comm, defer=False):
     """dcn_v2_backward with grad_weight / grad_bias all-reduced over `comm` inside the producing kernel."""
     return dcn_v2_backward(input, weight, bias, offset, mask, grad_output, kernel_h, kernel_w, stride_h,
-                           stride_w, pad_h, pad_w, dilation_h, dilation_w, deformable_group, comm)
+                           stride_w, pad_h, pad_w, dilation_h, dilation_w, deformable_group, comm, defer)
 
 
 def _check_packed(g, ho, wo, offset_mask):

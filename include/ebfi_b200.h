@@ -283,14 +283,23 @@ size_t ebfi_dp_comm_bytes(size_t n_floats);
 /* In place: a[0, na) and b[0, nb) become the sums over all ranks (one kernel, no NCCL). */
 int ebfi_dp_allreduce_sum(void *stream, const ebfi_dp_comm *comm, float *a, size_t na, float *b, size_t nb);
 
+/* The same exchange in two halves, so that the NVLink latency and the skew between the ranks hide behind the work in
+ * between: publish copies the local values into the symmetric buffer and signals the peers (does not wait);
+ * complete waits for every peer's values of the LAST publish and writes the rank-ordered sums into a / b (same sizes).
+ * At most one publish may be outstanding per communicator. */
+int ebfi_dp_publish(void *stream, const ebfi_dp_comm *comm, const float *a, size_t na, const float *b, size_t nb);
+int ebfi_dp_complete(void *stream, const ebfi_dp_comm *comm, float *a, size_t na, float *b, size_t nb);
+
 /* ebfi_dcnv2_backward whose grad_weight / grad_bias are the sums over all ranks of `comm`; on the tensor-core box path
- * the exchange is fused into the kernel that reduces the per-CTA partials. The other three gradients are per rank. */
+ * the exchange is fused into the kernel that reduces the per-CTA partials. The other three gradients are per rank.
+ * defer != 0: the kernel only publishes — grad_weight / grad_bias hold this rank's sums until the caller runs
+ * ebfi_dp_complete(stream, comm, grad_weight, Cout*C*kh*kw, grad_bias, Cout) (e.g. right before the optimizer step). */
 int ebfi_dcnv2_backward_dp(void *stream, const ebfi_dcn_geom *g,
                            const float *input, const float *weight, const float *bias,
                            const float *offset, const float *mask, const float *grad_output,
                            float *grad_input, float *grad_offset, float *grad_mask,
                            float *grad_weight, float *grad_bias,
-                           void *workspace, size_t workspace_bytes, const ebfi_dp_comm *comm);
+                           void *workspace, size_t workspace_bytes, const ebfi_dp_comm *comm, int defer);
 
 /* ---- self test --------------------------------------------------------------- */
 

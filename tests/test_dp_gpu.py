@@ -41,12 +41,18 @@ def test_world_one_backward_dp_equals_backward():
         got = _ext.dcn_v2_backward_dp(x, w, b, off, msk, go, *GEOM, comm)
         for a, c in zip(got, want):
             assert torch.equal(a, c)
+    got = _ext.dcn_v2_backward_dp(x, w, b, off, msk, go, *GEOM, comm, defer=True)      # publish ... complete
+    comm_call = lambda fn, *t: L.check(getattr(L.load(), fn)(L.stream_ptr(dev), comm.struct, L.ptr(t[0]), t[0].numel(),
+                                                             L.ptr(t[1]), t[1].numel()), fn)
+    comm_call("ebfi_dp_complete", got[3], got[4])
+    for a, c in zip(got, want):
+        assert torch.equal(a, c)
     a, c = torch.randn(1000, device=dev), torch.randn(77, device=dev)
     a0, c0 = a.clone(), c.clone()
     L.check(L.load().ebfi_dp_allreduce_sum(L.stream_ptr(dev), comm.struct, L.ptr(a), a.numel(), L.ptr(c), c.numel()), "dp")
     torch.cuda.synchronize()
     assert torch.equal(a, a0) and torch.equal(c, c0)
-    assert int(comm.buf[:4].view(torch.int32)[0]) == 4     # four launches so far
+    assert int(comm.buf[:4].view(torch.int32)[0]) == 5     # five publishing launches so far
 
 
 def _free_port():
@@ -68,7 +74,12 @@ def _worker(rank, world, port, q):
         comm = parallel.GradComm(w.numel() + b.numel(), dev)
         ok = True
         for it in range(4):
-            fused = _ext.dcn_v2_backward_dp(x, w, b, off, msk, go, *GEOM, comm)
+            if it % 2 == 0:
+                fused = _ext.dcn_v2_backward_dp(x, w, b, off, msk, go, *GEOM, comm)
+            else:                                        # two halves with unrelated work in between
+                fused = _ext.dcn_v2_backward_dp(x, w, b, off, msk, go, *GEOM, comm, defer=True)
+                torch.zeros(32 << 20, device=dev).sum()
+                comm.complete(fused[3], fused[4])
             local = _ext.dcn_v2_backward(x, w, b, off, msk, go, *GEOM)
             gw, gb = local[3].clone(), local[4].clone()
             dist.all_reduce(gw); dist.all_reduce(gb)
@@ -80,6 +91,11 @@ def _worker(rank, world, port, q):
             ref = fused[3].clone(); dist.broadcast(ref, 0)
             ok &= torch.equal(ref, fused[3])
         t = torch.arange(5000, device=dev, dtype=torch.float32) * (rank + 1)
+        comm.publish(t)
+        comm.complete(t)
+        torch.cuda.synchronize()
+        ok &= torch.equal(t, torch.arange(5000, device=dev, dtype=torch.float32) * sum(range(1, world + 1)))
+        t = torch.arange(5000, device=dev, dtype=torch.float32) * (rank + 1)
         comm.allreduce_(t)
         torch.cuda.synchronize()
         ok &= torch.equal(t, torch.arange(5000, device=dev, dtype=torch.float32) * sum(range(1, world + 1)))
@@ -90,7 +106,7 @@ def _worker(rank, world, port, q):
         q.put((rank, False, traceback.format_exc()[-1500:]))
 
 
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("world", [2, 8])
 def test_fused_allreduce_matches_nccl(world):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
