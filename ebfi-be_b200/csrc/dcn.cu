@@ -382,8 +382,9 @@ __global__ void dcn_det_bound(const float *__restrict__ gout, const float *__res
 __global__ void dcn_i64_to_f32(const long long *__restrict__ src, float *__restrict__ dst, size_t n, DcnDims d)
 {
     const float inv = ldexpf(1.f, -det_scale_exp(d));
+    const bool bad = det_bound_nonfinite(d);
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        dst[i] = __ll2float_rn(src[i]) * inv;
+        dst[i] = bad ? __uint_as_float(0x7FC00000u) : __ll2float_rn(src[i]) * inv;
 }
 
 int fill_dims(const ebfi_dcn_geom *q, DcnDims &d)

@@ -388,7 +388,7 @@ __global__ void blocked_to_nchw(const float *__restrict__ src, float *__restrict
 // fixed-point (BG, HW, 8) int64 -> fp32 NCHW: one rounding per element
 __global__ void blocked_i64_to_nchw(const long long *__restrict__ src, float *__restrict__ dst, int BG, int HW, DcnDims d)
 {
-    const float inv = ldexpf(1.f, -det_scale_exp(d));
+    const float inv = det_bound_nonfinite(d) ? __uint_as_float(0x7FC00000u) : ldexpf(1.f, -det_scale_exp(d));   // NaN propagates
     const size_t n = (size_t)BG * HW;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const size_t bg = i / HW, px = i - bg * HW;

@@ -38,6 +38,13 @@ __device__ __forceinline__ int det_scale_exp(const DcnDims &d)
     if (bound > 0.f && bound < 3.0e38f) frexpf(bound, &e);      // bound < 2^e
     return max(-120, min(120, d.det_head - e));
 }
+// A NaN / Inf in grad_output, weight or mask makes the bound non-finite: the fixed-point sums are then meaningless and
+// the conversion kernels write NaN instead, so that overflow checks on grad_input (AMP GradScaler) still fire.
+__device__ __forceinline__ bool det_bound_nonfinite(const DcnDims &d)
+{
+    const float bound = d.det_bound[0] * d.det_bound[1] * d.det_bound[2];
+    return !(bound < 3.0e38f);
+}
 __device__ __forceinline__ void det_add(long long *p, float v, float scale)
 {
     // power-of-two scaling is exact; one rounding to the fixed-point grid; integer addition is associative

@@ -23,6 +23,7 @@ class HostPipeline:
         self.s_in = torch.cuda.Stream(self.device)
         self.s_out = torch.cuda.Stream(self.device)
         self._bufs = {}
+        self._dcn_busy = []          # events of the previous dcn_forward_backward still using the cached buffers
 
     def _buf(self, key, like):
         b = self._bufs.get(key)
@@ -78,6 +79,10 @@ class HostPipeline:
         grad_weight, grad_bias. Single shot (the DCN tensors are 20x smaller than FAC's)."""
         comp = torch.cuda.current_stream(self.device)
         with torch.cuda.stream(self.s_in):
+            # the cached device buffers are still read by the previous call's kernels / D2H copies until its `done`
+            # and copy-out events: order this call's H2D after them
+            for e in self._dcn_busy:
+                self.s_in.wait_event(e)
             dev = [self._buf(("d", j), t) for j, t in enumerate((input, offset, mask, weight, bias, grad_output))]
             for d_, h_ in zip(dev, (input, offset, mask, weight, bias, grad_output)):
                 d_.copy_(h_, non_blocking=True)
@@ -92,5 +97,7 @@ class HostPipeline:
             for name, t in zip(("out", "grad_input", "grad_offset", "grad_mask", "grad_weight", "grad_bias"),
                                [o.detach()] + [l.grad for l in leaves]):
                 results[name].copy_(t, non_blocking=True)
+            copied = torch.cuda.Event(); copied.record(self.s_out)
+        self._dcn_busy = [done, copied]
         keep = (o, leaves)
         return self.s_out, keep                              # caller synchronises (lets FAC overlap the D2H)
