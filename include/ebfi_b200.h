@@ -67,24 +67,29 @@ typedef struct ebfi_dcn_geom {
     int flags;                            /* 0, or EBFI_DCN_DETERMINISTIC (new; not in the reference's argument list) */
 } ebfi_dcn_geom;
 
-/* Backward only: accumulate grad_input in 64-bit fixed point (integer atomics are associative), so that
- * ALL five gradients are bit-reproducible run to run. The reference's col2im uses float atomicAdd
- * (dcn_v2_im2col_cuda.cu:249) and is not; neither is the default mode here. The fixed-point scale is a
- * power of two derived on the device from max|grad_output|, max|weight| and max|mask| such that no
- * sum can overflow; resolution is at least 2^-20 of the largest possible single contribution. About 2x
- * slower than the default vector reductions. */
+/* Backward only: accumulate grad_input in 64-bit fixed point in global memory (integer atomics are associative), so
+ * that ALL five gradients are bit-reproducible run to run for ANY offsets. The reference's col2im uses float
+ * atomicAdd (dcn_v2_im2col_cuda.cu:249) and is not. The DEFAULT mode (no flag) is already bit-reproducible on the
+ * tensor-core path (8 channels per group, 64 outputs) for every sample whose four corners lie within ~7 pixels of its
+ * tile's undeformed footprint: those accumulate in shared-memory fixed point and the per-tile boxes are summed in a
+ * fixed order (csrc/dcn_bwd_box.cu); only samples beyond that use float red.global.add. This flag removes that last
+ * order dependence (and covers the CUDA-core path) at ~3x the cost. The fixed-point scale is a power of two derived on
+ * the device from max|grad_output|, max|weight| and max|mask| such that no sum can overflow; resolution is at least
+ * 2^-20 of the largest possible single contribution. A non-finite gradient yields NaN (never a silent zero). */
 #define EBFI_DCN_DETERMINISTIC 1
 
 /* Output spatial size, formula of dcn_v2_cuda.cu:64-65. Returns EBFI_ERR_INVALID
  * when the geometry is inconsistent (non-positive sizes, C % dg != 0, ...). */
 int ebfi_dcnv2_output_size(const ebfi_dcn_geom *g, int *height_out, int *width_out);
 
-/* Scratch the backward pass needs (per-CTA grad_weight / grad_bias partials). The column
- * buffer of the reference (dcn_v2_cuda.cu:68) never exists in HBM in either pass. */
+/* Scratch the backward pass needs: per-CTA grad_weight / grad_bias partials, the group-blocked copy of the input and,
+ * on the tensor-core path, one dense 24 x 30-pixel grad_input box per (128-pixel tile, deformable group) — about 5.6x
+ * the size of grad_input. 32-byte aligned device memory. The column buffer of the reference (dcn_v2_cuda.cu:68) never
+ * exists in HBM in either pass. */
 size_t ebfi_dcnv2_backward_workspace_bytes(const ebfi_dcn_geom *g);
 
 /* Scratch for the forward pass: the TF32 hi/lo weight images the tensor-core kernel streams
- * into shared memory (2 x the weight tensor). 16-byte aligned device memory. Without it (NULL /
+ * into shared memory (2 x the weight tensor) + the group-blocked input copy. 32-byte aligned device memory. Without it (NULL /
  * too small) the forward falls back to its CUDA-core kernel, which needs none. */
 size_t ebfi_dcnv2_forward_workspace_bytes(const ebfi_dcn_geom *g);
 
@@ -98,7 +103,7 @@ int ebfi_dcnv2_forward(void *stream, const ebfi_dcn_geom *g,
 
 /* All five gradients of dcn_v2_cuda_backward (dcn_v2_cuda.cu:97-216), every
  * output written in full. grad_offset / grad_mask / grad_weight / grad_bias are
- * reduced in a fixed order (bit-reproducible run to run).
+ * reduced in a fixed order (bit-reproducible run to run); grad_input: see EBFI_DCN_DETERMINISTIC.
  * Reference quirk kept on purpose: the grad_input scatter uses pad_h for BOTH
  * paddings (dcn_v2_im2col_cuda.cu:368 passes `pad_h, pad_h`). */
 int ebfi_dcnv2_backward(void *stream, const ebfi_dcn_geom *g,
