@@ -35,6 +35,11 @@ KEEP = [
     "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+    "smsp__inst_executed_op_shared_atom.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "lts__t_sectors_srcunit_tex_op_atom.sum", "lts__t_sectors_op_red.sum", "lts__t_sectors_op_atom.sum",
+    "lts__t_sector_op_red_hit_rate.pct", "l1tex__t_set_accesses_pipe_lsu_mem_global_op_red.sum",
+    "sm__pipe_tensor_op_umma_cycles_active.avg.pct_of_peak_sustained_elapsed",
 ]
 
 
