@@ -46,6 +46,29 @@ def test_gemm_bf16x3_matches_fp64(M, N, K, lbo):
     assert err < 3e-5, float(err)
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 80, 64), (128, 16, 16), (128, 64, 128)])
+def test_gemm_bf16x3_mn_major_a(M, N, K):
+    """kind::f16 accepts an MN-major A operand in the no-swizzle core-matrix layout (kind::tf32 does not): the same
+    128-byte core matrices serve a K-major read over one index and an MN-major read over the other, which is how the
+    DCN backward uses ONE grad_output copy for both of its contractions (dcn_bwd_box.cu). Bit 16 of the LBO argument
+    selects the MN-major store + descriptor in the self test."""
+    from ebfi_be_b200 import _lib as L
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A, B = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g)
+    want = A.double() @ B.double().t()
+    Ad, Bd = A.to(dev), B.to(dev)
+    outs = []
+    for amn in (0, 1):
+        C = torch.full((M, N), float("nan"), device=dev)
+        L.check(L.load().ebfi_selftest_gemm_bf16x3(L.stream_ptr(dev), L.ptr(Ad), L.ptr(Bd), L.ptr(C), M, N, K, 128 | (amn << 16)),
+                "selftest_gemm_bf16")
+        torch.cuda.synchronize()
+        outs.append(C.cpu())
+        assert float((C.double().cpu() - want).abs().max() / want.abs().max()) < 3e-5
+    assert torch.equal(outs[0], outs[1])         # same products, same accumulation order
+
+
 def test_probe_documents_the_k_major_core_matrix_layout():
     """addr(row, k) = (row/8)*SBO + (k/4)*LBO + (row%8)*16 + (k%4)*4 bytes — read back from the hardware."""
     from ebfi_be_b200 import _lib as L
