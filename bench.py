@@ -462,11 +462,13 @@ def run_ours(args):
     peak, peak_src = peaks()
     op_bytes = {"dcn_fwd": DCN_FWD_BYTES, "dcn_bwd": DCN_BWD_BYTES, "fac_fwd": FAC_FWD_BYTES, "fac_bwd": FAC_BWD_BYTES}
     gbs = lambda nbytes, ms: nbytes / (ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp):      # DRAM bytes of one launch from the committed `ncu --set full` capture (ncu cannot run inside a timed bench)
         with open(tp) as f:
-            traffic = json.load(f).get("fac_bwd_march")
+            tj = json.load(f)
+        traffic = tj.get("fac_bwd_march")
+        traffic_src = f"profiles/{tj.get('tag', '?')}_fac_bwd_march.json: dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full)"
     dom = "fac_bwd"
     line = {
         "metric": "DCNv2+FAC fwd+bwd Mpix/s", "value": round(world * MPIX_PER_STEP / (ms_step * 1e-3), 3),
@@ -485,7 +487,7 @@ def run_ours(args):
                                   + (f" (peer-memory communicator unavailable: {comm_err})" if comm_err else ""))},
         "roofline": {"bound": "hbm", "kernel": "fac_bwd_march<5,4,ring> (FAC fused backward)",
                      "achieved": round(gbs(op_bytes[dom], op_ms[dom]), 1), "peak": peak, "unit": "GB/s",
-                     "frac": round(gbs(op_bytes[dom], op_ms[dom]) / peak, 4), "traffic": traffic,
+                     "frac": round(gbs(op_bytes[dom], op_ms[dom]) / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_bytes_per_launch": op_bytes[dom], "peak_source": peak_src,
                      "step_frac": round(gbs(STEP_BYTES, ms_step) / peak, 4)},
         "breakdown": {n: {"ms": round(op_ms[n], 4), "cold_ms": round(cold[n], 4),
