@@ -64,11 +64,16 @@ SIGNATURES = {
     "ebfi_events_raw_to_stack": (c_int, [c_void] * 5 + [c_i64, c_int, c_int, c_int, c_void, c_void, c_int]),
     "ebfi_frame_to_lap": (c_int, [c_void] * 3 + [c_int] * 3),
     "ebfi_frame_to_dcp": (c_int, [c_void] * 4 + [c_int] * 4),
+}
+# test-only probes: lib/libebfi_b200_selftest.so, include/ebfi_b200_selftest.h
+SELFTEST_LIB_PATH = os.path.join(os.path.dirname(LIB_PATH), "libebfi_b200_selftest.so")
+SELFTEST_SIGNATURES = {
     "ebfi_selftest_gemm_tf32x3": (c_int, [c_void] * 4 + [c_int] * 4),
     "ebfi_selftest_gemm_bf16x3": (c_int, [c_void] * 4 + [c_int] * 4),
     "ebfi_selftest_mma_rate": (c_int, [c_void, c_void] + [c_int] * 6),
     "ebfi_selftest_umma_probe": (c_int, [c_void, c_void, c_int, c_int, c_int]),
 }
+_selftest = None
 
 
 def load():
@@ -88,6 +93,21 @@ def load():
         raise RuntimeError("libebfi_b200.so ABI version mismatch")
     _lib = lib
     return lib
+
+
+def load_selftest():
+    """dlopen the test-only probe library (after the product library it links against)."""
+    global _selftest
+    if _selftest is None:
+        load()
+        if not os.path.exists(SELFTEST_LIB_PATH):
+            raise RuntimeError(f"{SELFTEST_LIB_PATH} is missing: run `python ebfi-be_b200/build.py`")
+        lib = ctypes.CDLL(SELFTEST_LIB_PATH)
+        for name, (res, args) in SELFTEST_SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _selftest = lib
+    return _selftest
 
 
 def check(rc, what):

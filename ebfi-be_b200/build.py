@@ -13,6 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libebfi_b200.so")
+SELFTEST_LIB = os.path.join(LIBDIR, "libebfi_b200_selftest.so")      # hardware probes, test-only (include/ebfi_b200_selftest.h)
+SELFTEST_SOURCES = {"tcgemm_selftest.cu"}
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
          "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr",
@@ -54,8 +56,13 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    if procs or not os.path.exists(LIB):
-        subprocess.run([NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"], check=True)
+    st_objs = [o for o in objs if os.path.basename(o)[:-2] + ".cu" in SELFTEST_SOURCES]
+    objs = [o for o in objs if o not in st_objs]
+    if procs or not os.path.exists(LIB) or not os.path.exists(SELFTEST_LIB):
+        arch = ["-gencode", "arch=compute_100a,code=sm_100a"]
+        subprocess.run([NVCC, "-shared", "-o", LIB] + objs + arch, check=True)
+        subprocess.run([NVCC, "-shared", "-o", SELFTEST_LIB] + st_objs + arch +
+                       ["-L", LIBDIR, "-lebfi_b200", "-Xlinker", "-rpath=$ORIGIN"], check=True)
     return LIB
 
 

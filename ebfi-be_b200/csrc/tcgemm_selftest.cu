@@ -1,11 +1,12 @@
 // tcgemm_selftest.cu — one-CTA 3xTF32 GEMM on the tcgen05 path, C[MxN] = A[MxK] * B[NxK]^T.
 //
-// Not on the hot path: it exists to pin the plumbing of umma.cuh (shared-memory descriptors for
+// Test-only (libebfi_b200_selftest.so, include/ebfi_b200_selftest.h): it exists to pin the plumbing of umma.cuh (shared-memory descriptors for
 // K-major and MN-major operands in the no-swizzle core-matrix layout, instruction descriptor,
 // TMEM allocation / tcgen05.ld lane mapping for M = 128 and M = 64, commit -> mbarrier) against
 // an fp64 reference, independently of the DCN kernels that are built on the same pieces
 // (tests/test_tcgen05_gpu.py).
 #include "common.cuh"
+#include "../../include/ebfi_b200_selftest.h"
 #include "umma.cuh"
 
 namespace {

@@ -14,8 +14,8 @@ import ebfi_be_b200
 from ebfi_be_b200 import _lib as L
 
 
-def _declared_symbols():
-    text = open(os.path.join(ROOT, "include", "ebfi_b200.h")).read()
+def _declared_symbols(header="ebfi_b200.h"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(ebfi_[a-z0-9_]+)\s*\(", text)))
 
@@ -33,6 +33,17 @@ def test_every_declared_symbol_is_exported_and_bound():
         assert hasattr(lib, name), f"{name} declared in include/ebfi_b200.h but not exported"
         assert name in L.SIGNATURES, f"{name} has no ctypes prototype in _lib.SIGNATURES"
     assert sorted(L.SIGNATURES) == declared
+
+
+def test_selftest_probes_live_in_their_own_library():
+    """The tcgen05 probes are test infrastructure: declared in include/ebfi_b200_selftest.h, exported by
+    libebfi_b200_selftest.so only."""
+    main, st = ctypes.CDLL(L.LIB_PATH), ctypes.CDLL(L.SELFTEST_LIB_PATH)
+    declared = [s for s in _declared_symbols("ebfi_b200_selftest.h") if s.startswith("ebfi_selftest_")]
+    assert sorted(L.SELFTEST_SIGNATURES) == declared and len(declared) == 4
+    for name in declared:
+        assert hasattr(st, name) and not hasattr(main, name)
+    assert not any(s.startswith("ebfi_selftest_") for s in _declared_symbols())
 
 
 def test_abi_version_and_error_string():

@@ -20,7 +20,7 @@ def test_gemm_tf32x3_matches_fp64(M, N, K, a_mn):
     Ad = (A.t().contiguous() if a_mn else A).to(dev)
     Bd = B.to(dev)
     C = torch.full((M, N), float("nan"), device=dev)
-    L.check(L.load().ebfi_selftest_gemm_tf32x3(L.stream_ptr(dev), L.ptr(Ad), L.ptr(Bd), L.ptr(C), M, N, K, a_mn),
+    L.check(L.load_selftest().ebfi_selftest_gemm_tf32x3(L.stream_ptr(dev), L.ptr(Ad), L.ptr(Bd), L.ptr(C), M, N, K, a_mn),
             "selftest_gemm")
     torch.cuda.synchronize()
     err = (C.double().cpu() - want).abs().max() / want.abs().max()
@@ -38,7 +38,7 @@ def test_gemm_bf16x3_matches_fp64(M, N, K, lbo):
     want = A.double() @ B.double().t()
     Ad, Bd = A.to(dev), B.to(dev)            # keep the device copies alive across the call
     C = torch.full((M, N), float("nan"), device=dev)
-    L.check(L.load().ebfi_selftest_gemm_bf16x3(L.stream_ptr(dev), L.ptr(Ad), L.ptr(Bd), L.ptr(C), M, N, K, lbo),
+    L.check(L.load_selftest().ebfi_selftest_gemm_bf16x3(L.stream_ptr(dev), L.ptr(Ad), L.ptr(Bd), L.ptr(C), M, N, K, lbo),
             "selftest_gemm_bf16")
     torch.cuda.synchronize()
     err = (C.double().cpu() - want).abs().max() / want.abs().max()
@@ -61,7 +61,7 @@ def test_gemm_bf16x3_mn_major_a(M, N, K):
     outs = []
     for amn in (0, 1):
         C = torch.full((M, N), float("nan"), device=dev)
-        L.check(L.load().ebfi_selftest_gemm_bf16x3(L.stream_ptr(dev), L.ptr(Ad), L.ptr(Bd), L.ptr(C), M, N, K, 128 | (amn << 16)),
+        L.check(L.load_selftest().ebfi_selftest_gemm_bf16x3(L.stream_ptr(dev), L.ptr(Ad), L.ptr(Bd), L.ptr(C), M, N, K, 128 | (amn << 16)),
                 "selftest_gemm_bf16")
         torch.cuda.synchronize()
         outs.append(C.cpu())
@@ -74,7 +74,7 @@ def test_probe_documents_the_k_major_core_matrix_layout():
     from ebfi_be_b200 import _lib as L
     dev = torch.device("cuda:0")
     C = torch.zeros(128, 8, device=dev)
-    L.check(L.load().ebfi_selftest_umma_probe(L.stream_ptr(dev), L.ptr(C), 128, 256, 0), "probe")
+    L.check(L.load_selftest().ebfi_selftest_umma_probe(L.stream_ptr(dev), L.ptr(C), 128, 256, 0), "probe")
     torch.cuda.synchronize()
     got = C.cpu().long()
     for m in (0, 1, 7, 8, 9, 64, 127):

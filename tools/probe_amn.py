@@ -11,7 +11,7 @@ for (M, N, K) in [(128, 80, 64), (128, 16, 16), (128, 64, 128)]:
     Ad, Bd = A.to(dev), B.to(dev)
     for amn in (0, 1):
         C = torch.full((M, N), float("nan"), device=dev)
-        L.check(L.load().ebfi_selftest_gemm_bf16x3(L.stream_ptr(dev), L.ptr(Ad), L.ptr(Bd), L.ptr(C), M, N, K, 128 | (amn << 16)), "selftest")
+        L.check(L.load_selftest().ebfi_selftest_gemm_bf16x3(L.stream_ptr(dev), L.ptr(Ad), L.ptr(Bd), L.ptr(C), M, N, K, 128 | (amn << 16)), "selftest")
         torch.cuda.synchronize()
         err = (C.double().cpu() - want).abs().max() / want.abs().max()
         print(f"M={M} N={N} K={K} a_mn={amn}: rel err {float(err):.3e}", flush=True)

@@ -2,7 +2,7 @@
 import sys, torch
 sys.path.insert(0, "/root/repo")
 from ebfi_be_b200 import _lib as L
-lib = L.load()
+lib = L.load_selftest()
 dev = torch.device("cuda:0")
 out = torch.zeros(148, device=dev)
 for sbo, bsbo in ((128, 256), (160, 256), (160, 18432)):
