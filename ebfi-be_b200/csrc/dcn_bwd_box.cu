@@ -567,7 +567,7 @@ dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__rest
         int e2 = 0;
         if (tmax && !nonfinite) frexpf(__uint_as_float(tmax), &e2);      // M < 2^e2
         const int wbits = 32 - __clz(max(w_max[bb], 1));                 // contributions per element < 2^wbits
-        const int k2 = max(-100, min(100, 30 - wbits - e2));
+        const int k2 = max(-126, min(126, 30 - wbits - e2));            // 2^k2 and 2^-k2 are normal fp32 numbers
         const float inv_scale = ldexpf(1.f, -k2);
         if (cur.gi != 0) {                               // col is still read by GEMM3 of the previous iteration
             umma::mbar_wait(&bar_g3, ph_g3);

@@ -159,14 +159,16 @@ def test_grad_input_scale_invariance(dcn):
     b = torch.randn(64, device=dev())
     go = torch.randn(B, 64, H, W, device=dev())
     ref = None
-    for sc in (1.0, 1e-12, 1e12, 2.0 ** -100):
+    for sc in (1.0, 2.0 ** -20, 2.0 ** 20, 2.0 ** -100, 2.0 ** 90, 1e-12, 1e12):
         xi = x.clone().requires_grad_()
         dcn.dcn_v2_conv(xi, off, msk, w, b, 1, 1, 1, dg).backward(go * sc)
         g = xi.grad.double() / sc
         if ref is None:
             ref = g
-        else:
-            assert float((g - ref).abs().max() / ref.abs().max()) < 2e-6, sc
+        elif sc in (1e-12, 1e12):       # go * sc rounds: the bf16 hi/lo operand splits change, at the GEMM's 2^-16 level
+            assert float((g - ref).abs().max() / ref.abs().max()) < 3e-5, sc
+        else:                            # power-of-two scalings are exact all the way through
+            assert torch.equal(g, ref), sc
 
 
 def test_nonfinite_grad_output_reaches_grad_input(dcn):
