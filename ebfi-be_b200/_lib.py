@@ -25,6 +25,7 @@ class DcnGeom(ctypes.Structure):
 
 
 EBFI_DCN_DETERMINISTIC = 1
+EBFI_DCN_INPUT_BLOCKED = 2
 
 
 class DpComm(ctypes.Structure):
@@ -41,6 +42,7 @@ SIGNATURES = {
     "ebfi_dcnv2_output_size": (c_int, [_GEOM_P, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "ebfi_dcnv2_backward_workspace_bytes": (c_size, [_GEOM_P]),
     "ebfi_dcnv2_forward_workspace_bytes": (c_size, [_GEOM_P]),
+    "ebfi_dcnv2_blocked_input_offset": (c_size, [_GEOM_P]),
     "ebfi_dcnv2_forward": (c_int, [c_void, _GEOM_P] + [c_void] * 6 + [c_void, c_size]),
     "ebfi_dcnv2_backward": (c_int, [c_void, _GEOM_P] + [c_void] * 11 + [c_void, c_size]),
     "ebfi_dcnv2_backward_dp": (c_int, [c_void, _GEOM_P] + [c_void] * 11 + [c_void, c_size, ctypes.POINTER(DpComm), c_int]),

@@ -31,6 +31,7 @@ namespace ebfi_dcn {
 int forward_tc(cudaStream_t st, const DcnDims &d, const float *input, const float *weight, const float *bias,
                const float *offset, const float *mask, float *output, void *workspace, size_t workspace_bytes);
 size_t forward_tc_workspace(const DcnDims &d);
+size_t forward_tc_blocked_offset(const DcnDims &d);
 // tensor-core backward (dcn_bwd_tc.cu); splits == 0 when the shape is not eligible
 int backward_box_splits(const DcnDims &d);
 size_t backward_box_scratch_bytes(const DcnDims &d);
@@ -409,8 +410,9 @@ int fill_dims(const ebfi_dcn_geom *q, DcnDims &d)
     const long long taps = (long long)d.dg * d.KK * Ho * Wo;
     d.off_bs = 2 * taps; d.mask_bs = taps; d.packed = 0; d.abs_sum = nullptr;
     d.off_bp = 2 * d.dg * d.KK; d.mask_bp = d.dg * d.KK;
-    EBFI_REQUIRE((q->flags & ~EBFI_DCN_DETERMINISTIC) == 0, "dcn: unknown flags 0x%x", q->flags);
+    EBFI_REQUIRE((q->flags & ~(EBFI_DCN_DETERMINISTIC | EBFI_DCN_INPUT_BLOCKED)) == 0, "dcn: unknown flags 0x%x", q->flags);
     d.det = (q->flags & EBFI_DCN_DETERMINISTIC) ? 1 : 0;
+    d.in_blocked = (q->flags & EBFI_DCN_INPUT_BLOCKED) ? 1 : 0;
     d.det_bound = nullptr;
     // an element of grad_input receives at most one contribution per (output pixel, tap) of its sample
     int bits = 1;
@@ -469,6 +471,15 @@ size_t ebfi_dcnv2_backward_workspace_bytes(const ebfi_dcn_geom *q)
            std::max({backward_tc_scratch_bytes(d), backward_box_scratch_bytes(d), det}) + 512;
 }
 
+size_t ebfi_dcnv2_blocked_input_offset(const ebfi_dcn_geom *q)
+{
+    DcnDims d{};
+    if (fill_dims(q, d) != EBFI_OK) return 0;
+    d.det = 0;
+    if (backward_box_splits(d) == 0) return 0;           // the backward could not use it
+    return forward_tc_blocked_offset(d);
+}
+
 size_t ebfi_dcnv2_forward_workspace_bytes(const ebfi_dcn_geom *q)
 {
     DcnDims d{};
@@ -518,6 +529,11 @@ static int run_backward(void *stream, const DcnDims &d_in, const float *input, c
     const int S_box = tc_ok ? backward_box_splits(d) : 0;
     const int S_tc = S_box > 0 ? S_box : (tc_ok ? backward_tc_splits(d) : 0);
     const int S = S_tc > 0 ? S_tc : bwd_splits(d);
+    if (d.in_blocked) {
+        EBFI_REQUIRE(S_box > 0, "dcn_backward: EBFI_DCN_INPUT_BLOCKED needs the box path (ebfi_dcnv2_blocked_input_offset() != 0 "
+                                "and no EBFI_DCN_DETERMINISTIC)");
+        EBFI_REQUIRE((reinterpret_cast<uintptr_t>(input) & 31u) == 0, "dcn_backward: the blocked input must be 32-byte aligned");
+    }
     const size_t n_w = (size_t)d.Co * d.C * d.KK, n_b = (size_t)d.Co;
     const size_t n_in = (size_t)d.B * d.C * d.H * d.W;
     // workspace: [grad_weight / grad_bias partials][scratch][deterministic mode: 3-float bound]

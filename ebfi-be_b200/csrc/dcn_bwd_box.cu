@@ -861,8 +861,13 @@ int backward_box(cudaStream_t st, const DcnDims &d, const float *input, const fl
     unsigned char *wimg = reinterpret_cast<unsigned char *>(gin_blk + n);
     float *pbox = reinterpret_cast<float *>(wimg + ebfi::round_up((size_t)d.dg * pl.wt_bytes, (size_t)256));
     const int BG = d.B * d.dg, HW = d.H * d.W;
-    // blocked copy of the input + zero fill of the far-sample accumulator in one pass
-    if (int rc = launch_nchw_to_blocked(st, input, in_blk, BG, HW, gin_blk, 2)) return rc;
+    if (d.in_blocked) {
+        // the caller kept the forward's blocked copy (EBFI_DCN_INPUT_BLOCKED): only the far-sample accumulator is cleared
+        in_blk = const_cast<float *>(input);
+        EBFI_CUDA_OK(cudaMemsetAsync(gin_blk, 0, n * sizeof(float), st));
+    } else if (int rc = launch_nchw_to_blocked(st, input, in_blk, BG, HW, gin_blk, 2)) {
+        return rc;       // blocked copy of the input + zero fill of the far-sample accumulator in one pass
+    }
     dcn_bwd_prep_weights<<<ceil_div(d.dg * pl.N1 * CO, 256), 256, 0, st>>>(weight, reinterpret_cast<unsigned short *>(wimg), d, pl);
     EBFI_LAUNCH_OK("dcn_bwd_prep_weights");
 

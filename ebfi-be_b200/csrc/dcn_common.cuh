@@ -29,6 +29,7 @@ struct DcnDims {
     // bound < 2^e.
     int det, det_head;
     const float *det_bound;
+    int in_blocked;   // EBFI_DCN_INPUT_BLOCKED (backward): `input` already is the group-blocked copy [b][C/8][y][x][8]
 };
 
 __device__ __forceinline__ int det_scale_exp(const DcnDims &d)

@@ -452,6 +452,14 @@ bool make_plan(const DcnDims &d, BoxPlan &pl)
 
 }  // namespace
 
+// byte offset of the group-blocked input copy inside the forward workspace (0: this shape has no tensor-core forward)
+size_t forward_tc_blocked_offset(const DcnDims &d)
+{
+    BoxPlan pl{};
+    if (!make_plan(d, pl)) return 0;
+    return ebfi::round_up((size_t)d.dg * pl.ncs * pl.TPR * 2 * pl.b_bytes, (size_t)256);
+}
+
 size_t forward_tc_workspace(const DcnDims &d)
 {
     BoxPlan pl{};

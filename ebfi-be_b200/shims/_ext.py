@@ -29,6 +29,18 @@ def _deterministic():
             if (torch.are_deterministic_algorithms_enabled() or os.environ.get("EBFI_DCN_DETERMINISTIC") == "1") else 0)
 
 
+# The forward leaves a group-blocked copy of `input` in its workspace; the backward of the SAME tensor (same storage,
+# same version counter, same geometry) reads it instead of re-blocking (EBFI_DCN_INPUT_BLOCKED). One entry per device:
+# a training step runs backward right after forward; anything else simply misses and re-blocks. The entry holds the
+# input's storage, so its address cannot be recycled for another tensor while the entry is alive.
+_blocked_cache = {}
+
+
+def _blocked_key(input, g):
+    return (input.data_ptr(), input._version, tuple(input.shape), g.kernel_h, g.kernel_w, g.stride_h, g.stride_w,
+            g.pad_h, g.pad_w, g.dilation_h, g.dilation_w, g.deformable_group)
+
+
 def _geom(input, weight, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w,
           dilation_h, dilation_w, deformable_group, flags=0):
     if input.dim() != 4 or weight.dim() != 4:
@@ -95,6 +107,12 @@ def dcn_v2_forward(input, weight, bias, offset, mask, kernel_h, kernel_w, stride
         L.check(lib.ebfi_dcnv2_forward(L.stream_ptr(input.device), g, L.ptr(input), L.ptr(weight),
                                        L.ptr(bias), L.ptr(offset), L.ptr(mask), L.ptr(output), L.ptr(ws), nbytes),
                 "dcn_v2_forward")
+        off_blk = lib.ebfi_dcnv2_blocked_input_offset(g)
+        if off_blk and os.environ.get("EBFI_DCN_NO_BLOCKED_REUSE") != "1":
+            # keeps `ws` alive until the next forward on this device; the stream that runs the backward is the one that
+            # ran the forward in autograd (and in the reference's trainer), which orders the read after the write
+            _blocked_cache[input.device.index] = (_blocked_key(input, g), ws, off_blk, torch.cuda.current_stream(input.device),
+                                                  input.untyped_storage())
     return output
 
 
@@ -125,7 +143,13 @@ def dcn_v2_backward(input, weight, bias, offset, mask, grad_output, kernel_h, ke
         grads = [torch.empty_like(t) for t in (input, offset, mask, weight, bias)]
         nbytes = lib.ebfi_dcnv2_backward_workspace_bytes(g)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=input.device)
-        args = (L.stream_ptr(input.device), g, L.ptr(input), L.ptr(weight), L.ptr(bias), L.ptr(offset), L.ptr(mask),
+        in_ptr = L.ptr(input)
+        hit = _blocked_cache.get(input.device.index)
+        if (hit is not None and not g.flags and hit[0] == _blocked_key(input, g)
+                and hit[3] == torch.cuda.current_stream(input.device)):
+            g.flags |= L.EBFI_DCN_INPUT_BLOCKED
+            in_ptr = L.c_void(hit[1].data_ptr() + hit[2])
+        args = (L.stream_ptr(input.device), g, in_ptr, L.ptr(weight), L.ptr(bias), L.ptr(offset), L.ptr(mask),
                 L.ptr(grad_output), *(L.ptr(t) for t in grads), L.ptr(ws), nbytes)
         if comm is None:
             L.check(lib.ebfi_dcnv2_backward(*args), "dcn_v2_backward")

@@ -78,6 +78,12 @@ typedef struct ebfi_dcn_geom {
  * 2^-20 of the largest possible single contribution. A non-finite gradient yields NaN (never a silent zero). */
 #define EBFI_DCN_DETERMINISTIC 1
 
+/* Backward only: `input` is not the NCHW tensor but its group-blocked copy [B][C/8][H][W][8 channels] (32-byte aligned)
+ * that ebfi_dcnv2_forward left in its workspace at byte offset ebfi_dcnv2_blocked_input_offset(g) — a caller that keeps
+ * the forward workspace alive until the backward (an autograd context) saves the re-blocking pass. Only valid when
+ * that offset is non-zero and EBFI_DCN_DETERMINISTIC is not set. */
+#define EBFI_DCN_INPUT_BLOCKED 2
+
 /* Output spatial size, formula of dcn_v2_cuda.cu:64-65. Returns EBFI_ERR_INVALID
  * when the geometry is inconsistent (non-positive sizes, C % dg != 0, ...). */
 int ebfi_dcnv2_output_size(const ebfi_dcn_geom *g, int *height_out, int *width_out);
@@ -92,6 +98,10 @@ size_t ebfi_dcnv2_backward_workspace_bytes(const ebfi_dcn_geom *g);
  * into shared memory (2 x the weight tensor) + the group-blocked input copy. 32-byte aligned device memory. Without it (NULL /
  * too small) the forward falls back to its CUDA-core kernel, which needs none. */
 size_t ebfi_dcnv2_forward_workspace_bytes(const ebfi_dcn_geom *g);
+
+/* Byte offset of the group-blocked input copy inside the forward workspace after ebfi_dcnv2_forward, or 0 when this
+ * geometry does not produce / the backward cannot consume one (see EBFI_DCN_INPUT_BLOCKED). */
+size_t ebfi_dcnv2_blocked_input_offset(const ebfi_dcn_geom *g);
 
 /* out[b,co,h,w] = bias[co] + sum_{c,i,j} weight[co,c,i,j] * mask * bilinear(input[b,c], ...)
  * Replaces dcn_v2_cuda_forward (dcn_v2_cuda.cu:20-95). `output` is written in

@@ -191,6 +191,38 @@ def test_nonfinite_grad_output_reaches_grad_input(dcn):
         assert bool(torch.isfinite(xi.grad[0, :, 20:, :8]).all())      # far from the bad pixel: untouched
 
 
+def test_backward_reuses_the_forwards_blocked_input(dcn, monkeypatch):
+    """The forward's group-blocked input copy is handed to the backward of the same tensor (EBFI_DCN_INPUT_BLOCKED):
+    identical results, and any change of the tensor (version counter) or a different tensor misses the cache."""
+    from gpu_util import dev
+    from ebfi_be_b200.shims import _ext
+    torch.manual_seed(9)
+    B, C, H, W, dg = 2, 64, 40, 48, 8
+    x = torch.randn(B, C, H, W, device=dev())
+    off = 2 * torch.randn(B, 2 * dg * 9, H, W, device=dev())
+    msk = torch.sigmoid(torch.randn(B, dg * 9, H, W, device=dev()))
+    w = torch.randn(64, C, 3, 3, device=dev()) / 24
+    b = torch.randn(64, device=dev())
+    go = torch.randn(B, 64, H, W, device=dev())
+    geom = (3, 3, 1, 1, 1, 1, 1, 1, dg)
+    monkeypatch.setenv("EBFI_DCN_NO_BLOCKED_REUSE", "1")
+    _ext._blocked_cache.clear()
+    _ext.dcn_v2_forward(x, w, b, off, msk, *geom)
+    assert not _ext._blocked_cache
+    plain = _ext.dcn_v2_backward(x, w, b, off, msk, go, *geom)
+    monkeypatch.delenv("EBFI_DCN_NO_BLOCKED_REUSE")
+    _ext.dcn_v2_forward(x, w, b, off, msk, *geom)
+    assert _ext._blocked_cache[dev().index][0] == _ext._blocked_key(x, _ext._geom(x, w, *geom)[0])
+    reused = _ext.dcn_v2_backward(x, w, b, off, msk, go, *geom)
+    for a, c in zip(reused, plain):
+        assert torch.equal(a, c)
+    x.mul_(2.0)                                  # version bump: the cached copy is stale and must not be used
+    want = _ext.dcn_v2_backward(x.clone(), w, b, off, msk, go, *geom)      # a different tensor: cache miss
+    got = _ext.dcn_v2_backward(x, w, b, off, msk, go, *geom)
+    for a, c in zip(got, want):
+        assert torch.equal(a, c)
+
+
 def test_reductions_are_bit_reproducible(dcn):
     """grad_offset / grad_mask / grad_weight / grad_bias use fixed-order reductions."""
     from gpu_util import dev
