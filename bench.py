@@ -705,6 +705,7 @@ def cpu_baseline(budget_s=20.0):
             "events_dataset_path_16bins_Mev_s": round(n_ev / 1e6 / t_r, 2),
             "value": round(mpix / (td + tf), 5), "unit": "Mpix/s", "cores": torch.get_num_threads(),
             "kind": "reference" if ref_dcn is not None else "port",
+            "kind_by_leg": {"dcn": "reference" if ref_dcn is not None else "port", "fac": "port"},
             "sample": f"top {rows} of 256 rows of the same step (DCN B=1 + FAC B=4, fwd+bwd): "
                       f"DCN {td:.2f} s via " + ("the reference's CPU build oracle/_ref/dcn_cpu (serial loops + MKL GEMM)"
                                                if ref_dcn is not None else "the oracle C port")
@@ -745,7 +746,8 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "BASELINE configs[0]+[1] (DCNv2 B=1 + FAC B=4, 256x256, fwd+bwd), CPU, bounded sample",
                    "rows_per_step": rows},
-        "cpu_baseline": {"value": val, "unit": "Mpix/s", "cores": torch.get_num_threads(), "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "Mpix/s", "cores": torch.get_num_threads(), "kind": kind,
+                         "kind_by_leg": {"dcn": kind, "fac": "port"}, "sample": sample},
         "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "breakdown": {"dcn_s_per_step": round(sd / args.steps, 3), "fac_s_per_step": round(sf / args.steps, 3)},
     }), flush=True)
