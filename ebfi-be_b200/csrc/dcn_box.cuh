@@ -26,6 +26,15 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr)
     return v;
 }
 
+// Packed fp32x2 arithmetic (sm_100 FFMA2 / FMUL2): one issue slot for two lanes of math. The kernels that use the box
+// are bound by instruction issue, not by the FMA pipe, so halving the FMA instruction count is a direct gain. A scalar
+// operand is written as pack2(s, s): ptxas folds it into the instruction's broadcast form (R.F32), no extra move.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
 // Visiting order of one in-box sample. Chunk c (0..7): corner c >> 1 (0 (y0,x0), 1 (y0,x0+1), 2 (y0+1,x0), 3 (y0+1,x0+1)),
 // 16-byte half c & 1 (channels 0-3 / 4-7). Step i reads chunk (c0 + i) & 7: even steps are one half, odd steps the
 // other — half 0 first iff !odd.

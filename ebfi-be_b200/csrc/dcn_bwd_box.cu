@@ -167,15 +167,24 @@ __device__ __forceinline__ void sample_bwd(const DcnDims &d, const SampleCtx &sc
         box::rot_corners(rt.c0, hy * hx, hy * lx, ly * hx, ly * lx, wv);       // bilinear weights
         box::rot_corners(rt.c0, -hx, -lx, hx, lx, wyv);                         // d/dy (im2col_cuda.cu:99-120)
         box::rot_corners(rt.c0, -hy, hy, -ly, ly, wxv);                         // d/dx
+        // packed fp32x2 FMAs: accumulators [A | B half][value, d/dy, d/dx][channel pair]
+        box::f32x2 acc[2][3][2] = {};
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const float4 q = box::lds128(box::step_addr(rt, i));
             const float cw = box::step_coef(wv, odd, i), cy = box::step_coef(wyv, odd, i), cx = box::step_coef(wxv, odd, i);
-            float *v = (i & 1) ? vb : va, *yy = (i & 1) ? yb4 : ya, *xx = (i & 1) ? xb4 : xa;
-            v[0] += cw * q.x; v[1] += cw * q.y; v[2] += cw * q.z; v[3] += cw * q.w;
-            yy[0] += cy * q.x; yy[1] += cy * q.y; yy[2] += cy * q.z; yy[3] += cy * q.w;
-            xx[0] += cx * q.x; xx[1] += cx * q.y; xx[2] += cx * q.z; xx[3] += cx * q.w;
+            const box::f32x2 q01 = box::pack2(q.x, q.y), q23 = box::pack2(q.z, q.w);
+            box::f32x2 (&a)[3][2] = acc[i & 1];
+            a[0][0] = box::ffma2(box::pack2(cw, cw), q01, a[0][0]); a[0][1] = box::ffma2(box::pack2(cw, cw), q23, a[0][1]);
+            a[1][0] = box::ffma2(box::pack2(cy, cy), q01, a[1][0]); a[1][1] = box::ffma2(box::pack2(cy, cy), q23, a[1][1]);
+            a[2][0] = box::ffma2(box::pack2(cx, cx), q01, a[2][0]); a[2][1] = box::ffma2(box::pack2(cx, cx), q23, a[2][1]);
         }
+        box::unpack2(acc[0][0][0], va[0], va[1]); box::unpack2(acc[0][0][1], va[2], va[3]);
+        box::unpack2(acc[1][0][0], vb[0], vb[1]); box::unpack2(acc[1][0][1], vb[2], vb[3]);
+        box::unpack2(acc[0][1][0], ya[0], ya[1]); box::unpack2(acc[0][1][1], ya[2], ya[3]);
+        box::unpack2(acc[1][1][0], yb4[0], yb4[1]); box::unpack2(acc[1][1][1], yb4[2], yb4[3]);
+        box::unpack2(acc[0][2][0], xa[0], xa[1]); box::unpack2(acc[0][2][1], xa[2], xa[3]);
+        box::unpack2(acc[1][2][0], xb4[0], xb4[1]); box::unpack2(acc[1][2][1], xb4[2], xb4[3]);
     } else if (inside) {
         const Tap tp = make_tap(y, x, d.H, d.W);
         const f8 a1 = ldg_f8(ib + (size_t)tp.i00 * CS, tp.c00), a2 = ldg_f8(ib + (size_t)tp.i01 * CS, tp.c01);
@@ -191,19 +200,34 @@ __device__ __forceinline__ void sample_bwd(const DcnDims &d, const SampleCtx &sc
             xb4[j] = -hy * a1.v[4 + j] + hy * a2.v[4 + j] - ly * a3.v[4 + j] + ly * a4.v[4 + j];
         }
     }
-    float s_m = 0.f, s_y = 0.f, s_x = 0.f;
     float ta[4], tb[4];                  // colgrad * mask of the A / B halves
+    {
+        // channel pairs on the packed fp32x2 pipe; the two lanes of each sum are added at the end
+        using box::f32x2;
+        const f32x2 m2 = box::pack2(m, m);
+        f32x2 sm2 = 0, sy2 = 0, sx2 = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float ga = odd ? gc[4 + j] : gc[j], gb4 = odd ? gc[j] : gc[4 + j];
-        s_m += ga * va[j] + gb4 * vb[j];                      // grad_mask (im2col_cuda.cu:311)
-        ta[j] = ga * m; tb[j] = gb4 * m;
-        s_y += ya[j] * ta[j] + yb4[j] * tb[j];                // grad_offset
-        s_x += xa[j] * ta[j] + xb4[j] * tb[j];
-        colv[j] = (odd ? vb[j] : va[j]) * m;                  // recomputed column, natural channel order
-        colv[4 + j] = (odd ? va[j] : vb[j]) * m;
+        for (int h = 0; h < 2; ++h) {        // channel pairs (2h, 2h+1) of each half
+            const f32x2 ga = box::pack2(odd ? gc[4 + 2 * h] : gc[2 * h], odd ? gc[5 + 2 * h] : gc[2 * h + 1]);
+            const f32x2 gb2 = box::pack2(odd ? gc[2 * h] : gc[4 + 2 * h], odd ? gc[2 * h + 1] : gc[5 + 2 * h]);
+            const f32x2 va2 = box::pack2(va[2 * h], va[2 * h + 1]), vb2 = box::pack2(vb[2 * h], vb[2 * h + 1]);
+            sm2 = box::ffma2(ga, va2, sm2); sm2 = box::ffma2(gb2, vb2, sm2);           // grad_mask (im2col_cuda.cu:311)
+            const f32x2 ta2 = box::fmul2(ga, m2), tb2 = box::fmul2(gb2, m2);
+            box::unpack2(ta2, ta[2 * h], ta[2 * h + 1]); box::unpack2(tb2, tb[2 * h], tb[2 * h + 1]);
+            sy2 = box::ffma2(box::pack2(ya[2 * h], ya[2 * h + 1]), ta2, sy2);           // grad_offset
+            sy2 = box::ffma2(box::pack2(yb4[2 * h], yb4[2 * h + 1]), tb2, sy2);
+            sx2 = box::ffma2(box::pack2(xa[2 * h], xa[2 * h + 1]), ta2, sx2);
+            sx2 = box::ffma2(box::pack2(xb4[2 * h], xb4[2 * h + 1]), tb2, sx2);
+            // recomputed column, natural channel order
+            const f32x2 ca = box::fmul2(va2, m2), cb = box::fmul2(vb2, m2);
+            box::unpack2(odd ? cb : ca, colv[2 * h], colv[2 * h + 1]);
+            box::unpack2(odd ? ca : cb, colv[4 + 2 * h], colv[5 + 2 * h]);
+        }
+        float lo, hi;
+        box::unpack2(sy2, lo, hi); g_y = lo + hi;
+        box::unpack2(sx2, lo, hi); g_x = lo + hi;
+        box::unpack2(sm2, lo, hi); g_m = (lo + hi) * mask_act_grad_t<PACKED>(m);
     }
-    g_y = s_y; g_x = s_x; g_m = s_m * mask_act_grad_t<PACKED>(m);
     // ---- grad_input (im2col_cuda.cu:236-251); the scatter's x uses pad_h (:368)
     bool q_inside = inside, q_inbox = inbox, q_odd = odd;
     float qhx = hx, qlx = lx;
@@ -232,9 +256,12 @@ __device__ __forceinline__ void sample_bwd(const DcnDims &d, const SampleCtx &sc
             const uint32_t a = box::step_addr(rq, i);
             const float cf = box::step_coef(qv, q_odd, i);
             const float *tt = (i & 1) ? tb : ta;
+            float pr[4];
+            box::unpack2(box::fmul2(box::pack2(cf, cf), box::pack2(tt[0], tt[1])), pr[0], pr[1]);
+            box::unpack2(box::fmul2(box::pack2(cf, cf), box::pack2(tt[2], tt[3])), pr[2], pr[3]);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                atoms_add(a + ((((uint32_t)j + wrot) & 3u) << 2), __float2int_rn(cf * tt[j]));
+                atoms_add(a + ((((uint32_t)j + wrot) & 3u) << 2), __float2int_rn(pr[j]));
         }
     } else if (q_inside) {
         const Tap tq = make_tap(y, xs, d.H, d.W);

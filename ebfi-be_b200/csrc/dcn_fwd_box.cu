@@ -26,6 +26,7 @@
 //
 // fp32 parity: products are 3xTF32 (umma.cuh); the hi*hi chain is spread over several TMEM accumulators because
 // the tensor core's fp32 accumulate rounds toward zero.
+#include "dcn_box.cuh"
 #include "dcn_common.cuh"
 #include "tma.cuh"
 #include "umma.cuh"
@@ -98,14 +99,19 @@ __device__ __forceinline__ bool sample8(float y, float x, float m, int H, int W,
         constexpr uint32_t T_LO = 0x03020100u, T_HI = 0x03020100u + 0x01010101u * (BOX_PITCH / 16);
         const uint32_t ta = (c0 & 4u) ? T_HI : T_LO, tb = (c0 & 4u) ? T_LO : T_HI, sh = (c0 & 3u) * 8u;
         const uint32_t r_lo = __funnelshift_r(ta, tb, sh), r_hi = __funnelshift_r(tb, ta, sh);
+        // packed fp32x2 FMAs (FFMA2): half the FMA issue slots; the scalar weight is the instruction's broadcast operand
+        box::f32x2 acc[2][2] = {};
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const uint32_t o16 = __byte_perm(i < 4 ? r_lo : r_hi, 0u, 0x4440u | (uint32_t)(i & 3));
             const float4 q = lds128(base + (o16 << 4));
             const float wi = odd ? wr[(i + 1) >> 1] : wr[i >> 1];
-            float *a = (i & 1) ? hb : ha;                      // even / odd steps = the two 16-byte halves
-            a[0] += wi * q.x; a[1] += wi * q.y; a[2] += wi * q.z; a[3] += wi * q.w;
+            box::f32x2 (&a)[2] = acc[i & 1];                   // even / odd steps = the two 16-byte halves
+            a[0] = box::ffma2(box::pack2(wi, wi), box::pack2(q.x, q.y), a[0]);
+            a[1] = box::ffma2(box::pack2(wi, wi), box::pack2(q.z, q.w), a[1]);
         }
+        box::unpack2(acc[0][0], ha[0], ha[1]); box::unpack2(acc[0][1], ha[2], ha[3]);
+        box::unpack2(acc[1][0], hb[0], hb[1]); box::unpack2(acc[1][1], hb[2], hb[3]);
         return odd;
     }
     const Tap tp = make_tap(y, x, H, W);
