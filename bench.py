@@ -49,9 +49,10 @@ FAC_OUT = B_FAC * C * H * W
 FAC_FWD_BYTES = _F * (FAC_IN + FAC_KER + FAC_OUT)
 FAC_BWD_BYTES = _F * (FAC_KER + FAC_OUT + FAC_IN + FAC_IN + FAC_KER)
 STEP_BYTES = DCN_FWD_BYTES + DCN_BWD_BYTES + FAC_FWD_BYTES + FAC_BWD_BYTES
-# kernels of ours per step (profiles/r1b_launches.txt): DCN forward = dcn_prep_weights + nchw_to_blocked +
-# dcn_fwd_tc_kernel; DCN backward = nchw_to_blocked + dcn_bwd_tc_kernel + blocked_to_nchw +
-# dcn_reduce_partials; FAC = fac_fwd_march + fac_bwd_march
+# kernels of ours per step (profiles/r2f_launches.txt): DCN forward = dcn_prep_weights + nchw_to_blocked +
+# dcn_fwd_box_kernel; DCN backward = dcn_bwd_prep_weights + dcn_bwd_box_kernel + dcn_gin_collect +
+# dcn_box_reduce_partials (the forward's blocked input copy is reused: a memset node replaces nchw_to_blocked);
+# FAC = fac_fwd_march + fac_bwd_march; N > 1 with the fused exchange: + dp_complete_kernel
 LAUNCHES_PER_STEP = 9
 
 
@@ -506,7 +507,7 @@ def run_ours(args):
         "cfg4_inference_720p": cfg4,
         "cfg5_train_step": cfg5,
         "widening": widen,
-        "gpu_launches": LAUNCHES_PER_STEP * args.steps,
+        "gpu_launches": (LAUNCHES_PER_STEP + (1 if comm is not None else 0)) * args.steps,
         "launch_mode": "eager" if args.no_graphs else "one CUDA graph per operator call (4 replays per step)",
         "clocks": clk.summary(),
     }
