@@ -41,6 +41,27 @@ def _blocked_key(input, g):
             g.pad_h, g.pad_w, g.dilation_h, g.dilation_w, g.deformable_group)
 
 
+def _remember_blocked(lib, g, input, ws):
+    """After a forward: note where its workspace holds the group-blocked copy of `input`."""
+    off_blk = lib.ebfi_dcnv2_blocked_input_offset(g)
+    if off_blk and os.environ.get("EBFI_DCN_NO_BLOCKED_REUSE") != "1":
+        # keeps `ws` alive until the next forward on this device; the stream that runs the backward is the one that
+        # ran the forward in autograd (and in the reference's trainer), which orders the read after the write
+        _blocked_cache[input.device.index] = (_blocked_key(input, g), ws, off_blk, torch.cuda.current_stream(input.device),
+                                              input.untyped_storage())
+
+
+def _blocked_input_ptr(g, input):
+    """Before a backward: the forward's blocked copy of this very tensor if it is still alive (sets the geometry flag),
+    else the tensor itself."""
+    hit = _blocked_cache.get(input.device.index)
+    if (hit is not None and not g.flags and hit[0] == _blocked_key(input, g)
+            and hit[3] == torch.cuda.current_stream(input.device)):
+        g.flags |= L.EBFI_DCN_INPUT_BLOCKED
+        return L.c_void(hit[1].data_ptr() + hit[2])
+    return L.ptr(input)
+
+
 def _geom(input, weight, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w,
           dilation_h, dilation_w, deformable_group, flags=0):
     if input.dim() != 4 or weight.dim() != 4:
@@ -107,12 +128,7 @@ def dcn_v2_forward(input, weight, bias, offset, mask, kernel_h, kernel_w, stride
         L.check(lib.ebfi_dcnv2_forward(L.stream_ptr(input.device), g, L.ptr(input), L.ptr(weight),
                                        L.ptr(bias), L.ptr(offset), L.ptr(mask), L.ptr(output), L.ptr(ws), nbytes),
                 "dcn_v2_forward")
-        off_blk = lib.ebfi_dcnv2_blocked_input_offset(g)
-        if off_blk and os.environ.get("EBFI_DCN_NO_BLOCKED_REUSE") != "1":
-            # keeps `ws` alive until the next forward on this device; the stream that runs the backward is the one that
-            # ran the forward in autograd (and in the reference's trainer), which orders the read after the write
-            _blocked_cache[input.device.index] = (_blocked_key(input, g), ws, off_blk, torch.cuda.current_stream(input.device),
-                                                  input.untyped_storage())
+        _remember_blocked(lib, g, input, ws)
     return output
 
 
@@ -143,12 +159,7 @@ def dcn_v2_backward(input, weight, bias, offset, mask, grad_output, kernel_h, ke
         grads = [torch.empty_like(t) for t in (input, offset, mask, weight, bias)]
         nbytes = lib.ebfi_dcnv2_backward_workspace_bytes(g)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=input.device)
-        in_ptr = L.ptr(input)
-        hit = _blocked_cache.get(input.device.index)
-        if (hit is not None and not g.flags and hit[0] == _blocked_key(input, g)
-                and hit[3] == torch.cuda.current_stream(input.device)):
-            g.flags |= L.EBFI_DCN_INPUT_BLOCKED
-            in_ptr = L.c_void(hit[1].data_ptr() + hit[2])
+        in_ptr = _blocked_input_ptr(g, input)
         args = (L.stream_ptr(input.device), g, in_ptr, L.ptr(weight), L.ptr(bias), L.ptr(offset), L.ptr(mask),
                 L.ptr(grad_output), *(L.ptr(t) for t in grads), L.ptr(ws), nbytes)
         if comm is None:
@@ -199,6 +210,7 @@ def dcn_v2_forward_packed(input, weight, bias, offset_mask, kernel_h, kernel_w, 
                                               L.ptr(abs_offset_sum) if abs_offset_sum is not None else None,
                                               L.ptr(ws), nbytes),
                 "dcn_v2_forward_packed")
+        _remember_blocked(lib, g, input, ws)
     return output
 
 
@@ -225,7 +237,8 @@ def dcn_v2_backward_packed(input, weight, bias, offset_mask, grad_output, kernel
         grads = [torch.empty_like(t) for t in (input, offset_mask, weight, bias)]
         nbytes = lib.ebfi_dcnv2_backward_workspace_bytes(g)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=input.device)
-        L.check(lib.ebfi_dcnv2_backward_packed(L.stream_ptr(input.device), g, L.ptr(input), L.ptr(weight),
+        in_ptr = _blocked_input_ptr(g, input)
+        L.check(lib.ebfi_dcnv2_backward_packed(L.stream_ptr(input.device), g, in_ptr, L.ptr(weight),
                                                L.ptr(bias), L.ptr(offset_mask), L.ptr(grad_output),
                                                *(L.ptr(t) for t in grads), L.ptr(ws), nbytes),
                 "dcn_v2_backward_packed")
