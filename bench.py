@@ -534,12 +534,20 @@ def widening_numbers(torch, dev, d, timed):
         act, kpn = torch.nn.LeakyReLU(), KernelConv2D(kernel_size=K_FAC)
         t_ref = timed(lambda: kpn(ev, act(conv(torch.cat([ev, fr], 1)))), n=5)
         t_fused = timed(lambda: modification.kernelconv_fac_fused(ev, fr, conv.weight, conv.bias, K_FAC, 0.01), n=5)
+        # the same sequence at the fused kernel's operand precision (bf16 conv operands, fp32 accumulation and output)
+        def ref_bf16():
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                k = act(conv(torch.cat([ev, fr], 1)))
+            return kpn(ev, k.float())
+        t_ref16 = timed(ref_bf16, n=5)
         flops = 2.0 * B_FAC * H * W * (C * K_FAC * K_FAC) * (2 * C * 9)
         out["kernelconv_to_fac_forward"] = {
             "workload": f"B={B_FAC} C={C} K={K_FAC} {H}x{W}, fp32 tensors (conv operands bf16 on the tensor cores)",
             "reference_sequence_ms": round(t_ref, 4), "fused_ms": round(t_fused, 4), "speedup": round(t_ref / t_fused, 2),
+            "reference_sequence_bf16_conv_ms": round(t_ref16, 4), "speedup_at_equal_precision": round(t_ref16 / t_fused, 2),
             "fused_TFLOPs": round(flops / (t_fused * 1e-3) / 1e12, 1),
-            "note": "reference sequence = cuDNN conv (TF32, torch default) + LeakyReLU + this repo's FAC forward; the "
+            "note": "reference sequence = cuDNN conv (TF32, torch default) + LeakyReLU + this repo's FAC forward; "
+                    "`_bf16_conv` = the same with the conv under bf16 autocast (the fused kernel's operand precision); the "
                     "1.68 GB kernel tensor is never materialised by the fused kernel"}
         del conv
     # rank 2: DCN_sep tail (chunk, cat, mean|offset| + host sync, sigmoid, op) forward + backward, dcn_v2.py:217-227
