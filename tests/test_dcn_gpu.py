@@ -96,20 +96,26 @@ def test_window_edges_match_oracle(dcn, oracle):
         assert rel_err(got, ref) < GRAD_TOL, name
 
 
-# (B, C=Co=64, H, W, pad_h, pad_w, offset sigma): shapes of the box backward (dcn_bwd_box.cu: 8 channels per group, 64 outputs)
-BOX_SHAPES = [(1, 40, 56, 1, 1, 2.0),        # ragged tiles (40 = 5 x 8 rows, 56 = 3.5 x 16 pixels)
-              (2, 33, 47, 1, 1, 1.0),        # odd sizes: offsets / masks read without TMA (row stride not 16-byte)
-              (1, 48, 64, 1, 1, 12.0),       # most samples leave the 24 x 30 box: global gather / red.add fall-back
-              (1, 32, 48, 2, 1, 2.0),        # pad_h != pad_w: the scatter's x uses pad_h (im2col_cuda.cu:368)
-              (3, 24, 16, 1, 1, 3.0)]        # one tile column, three samples
+# (B, H, W, pad_h, pad_w, offset sigma, stride, dilation): shapes of the box backward (dcn_bwd_box.cu: C = Cout = 64, 8 channels per group)
+BOX_SHAPES = [(1, 40, 56, 1, 1, 2.0, 1, 1),        # ragged tiles (40 = 5 x 8 rows, 56 = 3.5 x 16 pixels)
+              (2, 33, 47, 1, 1, 1.0, 1, 1),        # odd sizes: offsets / masks read without TMA (row stride not 16-byte)
+              (1, 48, 64, 1, 1, 12.0, 1, 1),       # most samples leave the 24 x 30 box: global gather / red.add fall-back
+              (1, 32, 48, 2, 1, 2.0, 1, 1),        # pad_h != pad_w: the scatter's x uses pad_h (im2col_cuda.cu:368)
+              (3, 24, 16, 1, 1, 3.0, 1, 1),        # one tile column, three samples
+              (1, 50, 70, 1, 1, 1.5, 2, 1),        # stride 2: a tile's footprint is 17 x 33 input pixels (wider than the box: SIMT path)
+              (1, 50, 36, 1, 1, 1.5, (2, 1), 1),   # stride 2 in y only: footprint 17 x 18 fits, box pitch in tiles = 16 rows
+              (2, 36, 52, 2, 2, 1.5, 1, 2),        # dilation 2: footprint 12 x 20
+              (1, 36, 40, 0, 0, 2.0, 1, 1)]        # no padding
 
 
 @pytest.mark.parametrize("shape", BOX_SHAPES)
 def test_box_backward_against_oracle(dcn, oracle, shape):
-    B, H, W, ph, pw, osc = shape
+    B, H, W, ph, pw, osc, stride, dil = shape
     C = Co = 64; dg = 8; k = 3
     rng = np.random.default_rng(abs(hash(shape)) % (2 ** 32))
-    Ho, Wo = H + 2 * ph - 2, W + 2 * pw - 2
+    sh, sw = (stride, stride) if isinstance(stride, int) else stride
+    Ho = (H + 2 * ph - (dil * (k - 1) + 1)) // sh + 1
+    Wo = (W + 2 * pw - (dil * (k - 1) + 1)) // sw + 1
     x = rng.standard_normal((B, C, H, W), dtype=np.float32)
     w = (rng.random((Co, C, k, k), dtype=np.float32) * 2 - 1) / 24
     b = rng.standard_normal(Co, dtype=np.float32)
@@ -118,9 +124,9 @@ def test_box_backward_against_oracle(dcn, oracle, shape):
     off = (np.round(rng.standard_normal((B, 2 * dg * k * k, Ho, Wo)) * osc * 64) / 64 + 1 / 128).astype(np.float32)
     msk = (1 / (1 + np.exp(-rng.standard_normal((B, dg * k * k, Ho, Wo))))).astype(np.float32)
     go = rng.standard_normal((B, Co, Ho, Wo), dtype=np.float32)
-    out, grads = _run(dcn, x, off, msk, w, b, go, 1, (ph, pw), 1, dg)
-    assert rel_err(out, oracle.dcn_forward(x, off, msk, w, b, 1, (ph, pw), 1, dg)) < FWD_TOL
-    for name, got, ref in zip(GRADS, grads, oracle.dcn_backward(x, off, msk, w, b, go, 1, (ph, pw), 1, dg)):
+    out, grads = _run(dcn, x, off, msk, w, b, go, (sh, sw), (ph, pw), dil, dg)
+    assert rel_err(out, oracle.dcn_forward(x, off, msk, w, b, (sh, sw), (ph, pw), dil, dg)) < FWD_TOL
+    for name, got, ref in zip(GRADS, grads, oracle.dcn_backward(x, off, msk, w, b, go, (sh, sw), (ph, pw), dil, dg)):
         assert rel_err(got, ref) < GRAD_TOL, name
 
 
