@@ -596,10 +596,6 @@ dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__rest
         const int wbits = 32 - __clz(max(w_max[bb], 1));                 // contributions per element < 2^wbits
         const int k2 = max(-126, min(126, 30 - wbits - e2));            // 2^k2 and 2^-k2 are normal fp32 numbers
         const float inv_scale = ldexpf(1.f, -k2);
-        if (cur.gi != 0) {                               // col is still read by GEMM3 of the previous iteration
-            umma::mbar_wait(&bar_g3, ph_g3);
-            ph_g3 ^= 1u;
-        }
         // ================= pass 2: the samples =================
         {
             SampleCtx sc;
@@ -645,9 +641,18 @@ dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__rest
                     gy[0] = g_y; gy[uplane] = g_x;
                     gmask_g[(unsigned)t * uplane + (unsigned)cur.pix] = g_m;
                 }
-                // column operand: the 8 channels of (tap t, pixel p) are one 16-byte chunk
+                // column operand: the 8 channels of (tap t, pixel p) are one 16-byte chunk. col is read by GEMM3 of the
+                // previous iteration until bar_g3 completes: waited for here, behind the first sample's gather and scatter
+                if (sidx == 0 && cur.gi != 0) {
+                    umma::mbar_wait(&bar_g3, ph_g3);
+                    ph_g3 ^= 1u;
+                }
                 st_split8(c_hi, c_lo, t * (TM * 16) + p * 16, colv);
                 if (++tj == d.kw) { tj = 0; ++ti; }
+            }
+            if (cur.gi != 0 && t_first >= d.KK) {        // a tap row without taps keeps its barrier phase in step
+                umma::mbar_wait(&bar_g3, ph_g3);
+                ph_g3 ^= 1u;
             }
             if (next_same_tile) pass1_end(bb ^ 1, um);
         }
