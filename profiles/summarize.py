@@ -68,8 +68,15 @@ def main(tag):
         traffic[kern] = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
         print(kern, summ.get("gpu__time_duration.sum"), "dram bytes", traffic[kern])
     if traffic:
-        with open(os.path.join(OUT, "ncu_traffic.json"), "w") as f:
-            json.dump({"tag": tag, **traffic}, f, indent=1)
+        # merge: a partial re-capture (a few kernels under a new tag) must not drop the other kernels' entries
+        tp = os.path.join(OUT, "ncu_traffic.json")
+        old = json.load(open(tp)) if os.path.exists(tp) else {}
+        tags = old.get("tags", {k: old.get("tag") for k in old if k not in ("tag", "tags")})
+        tags.update({k: tag for k in traffic})
+        merged = {k: v for k, v in old.items() if k not in ("tag", "tags")}
+        merged.update(traffic)
+        with open(tp, "w") as f:
+            json.dump({"tag": tags.get("fac_bwd_march", tag), "tags": tags, **merged}, f, indent=1)
     lf = os.path.join(ROOT, "gpurun_out", f"launches_{tag}.csv")
     if os.path.exists(lf):
         rows = list(csv.reader(l for l in open(lf) if l.startswith('"')))
