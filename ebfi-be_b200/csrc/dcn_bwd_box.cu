@@ -1,8 +1,9 @@
 // dcn_bwd_box.cu — DCNv2 backward from TMA-staged boxes: shared-memory gather, shared-memory (integer) scatter, both weight
 // contractions on the sm_100a tensor cores, grad_input without global atomics for every sample inside the box.
 //
-// One persistent CTA per SM. CTA (s, h) owns the deformable groups [h*GPC, h*GPC + GPC) and walks the 8 x 16-pixel output
-// tiles s, s+S, ...; an "iteration" is one (tile, group). Per tile the grad_output tile is staged ONCE, as bf16 hi/lo pairs
+// One persistent CTA per SM. CTA (s, h) owns the 8-channel units [h*GPC, h*GPC + GPC) (a unit = one deformable group when the
+// group has 8 channels, else a part of it: its offsets / masks are the group's) and walks the 8 x 16-pixel output tiles
+// s, s+S, ...; an "iteration" is one (tile, unit) — written (tile, group) below. Per tile the grad_output tile is staged ONCE, as bf16 hi/lo pairs
 // in the layout Q[co][px]. The same bytes serve both contractions because kind::f16 accepts MN-major operands in the
 // no-swizzle core-matrix layout (probed: tests/test_tcgen05_gpu.py):
 //   GEMM1  colgrad[128 px x 72] = gO_tile . W_g        A = Q read MN-major (M = px, K = co), B = W_g^T image (bulk copy)
@@ -59,13 +60,14 @@ struct BoxBwdPlan {
     int TPR;             // taps per thread row
     int Kc;              // CS * KK
     int N1, N3;          // GEMM1 / GEMM3 N (multiples of 16)
-    int GPC, NH;         // groups per CTA, CTA rows
+    int GPC, NH;         // units per CTA, CTA rows
     int tiles_x, tiles_y, ntiles;
     int my, mx;          // box margins above / left of the tile's undeformed footprint
     int wt_bytes;        // one group's W^T image, hi | lo
     int col_part;        // one bf16 image of the column operand
     int om_bytes, use_om_tma;
     int off_q, off_col, off_box, off_acc, off_cnt, off_om, smem;
+    int units, ncs, ncs_shift;      // 8-channel units (C / 8) = iterations per tile over all CTA rows; units per deformable group (2^shift)
 };
 
 __device__ __forceinline__ void st_bf16x8(unsigned char *base, int off, const unsigned short (&v)[8])
@@ -277,7 +279,8 @@ __device__ __forceinline__ void sample_bwd(const DcnDims &d, const SampleCtx &sc
     }
 }
 
-template <bool PACKED, int TPRT>
+// MULTI: more than one 8-channel unit per deformable group (the group's offset / mask gradients accumulate over its units)
+template <bool PACKED, int TPRT, bool MULTI>
 __global__ void __launch_bounds__(NTHR, 1)
 dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__restrict__ wimg,
                    const float *__restrict__ offset, const float *__restrict__ mask,
@@ -305,7 +308,7 @@ dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__rest
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int p = tid % TM, r = tid / TM;             // samplers: thread (pixel p, tap row r)
     const int S = gridDim.x, s = blockIdx.x;
-    const int g_begin = blockIdx.y * pl.GPC, ng = min(pl.GPC, d.dg - g_begin);
+    const int g_begin = blockIdx.y * pl.GPC, ng = min(pl.GPC, pl.units - g_begin);     // this CTA's 8-channel units
     const int total_tiles = d.B * pl.ntiles;
     const int NI = ((total_tiles - s + S - 1) / S) * ng;             // iterations (tile, group) of this CTA
     const int npix = d.Ho * d.Wo, Kdim = d.C * d.KK;
@@ -336,6 +339,7 @@ dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__rest
     const uint32_t wrot = (uint32_t)lane >> 3;
 
     // iteration n of this CTA = (tile s + (n / ng) * S, group g_begin + n % ng)
+    // g: 8-channel unit (channels 8g .. 8g+7); its deformable group (offsets / masks) is g >> ncs_shift
     struct Iter { int n, b, ty0, tx0, g, gi, tl, ho, wo, pix; bool valid; };
     auto set_tile = [&](Iter &it, int tile) {       // divisions once per tile
         it.b = tile / pl.ntiles;
@@ -373,11 +377,11 @@ dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__rest
         const int bb = n & 1;
         if (!leader) return;
         umma::mbar_expect_tx(&bar_in[bb], (uint32_t)(box::BYTES + (use_tma ? pl.om_bytes : 0)));
-        tma::load_3d(boxes + bb * box::BYTES, &tm_box, (it.tx0 * d.sw - d.pw - pl.mx) * 8, it.ty0 * d.sh - d.ph - pl.my, it.b * d.dg + it.g, &bar_in[bb]);
+        tma::load_3d(boxes + bb * box::BYTES, &tm_box, (it.tx0 * d.sw - d.pw - pl.mx) * 8, it.ty0 * d.sh - d.ph - pl.my, it.b * pl.units + it.g, &bar_in[bb]);
         if (use_tma) {
             unsigned char *dst = smem + pl.off_om + bb * pl.om_bytes;
-            tma::load_3d(dst, &tm_off, it.tx0, it.ty0, it.b * d.off_bp + it.g * 2 * d.KK, &bar_in[bb]);
-            tma::load_3d(dst + 2 * d.KK * TM * 4, &tm_mask, it.tx0, it.ty0, it.b * d.mask_bp + it.g * d.KK, &bar_in[bb]);
+            tma::load_3d(dst, &tm_off, it.tx0, it.ty0, it.b * d.off_bp + (MULTI ? it.g >> pl.ncs_shift : it.g) * 2 * d.KK, &bar_in[bb]);
+            tma::load_3d(dst + 2 * d.KK * TM * 4, &tm_mask, it.tx0, it.ty0, it.b * d.mask_bp + (MULTI ? it.g >> pl.ncs_shift : it.g) * d.KK, &bar_in[bb]);
         }
     };
     auto issue_w = [&](int n) {                     // W^T image of iteration n's group
@@ -481,8 +485,8 @@ dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__rest
         umma::mbar_wait(&bar_in[bb], par);           // box + offsets / masks have landed
         P1 q;
         q.om = oms + bb * (pl.om_bytes / 4);
-        q.off_g = offset + (size_t)it.b * d.off_bs + (size_t)it.g * 2 * d.KK * plane;
-        q.mask_g = mask + (size_t)it.b * d.mask_bs + (size_t)it.g * d.KK * plane;
+        q.off_g = offset + (size_t)it.b * d.off_bs + (size_t)(MULTI ? it.g >> pl.ncs_shift : it.g) * 2 * d.KK * plane;
+        q.mask_g = mask + (size_t)it.b * d.mask_bs + (size_t)(MULTI ? it.g >> pl.ncs_shift : it.g) * d.KK * plane;
         q.d1 = tmem + (uint32_t)(bb * pl.N1);
         q.cnt_s = cnt_s + (uint32_t)(bb * CNT_PAD);
         q.by0 = it.ty0 * d.sh - d.ph - pl.my; q.bxq0 = it.tx0 * d.sw - d.ph - pl.mx;
@@ -602,14 +606,14 @@ dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__rest
             sc.ho = cur.ho; sc.wo = cur.wo;
             sc.by0 = cur.ty0 * d.sh - d.ph - pl.my; sc.bx0 = cur.tx0 * d.sw - d.pw - pl.mx; sc.bxq0 = cur.tx0 * d.sw - d.ph - pl.mx;
             sc.box_s = umma::smem_u32(boxes + bb * box::BYTES); sc.acc_s = acc_s;
-            sc.ib = in_blk + ((size_t)cur.b * d.dg + cur.g) * in_plane * CS;
-            sc.gb = gin_blk + ((size_t)cur.b * d.dg + cur.g) * in_plane * CS;
+            sc.ib = in_blk + ((size_t)cur.b * pl.units + cur.g) * in_plane * CS;
+            sc.gb = gin_blk + ((size_t)cur.b * pl.units + cur.g) * in_plane * CS;
             sc.scale = ldexpf(1.f, k2);
             const float *om = oms + bb * (pl.om_bytes / 4);
-            const float *off_g = offset + (size_t)cur.b * d.off_bs + (size_t)cur.g * 2 * d.KK * plane;
-            const float *mask_g = mask + (size_t)cur.b * d.mask_bs + (size_t)cur.g * d.KK * plane;
-            float *goff_g = goff + (size_t)cur.b * d.off_bs + (size_t)cur.g * 2 * d.KK * plane;
-            float *gmask_g = gmask + (size_t)cur.b * d.mask_bs + (size_t)cur.g * d.KK * plane;
+            const float *off_g = offset + (size_t)cur.b * d.off_bs + (size_t)(MULTI ? cur.g >> pl.ncs_shift : cur.g) * 2 * d.KK * plane;
+            const float *mask_g = mask + (size_t)cur.b * d.mask_bs + (size_t)(MULTI ? cur.g >> pl.ncs_shift : cur.g) * d.KK * plane;
+            float *goff_g = goff + (size_t)cur.b * d.off_bs + (size_t)(MULTI ? cur.g >> pl.ncs_shift : cur.g) * 2 * d.KK * plane;
+            float *gmask_g = gmask + (size_t)cur.b * d.mask_bs + (size_t)(MULTI ? cur.g >> pl.ncs_shift : cur.g) * d.KK * plane;
             const uint32_t d1 = tmem + (uint32_t)(bb * pl.N1);
             // pass 1 of the next group of the same tile is interleaved tap by tap (its colgrad was issued two iterations
             // ago): two independent instruction streams per warp; a new tile needs its Q first
@@ -637,7 +641,12 @@ dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__rest
                     }
                     float g_y, g_x, g_m;
                     sample_bwd<PACKED>(d, sc, gc, dy, dx, m, ti, tj, lane, wrot, colv, g_y, g_x, g_m);
+                    // more than 8 channels per deformable group: the group's units follow each other in this CTA and the
+                    // same thread owns the element in each of them -> plain read-modify-write, fixed order
                     float *gy = goff_g + (2u * (unsigned)t * uplane + (unsigned)cur.pix);
+                    if (MULTI && (cur.g & (pl.ncs - 1))) {
+                        g_y += gy[0]; g_x += gy[uplane]; g_m += gmask_g[(unsigned)t * uplane + (unsigned)cur.pix];
+                    }
                     gy[0] = g_y; gy[uplane] = g_x;
                     gmask_g[(unsigned)t * uplane + (unsigned)cur.pix] = g_m;
                 }
@@ -664,7 +673,7 @@ dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__rest
         if (tid == 0) { tile_max[bb] = 0u; w_max[bb] = 0; }
         // ---- the accumulation box -> dense fp32 partial (plain coalesced stores), cleared for the next iteration
         {
-            float4 *dst = reinterpret_cast<float4 *>(pbox + (((size_t)cur.b * pl.ntiles + cur.tl) * d.dg + cur.g) * BOX_F);
+            float4 *dst = reinterpret_cast<float4 *>(pbox + (((size_t)cur.b * pl.ntiles + cur.tl) * pl.units + cur.g) * BOX_F);
             const float qnan = __uint_as_float(0x7FC00000u);
             for (int c = tid; c < box::BH * box::BW; c += NSAMP) cnt[bb * (CNT_PAD / 4) + c] = 0;    // read by cell_max an interval ago
             for (int c = tid; c < BOX_F / 4; c += NSAMP) {
@@ -695,7 +704,7 @@ dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__rest
         const int row = (int)lane_base + lane, half = row >> 6, co = row & 63;
         const size_t slot = (size_t)2 * s + half;
         for (int gi = 0; gi < ng; ++gi) {
-            const int c0 = (g_begin + gi) * d.cpg;
+            const int c0 = (g_begin + gi) * CS;
             for (int cb = r * 8; cb < pl.N3; cb += NR * 8) {
                 float v[8];
                 if (NI > 0) {
@@ -762,7 +771,7 @@ dcn_box_reduce_partials(const float *__restrict__ gw_part, const float *__restri
 __global__ void dcn_bwd_prep_weights(const float *__restrict__ weight, unsigned short *__restrict__ wimg, DcnDims d, BoxBwdPlan pl)
 {
     const int per = pl.N1 * CO, Kdim = d.C * d.KK;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.dg * per; i += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < pl.units * per; i += gridDim.x * blockDim.x) {
         const int g = i / per, e = i - g * per;
         const int j = e & 7, rr = (e >> 3) & 7, rest = e >> 6;
         const int kc = rest % (CO / 8), rg = rest / (CO / 8);
@@ -781,11 +790,11 @@ __global__ void dcn_gin_collect(const float *__restrict__ pbox, const float *__r
                                 DcnDims d, BoxBwdPlan pl)
 {
     const int HW = d.H * d.W;
-    const size_t n = (size_t)d.B * d.dg * HW;
+    const size_t n = (size_t)d.B * pl.units * HW;
     const int sy = TH * d.sh, sx = TW * d.sw;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const size_t bg = i / HW;
-        const int px = (int)(i - bg * HW), b = (int)(bg / d.dg), g = (int)(bg - (size_t)b * d.dg);
+        const int px = (int)(i - bg * HW), b = (int)(bg / pl.units), g = (int)(bg - (size_t)b * pl.units);
         const int y = px / d.W, x = px - y * d.W;
         const float4 *fp = reinterpret_cast<const float4 *>(gin_blk + i * CS);
         float4 a0 = __ldg(fp), a1 = __ldg(fp + 1);
@@ -805,7 +814,7 @@ __global__ void dcn_gin_collect(const float *__restrict__ pbox, const float *__r
                 const int ty = ty_lo + a, tx = tx_lo + c;
                 u0[a * NX + c] = u1[a * NX + c] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (ty <= ty_hi && tx <= tx_hi) {
-                    const size_t bx = ((size_t)b * pl.ntiles + (size_t)ty * pl.tiles_x + tx) * d.dg + g;
+                    const size_t bx = ((size_t)b * pl.ntiles + (size_t)ty * pl.tiles_x + tx) * pl.units + g;
                     const int cell = (ny - ty * sy) * box::BW + (nx - tx * sx);
                     const float4 *bp = reinterpret_cast<const float4 *>(pbox + bx * BOX_F + (size_t)cell * CS);
                     u0[a * NX + c] = __ldg(bp); u1[a * NX + c] = __ldg(bp + 1);
@@ -824,17 +833,24 @@ __global__ void dcn_gin_collect(const float *__restrict__ pbox, const float *__r
 
 bool make_plan(const DcnDims &d, BoxBwdPlan &pl)
 {
-    if (d.cpg != CS || d.Co != CO || d.det) return false;
+    if (d.cpg % CS != 0 || d.Co != CO || d.det) return false;
+    pl.units = d.C / CS;
+    pl.ncs = d.cpg / CS;
+    if (pl.ncs & (pl.ncs - 1)) return false;             // units per group: a power of two (1, 2, 4)
+    pl.ncs_shift = 0;
+    while ((1 << pl.ncs_shift) < pl.ncs) ++pl.ncs_shift;
     if (getenv("EBFI_DCN_BWD_NO_BOX")) return false;
     if ((long)2 * d.KK * d.Ho * d.Wo >= (1L << 31) || d.KK > 15) return false;       // 32-bit offsets; <= 2^11 contributions per element
-    if ((long)d.B * d.dg >= (1L << 31) || (long)d.W * 8 >= (1L << 31)) return false;
+    if ((long)d.B * pl.units >= (1L << 31) || (long)d.W * 8 >= (1L << 31)) return false;
     pl.TPR = ceil_div(d.KK, NR);
     pl.Kc = CS * d.KK;
     pl.N1 = ebfi::round_up(pl.Kc, 16);
     pl.N3 = ebfi::round_up(pl.Kc + 1, 16);
-    pl.GPC = std::min({GPC_MAX, d.dg, (TMEM_COLS - 2 * pl.N1) / pl.N3});
+    pl.GPC = std::min({GPC_MAX, pl.units, (TMEM_COLS - 2 * pl.N1) / pl.N3});
     if (pl.GPC < 1 || pl.N1 > 256 || pl.N3 > 256) return false;
-    pl.NH = ceil_div(d.dg, pl.GPC);
+    // all units of a deformable group run in ONE CTA (their grad_offset / grad_mask sums are accumulated by the owner thread)
+    if (pl.GPC % pl.ncs != 0) return false;
+    pl.NH = ceil_div(pl.units, pl.GPC);
     pl.tiles_x = ceil_div(d.Wo, TW);
     pl.tiles_y = ceil_div(d.Ho, TH);
     pl.ntiles = pl.tiles_x * pl.tiles_y;
@@ -878,8 +894,8 @@ size_t backward_box_scratch_bytes(const DcnDims &d)
     BoxBwdPlan pl{};
     if (!make_plan(d, pl)) return 0;
     const size_t n = (size_t)d.B * d.C * d.H * d.W;
-    return 2 * n * sizeof(float) + ebfi::round_up((size_t)d.dg * pl.wt_bytes, (size_t)256) +
-           (size_t)d.B * pl.ntiles * d.dg * box::BYTES;
+    return 2 * n * sizeof(float) + ebfi::round_up((size_t)pl.units * pl.wt_bytes, (size_t)256) +
+           (size_t)d.B * pl.ntiles * pl.units * box::BYTES;
 }
 
 int backward_box(cudaStream_t st, const DcnDims &d, const float *input, const float *weight, const float *offset,
@@ -891,8 +907,8 @@ int backward_box(cudaStream_t st, const DcnDims &d, const float *input, const fl
     const size_t n = (size_t)d.B * d.C * d.H * d.W;
     float *in_blk = static_cast<float *>(scratch), *gin_blk = in_blk + n;
     unsigned char *wimg = reinterpret_cast<unsigned char *>(gin_blk + n);
-    float *pbox = reinterpret_cast<float *>(wimg + ebfi::round_up((size_t)d.dg * pl.wt_bytes, (size_t)256));
-    const int BG = d.B * d.dg, HW = d.H * d.W;
+    float *pbox = reinterpret_cast<float *>(wimg + ebfi::round_up((size_t)pl.units * pl.wt_bytes, (size_t)256));
+    const int BG = d.B * pl.units, HW = d.H * d.W;
     if (d.in_blocked) {
         // the caller kept the forward's blocked copy (EBFI_DCN_INPUT_BLOCKED): only the far-sample accumulator is cleared
         in_blk = const_cast<float *>(input);
@@ -900,7 +916,7 @@ int backward_box(cudaStream_t st, const DcnDims &d, const float *input, const fl
     } else if (int rc = launch_nchw_to_blocked(st, input, in_blk, BG, HW, gin_blk, 2)) {
         return rc;       // blocked copy of the input + zero fill of the far-sample accumulator in one pass
     }
-    dcn_bwd_prep_weights<<<ceil_div(d.dg * pl.N1 * CO, 256), 256, 0, st>>>(weight, reinterpret_cast<unsigned short *>(wimg), d, pl);
+    dcn_bwd_prep_weights<<<ceil_div(pl.units * pl.N1 * CO, 256), 256, 0, st>>>(weight, reinterpret_cast<unsigned short *>(wimg), d, pl);
     EBFI_LAUNCH_OK("dcn_bwd_prep_weights");
 
     CUtensorMap tm_box{}, tm_off{}, tm_mask{};
@@ -920,15 +936,16 @@ int backward_box(cudaStream_t st, const DcnDims &d, const float *input, const fl
         if (int rc = tma::encode_3d(tm_mask, mask, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, dims_m, str, box_m)) return rc;
     }
     dim3 grid(box_splits(d, pl), pl.NH);
-#define EBFI_BWD_BOX(P, T)                                                                                             \
+#define EBFI_BWD_BOX(P, T, M)                                                                                          \
     do {                                                                                                               \
-        EBFI_CUDA_OK(cudaFuncSetAttribute(dcn_bwd_box_kernel<P, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem)); \
-        dcn_bwd_box_kernel<P, T><<<grid, NTHR, pl.smem, st>>>(in_blk, wimg, offset, mask, gout, gin_blk, pbox, goff, gmask, \
-                                                              gw_part, gb_part, d, pl, tm_box, tm_off, tm_mask);       \
+        EBFI_CUDA_OK(cudaFuncSetAttribute(dcn_bwd_box_kernel<P, T, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem)); \
+        dcn_bwd_box_kernel<P, T, M><<<grid, NTHR, pl.smem, st>>>(in_blk, wimg, offset, mask, gout, gin_blk, pbox, goff, gmask, \
+                                                                 gw_part, gb_part, d, pl, tm_box, tm_off, tm_mask);    \
     } while (0)
     // TPRT > 0 unrolls the tap loop (several samples in flight per thread); measured slower on B200 at 3 taps (238 vs
     // 230 us: register pressure), so the rolled loop serves every shape
-    if (d.packed) EBFI_BWD_BOX(true, 0); else EBFI_BWD_BOX(false, 0);
+    if (pl.ncs > 1) { if (d.packed) EBFI_BWD_BOX(true, 0, true); else EBFI_BWD_BOX(false, 0, true); }
+    else            { if (d.packed) EBFI_BWD_BOX(true, 0, false); else EBFI_BWD_BOX(false, 0, false); }
 #undef EBFI_BWD_BOX
     EBFI_LAUNCH_OK("dcn_bwd_box_kernel");
     const unsigned cgrid = (unsigned)std::min<size_t>(ceil_div((size_t)BG * HW, (size_t)256), (size_t)ebfi::sm_count() * 16);

@@ -70,7 +70,7 @@ typedef struct ebfi_dcn_geom {
 /* Backward only: accumulate grad_input in 64-bit fixed point in global memory (integer atomics are associative), so
  * that ALL five gradients are bit-reproducible run to run for ANY offsets. The reference's col2im uses float
  * atomicAdd (dcn_v2_im2col_cuda.cu:249) and is not. The DEFAULT mode (no flag) is already bit-reproducible on the
- * tensor-core path (8 channels per group, 64 outputs) for every sample whose four corners lie within ~7 pixels of its
+ * tensor-core path (8, 16 or 32 channels per deformable group, 64 outputs) for every sample whose four corners lie within ~7 pixels of its
  * tile's undeformed footprint: those accumulate in shared-memory fixed point and the per-tile boxes are summed in a
  * fixed order (csrc/dcn_bwd_box.cu); only samples beyond that use float red.global.add. This flag removes that last
  * order dependence (and covers the CUDA-core path) at ~3x the cost. The fixed-point scale is a power of two derived on

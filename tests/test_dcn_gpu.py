@@ -108,6 +108,27 @@ BOX_SHAPES = [(1, 40, 56, 1, 1, 2.0, 1, 1),        # ragged tiles (40 = 5 x 8 ro
               (1, 36, 40, 0, 0, 2.0, 1, 1)]        # no padding
 
 
+# (C, dg): more than 8 channels per deformable group on the tensor-core path — the reference's own example
+# DCN(64, 64, 3, deformable_groups=2) (testcuda.py:169-180) has 32; grad_offset / grad_mask sum over the group's units
+@pytest.mark.parametrize("C,dg", [(64, 2), (64, 4), (32, 1), (16, 1), (96, 3)])
+def test_box_backward_channels_per_group(dcn, oracle, C, dg):
+    B, H, W, Co, k = 2, 36, 44, 64, 3
+    rng = np.random.default_rng(C * 10 + dg)
+    x = rng.standard_normal((B, C, H, W), dtype=np.float32)
+    w = (rng.random((Co, C, k, k), dtype=np.float32) * 2 - 1) / np.sqrt(C * 9)
+    b = rng.standard_normal(Co, dtype=np.float32)
+    off = (np.round(rng.standard_normal((B, 2 * dg * k * k, H, W)) * 2.0 * 64) / 64 + 1 / 128).astype(np.float32)
+    msk = (1 / (1 + np.exp(-rng.standard_normal((B, dg * k * k, H, W))))).astype(np.float32)
+    go = rng.standard_normal((B, Co, H, W), dtype=np.float32)
+    out, grads = _run(dcn, x, off, msk, w, b, go, 1, 1, 1, dg)
+    assert rel_err(out, oracle.dcn_forward(x, off, msk, w, b, 1, 1, 1, dg)) < FWD_TOL
+    for name, got, ref in zip(GRADS, grads, oracle.dcn_backward(x, off, msk, w, b, go, 1, 1, 1, dg)):
+        assert rel_err(got, ref) < GRAD_TOL, name
+    out2, grads2 = _run(dcn, x, off, msk, w, b, go, 1, 1, 1, dg)              # and bit-reproducible
+    for a, c in zip(grads, grads2):
+        assert np.array_equal(a, c)
+
+
 @pytest.mark.parametrize("shape", BOX_SHAPES)
 def test_box_backward_against_oracle(dcn, oracle, shape):
     B, H, W, ph, pw, osc, stride, dil = shape
