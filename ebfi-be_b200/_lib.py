@@ -62,6 +62,7 @@ SIGNATURES = {
     "ebfi_events_to_image": (c_int, [c_void] * 4 + [c_int, c_i64, c_int, c_int, c_void, c_int]),
     "ebfi_events_to_mask": (c_int, [c_void] * 4 + [c_int, c_i64, c_int, c_int, c_void, c_void, c_int]),
     "ebfi_events_to_voxel": (c_int, [c_void] * 5 + [c_int, c_i64, c_int, c_int, c_int, c_void, c_int]),
+    "ebfi_events_ts_sum_is_zero": (c_int, [c_void, c_void, c_int, c_i64, c_void, c_void]),
     "ebfi_events_to_stack": (c_int, [c_void] * 5 + [c_int, c_i64, c_int, c_int, c_int, c_void, c_void, c_int, c_void]),
     "ebfi_events_raw_to_stack": (c_int, [c_void] * 5 + [c_i64, c_int, c_int, c_int, c_void, c_void, c_int]),
     "ebfi_frame_to_lap": (c_int, [c_void] * 3 + [c_int] * 3),

@@ -21,6 +21,8 @@
 // order is a few ulp; see tests for the bound).
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace {
 
 using ebfi::ceil_div;
@@ -261,6 +263,49 @@ __global__ void events_stack_kernel(T *__restrict__ xs, T *__restrict__ ys, cons
     }
 }
 
+// flag <- (sum of ts == 0): the other half of events_to_stack's early-out (:319-320). Fixed summation order (per-thread
+// strided partials -> block tree -> the last block adds the block partials in index order), so the value compared with
+// zero is the same on every run; for the non-negative timestamps of the datasets any order gives the same answer.
+constexpr int SUM_BLOCKS = 592, SUM_THREADS = 256;
+template <typename T>
+__global__ void __launch_bounds__(SUM_THREADS)
+events_ts_sum_kernel(const T *__restrict__ ts, int64_t n, double *__restrict__ partial, unsigned *__restrict__ ticket,
+                     unsigned char *__restrict__ flag)
+{
+    __shared__ double sh[SUM_THREADS];
+    __shared__ bool last;
+    // per-thread partial in the dtype of ts (fp64 adds are scarce on this GPU), four independent chains in flight
+    T a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    const int64_t stride = (int64_t)gridDim.x * SUM_THREADS;
+    int64_t i = blockIdx.x * (int64_t)SUM_THREADS + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) { a0 += ts[i]; a1 += ts[i + stride]; a2 += ts[i + 2 * stride]; a3 += ts[i + 3 * stride]; }
+    for (; i < n; i += stride) a0 += ts[i];
+    sh[threadIdx.x] = ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
+    __syncthreads();
+    for (int o = SUM_THREADS / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = sh[0];
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last) {                                          // the last block adds the block partials: fixed tree again
+        __threadfence();
+        double t = 0.0;
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += SUM_THREADS) t += reinterpret_cast<volatile double *>(partial)[b];
+        sh[threadIdx.x] = t;
+        __syncthreads();
+        for (int o = SUM_THREADS / 2; o > 0; o >>= 1) {
+            if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) { *flag = sh[0] == 0.0 ? 1 : 0; *ticket = 0u; }
+    }
+}
+
 unsigned grid_for(int64_t n)
 {
     const int64_t want = ceil_div(n, (int64_t)256);
@@ -328,6 +373,24 @@ int ebfi_events_to_voxel(void *stream, void *xs, void *ys, const void *ts, const
     else
         events_voxel_kernel<double><<<grid_for(n), 256, 0, st>>>((double *)xs, (double *)ys, (const double *)ts, ps, n, num_bins, height, width, voxel, write_back);
     EBFI_LAUNCH_OK("events_voxel_kernel");
+    return EBFI_OK;
+}
+
+int ebfi_events_ts_sum_is_zero(void *stream, const void *ts, int dtype, int64_t n, void *scratch, unsigned char *flag)
+{
+    EBFI_REQUIRE(dtype == EBFI_F32 || dtype == EBFI_F64, "events_ts_sum_is_zero: dtype must be EBFI_F32 or EBFI_F64");
+    EBFI_REQUIRE(n >= 0 && flag && scratch && (n == 0 || ts), "events_ts_sum_is_zero: null pointer");
+    EBFI_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 7u) == 0, "events_ts_sum_is_zero: scratch must be 8-byte aligned");
+    cudaStream_t st = ebfi::as_stream(stream);
+    double *partial = static_cast<double *>(scratch);
+    unsigned *ticket = reinterpret_cast<unsigned *>(partial + SUM_BLOCKS);
+    EBFI_CUDA_OK(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
+    const unsigned grid = (unsigned)std::min<int64_t>(SUM_BLOCKS, std::max<int64_t>(1, ceil_div(n, (int64_t)SUM_THREADS)));
+    if (dtype == EBFI_F32)
+        events_ts_sum_kernel<float><<<grid, SUM_THREADS, 0, st>>>((const float *)ts, n, partial, ticket, flag);
+    else
+        events_ts_sum_kernel<double><<<grid, SUM_THREADS, 0, st>>>((const double *)ts, n, partial, ticket, flag);
+    EBFI_LAUNCH_OK("events_ts_sum_kernel");
     return EBFI_OK;
 }
 

@@ -104,7 +104,10 @@ def events_to_stack(xs, ys, ts, ps, B, sensor_size=(180, 240)):
     with torch.cuda.device(x.device):
         # the other half of the reference's early-out, `ts.sum() == 0`, stays on the device: the
         # kernels read the flag, the host never waits for it
-        skip = (t.sum() == 0).to(torch.uint8)
+        scratch = torch.empty(4800 + 8, dtype=torch.uint8, device=x.device)      # EBFI_EVENTS_SUM_SCRATCH_BYTES + the flag
+        skip = scratch[4800:4801]
+        L.check(L.load().ebfi_events_ts_sum_is_zero(L.stream_ptr(x.device), L.ptr(t), dt, t.numel(), L.ptr(scratch), L.ptr(skip)),
+                "events_ts_sum_is_zero")
         stack = torch.zeros((2, B, H, W), dtype=torch.float32, device=x.device)
         bounds = torch.empty(2 * B, dtype=torch.int64, device=x.device)
         L.check(L.load().ebfi_events_to_stack(L.stream_ptr(x.device), L.ptr(x), L.ptr(y), L.ptr(t), L.ptr(p),

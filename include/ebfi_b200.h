@@ -231,6 +231,13 @@ int ebfi_events_to_voxel(void *stream, void *xs, void *ys, const void *ts, const
                          int dtype, int64_t n_events, int num_bins, int height, int width,
                          float *voxel, int write_back);
 
+/* flag[0] <- (sum of the n timestamps == 0) ? 1 : 0, on the device, in a fixed summation order: the `ts.sum() == 0`
+ * half of events_to_stack's early-out (encodings.py:319-320) as the `skip_flag` of ebfi_events_to_stack.
+ * scratch: EBFI_EVENTS_SUM_SCRATCH_BYTES of 8-byte aligned device memory. */
+#define EBFI_EVENTS_SUM_SCRATCH_BYTES 4800
+int ebfi_events_ts_sum_is_zero(void *stream, const void *ts, int dtype, int64_t n_events, void *scratch,
+                               unsigned char *flag);
+
 /* events_to_stack (encodings.py:307-350): per-bin positive / negative counts.
  * The bin boundaries are found on the device with the reference's own binary
  * search (encodings.py:77-99), so boundary-equal timestamps are counted in both
