@@ -698,10 +698,10 @@ def cpu_baseline(budget_s=20.0):
     rows = int(max(8, min(H, 8 * budget_s / max(td + tf, 1e-6))))
     td, tf = _cpu_step(torch, ref_dcn, oracle, rows, data)
     mpix = (B_DCN + B_FAC) * rows * W / 1e6
-    # encoders: the oracle's serial C port of dataloader/encodings.py on 2 M events (same distribution)
+    # encoders: the oracle's serial C port of dataloader/encodings.py on the same 10 M events distribution
     import numpy as np
     rng = np.random.default_rng(7)
-    n_ev = 2_000_000
+    n_ev = 10_000_000          # BASELINE configs[2] in full: ~1 s of CPU work for the three encoders
     exs = rng.integers(0, 1280, n_ev).astype(np.float32); eys = rng.integers(0, 720, n_ev).astype(np.float32)
     ets = np.sort(rng.random(n_ev)).astype(np.float32); eps_ = (rng.integers(0, 2, n_ev) * 2 - 1).astype(np.float32)
     t0 = time.perf_counter(); oracle.events_to_voxel(exs, eys, ets, eps_, 5, (720, 1280)); t_v = time.perf_counter() - t0
