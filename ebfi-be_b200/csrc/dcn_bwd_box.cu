@@ -280,7 +280,7 @@ __device__ __forceinline__ void sample_bwd(const DcnDims &d, const SampleCtx &sc
 }
 
 // MULTI: more than one 8-channel unit per deformable group (the group's offset / mask gradients accumulate over its units)
-template <bool PACKED, int TPRT, bool MULTI>
+template <bool PACKED, bool MULTI>
 __global__ void __launch_bounds__(NTHR, 1)
 dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__restrict__ wimg,
                    const float *__restrict__ offset, const float *__restrict__ mask,
@@ -621,8 +621,9 @@ dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__rest
             unsigned um = 0u;
             if (next_same_tile) q1 = pass1_begin(nxt);
             int t = t_first, ti = ti_first, tj = tj_first;
-#pragma unroll (TPRT > 0 ? TPRT : 1)
-            for (int sidx = 0; sidx < (TPRT > 0 ? TPRT : pl.TPR) && t < d.KK; ++sidx, ++t) {
+            // rolled on purpose: unrolling it (three samples in flight per thread) measured slower on B200 (238 vs 230 us)
+#pragma unroll 1
+            for (int sidx = 0; sidx < pl.TPR && t < d.KK; ++sidx, ++t) {
                 if (next_same_tile) pass1_tap(nxt, q1, t, ti, tj, um);
                 float gc[8];
                 umma::tmem_ld8(umma::tmem_addr(d1, lane_base, t * 8), gc);     // colgrad[p][t*8 .. t*8+7]
@@ -936,16 +937,14 @@ int backward_box(cudaStream_t st, const DcnDims &d, const float *input, const fl
         if (int rc = tma::encode_3d(tm_mask, mask, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, dims_m, str, box_m)) return rc;
     }
     dim3 grid(box_splits(d, pl), pl.NH);
-#define EBFI_BWD_BOX(P, T, M)                                                                                          \
+#define EBFI_BWD_BOX(P, M)                                                                                             \
     do {                                                                                                               \
-        EBFI_CUDA_OK(cudaFuncSetAttribute(dcn_bwd_box_kernel<P, T, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem)); \
-        dcn_bwd_box_kernel<P, T, M><<<grid, NTHR, pl.smem, st>>>(in_blk, wimg, offset, mask, gout, gin_blk, pbox, goff, gmask, \
-                                                                 gw_part, gb_part, d, pl, tm_box, tm_off, tm_mask);    \
+        EBFI_CUDA_OK(cudaFuncSetAttribute(dcn_bwd_box_kernel<P, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem)); \
+        dcn_bwd_box_kernel<P, M><<<grid, NTHR, pl.smem, st>>>(in_blk, wimg, offset, mask, gout, gin_blk, pbox, goff, gmask, \
+                                                              gw_part, gb_part, d, pl, tm_box, tm_off, tm_mask);       \
     } while (0)
-    // TPRT > 0 unrolls the tap loop (several samples in flight per thread); measured slower on B200 at 3 taps (238 vs
-    // 230 us: register pressure), so the rolled loop serves every shape
-    if (pl.ncs > 1) { if (d.packed) EBFI_BWD_BOX(true, 0, true); else EBFI_BWD_BOX(false, 0, true); }
-    else            { if (d.packed) EBFI_BWD_BOX(true, 0, false); else EBFI_BWD_BOX(false, 0, false); }
+    if (pl.ncs > 1) { if (d.packed) EBFI_BWD_BOX(true, true); else EBFI_BWD_BOX(false, true); }
+    else            { if (d.packed) EBFI_BWD_BOX(true, false); else EBFI_BWD_BOX(false, false); }
 #undef EBFI_BWD_BOX
     EBFI_LAUNCH_OK("dcn_bwd_box_kernel");
     const unsigned cgrid = (unsigned)std::min<size_t>(ceil_div((size_t)BG * HW, (size_t)256), (size_t)ebfi::sm_count() * 16);
