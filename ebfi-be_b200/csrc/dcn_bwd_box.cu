@@ -3,15 +3,16 @@
 //
 // One persistent CTA per SM. CTA (s, h) owns the 8-channel units [h*GPC, h*GPC + GPC) (a unit = one deformable group when the
 // group has 8 channels, else a part of it: its offsets / masks are the group's) and walks the 8 x 16-pixel output tiles
-// s, s+S, ...; an "iteration" is one (tile, unit) — written (tile, group) below. Per tile the grad_output tile is staged ONCE, as bf16 hi/lo pairs
-// in the layout Q[co][px]. The same bytes serve both contractions because kind::f16 accepts MN-major operands in the
+// s, s+S, ...; an "iteration" is one (tile, unit) — written (tile, group) below. Per tile the grad_output tile is staged
+// ONCE, as bf16 hi/lo pairs in the layout Q[co][px]. The same bytes serve both contractions because kind::f16 accepts MN-major operands in the
 // no-swizzle core-matrix layout (probed: tests/test_tcgen05_gpu.py):
 //   GEMM1  colgrad[128 px x 72] = gO_tile . W_g        A = Q read MN-major (M = px, K = co), B = W_g^T image (bulk copy)
 //   GEMM3  gW_g[co x 72]      += gO_tile^T . col       A = [Q_hi ; Q_lo] stacked to M = 128 (K = px), B = col read MN-major
 // so the second grad_output copy of dcn_bwd_tc.cu is gone, a thread writes its 8 column values as ONE 16-byte chunk, and
 // two MMAs per K step yield all four hi/lo products (rows 0-63 and 64-127 of the accumulator are two partial sums).
 // GEMM3 accumulates in TMEM over all tiles of the CTA; an all-ones column gives grad_bias.
-// Per iteration (384 threads, thread = (pixel, tap row)):
+// Warps: 12 samplers (thread = (pixel, tap row)) + 1 issuer that runs every tcgen05 / TMA / bulk-copy instruction, signalled
+// through mbarriers, so that no sampler waits for a single-thread issue loop. Per iteration:
 //   * input: a 24 x 30-pixel box of the group-blocked input arrives by one 3-D TMA copy (zeros outside the image = the
 //     reference's per-corner bounds tests, im2col_cuda.cu:38-48); the four corners of a sample are read with eight
 //     conflict-free LDS.128 in the rotated order of dcn_box.cuh. Offsets and masks of the tile arrive by two more copies.
@@ -24,7 +25,7 @@
 //     scale = 2^30 / (n * M) cannot overflow and resolves a contribution to ~2^-24 of M (n is ~40). Integer addition is
 //     associative, so the box is bit-reproducible.
 //     The box is written — converted back to fp32 — as a dense partial to global memory with plain coalesced stores;
-//     dcn_gin_collect then sums, per input pixel, the <= 9 boxes that cover it in a fixed order and writes NCHW. No global
+//     dcn_gin_collect then sums, per input pixel, the <= 3 x 2 boxes that cover it in a fixed order and writes NCHW. No global
 //     atomics, no order dependence: grad_input is bit-identical run to run, by default.
 //   * samples whose corners leave the box (|offset| beyond ~7 pixels) fall back to 256-bit global loads and
 //     red.global.add.v4.f32 into a blocked fp32 buffer that dcn_gin_collect adds last (order-dependent only then, like
