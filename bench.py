@@ -292,6 +292,16 @@ def run_ours(args):
             op_ms[n] += marks[6 * s + i].elapsed_time(marks[6 * s + i + 1]) / args.steps
         allreduce_wait_ms += marks[6 * s + 4].elapsed_time(marks[6 * s + 5]) / args.steps
 
+    if world > 1:
+        # every rank's own kernel time per step vs its step time: tells a slow device from a late host apart
+        mine = torch.tensor([sum(op_ms.values()), allreduce_wait_ms, t0.elapsed_time(t1) / args.steps], device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [{"rank": i, "kernels_ms": round(float(v[0]), 4), "exchange_wait_ms": round(float(v[1]), 4),
+                     "step_ms": round(float(v[2]), 4)} for i, v in enumerate(allr)]
+    else:
+        per_rank = None
+
     # ---- e2e: autograd Functions, pinned host buffers in and out, copies inside the timed region
     pin = {k: v.pin_memory() for k, v in host.items()}
     res_names = ["out_d", "g_x", "g_off", "g_msk", "g_w", "g_b", "out_f", "g_xi", "g_ker"]
@@ -502,6 +512,7 @@ def run_ours(args):
                 "api": "ebfi_be_b200.host_pipeline (dcn_v2_conv / KernelConv2DFunction autograd, pinned host in/out, "
                        "per-sample H2D | compute | D2H on three streams)"},
         "allreduce_wait_ms": round(allreduce_wait_ms, 4) if world > 1 else None,
+        "per_rank": per_rank,
         "events": events,
         "events_per_rank": enc_scaling,
         "cfg4_inference_720p": cfg4,
