@@ -736,7 +736,7 @@ dcn_bwd_box_kernel(const float *__restrict__ in_blk, const unsigned char *__rest
 // grad_weight[co][k] = sum over the slots of part[slot][k][co], grad_bias likewise: fixed order (four interleaved slot
 // quarters per element, combined in a fixed order), coalesced reads along co.
 // DP: the first half of the data-parallel all-reduce of the two gradients is part of this kernel — the local sums also
-// go to the rank's symmetric buffer and the last block hands them to the peers over NVLink (dp_comm.cuh: no NCCL
+// are stored into every peer's symmetric buffer over NVLink and the last block raises the peers' flags (dp_comm.cuh: no NCCL
 // call, no bucket copies). The outputs hold the local sums until ebfi_dp_complete adds the peers' in rank order.
 template <int DP>
 __global__ void __launch_bounds__(256)
@@ -759,7 +759,7 @@ dcn_box_reduce_partials(const float *__restrict__ gw_part, const float *__restri
     if (DP) {
         epoch = ebfi_dp::epoch_of_launch(v);
         // in the order of the outputs (grad_weight | grad_bias): ebfi_dp_complete works on those two tensors
-        if (q == 0 && e < n_w + CO) ebfi_dp::data(v, v.rank, epoch & 1u)[e < n_w ? (size_t)(e % CO) * Kdim + e / CO : (size_t)e] = a;
+        if (q == 0 && e < n_w + CO) ebfi_dp::push(v, epoch, e < n_w ? (size_t)(e % CO) * Kdim + e / CO : (size_t)e, a);
     }
     if (q == 0) {
         if (e < n_w) gw[(size_t)(e % CO) * Kdim + e / CO] = a;

@@ -19,7 +19,7 @@ int make_view(const ebfi_dp_comm *c, size_t n_floats, View &v)
         EBFI_REQUIRE(q >= c->world || (v.base[q] && (reinterpret_cast<uintptr_t>(v.base[q]) & 255u) == 0),
                      "dp: peer_base[%d] is null or not 256-byte aligned", q);
     }
-    v.cap = (c->bytes - HDR_BYTES) / (2 * sizeof(float));
+    v.cap = (c->bytes - HDR_BYTES) / (2 * MAX_WORLD * sizeof(float));
     return EBFI_OK;
 }
 
@@ -29,9 +29,8 @@ namespace {
 __global__ void __launch_bounds__(256) dp_publish_kernel(View v, const float *a, size_t na, const float *b, size_t nb)
 {
     const unsigned epoch = epoch_of_launch(v);
-    float *mine = data(v, v.rank, epoch & 1u);
     for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < na + nb; e += (size_t)gridDim.x * blockDim.x)
-        mine[e] = e < na ? a[e] : b[e - na];
+        push(v, epoch, e, e < na ? a[e] : b[e - na]);
     publish(v, epoch);
 }
 

@@ -4,16 +4,18 @@
 // host: torch symmetric memory / cudaIpc — plumbing, include/ebfi_b200.h `ebfi_dp_comm`):
 //     [0, 256)        : epoch counter + block ticket (used by the owner only)
 //     [256, 512)      : flags[src rank] (uint32), written by the peers
-//     [512, ...)      : data[parity][capacity] (fp32), written by the owner, read by the peers
+//     [512, ...)      : data[parity][src rank][capacity] (fp32): slot [.][q] is WRITTEN BY RANK q over NVLink, read by the owner
 // publish (any kernel that produces the values; all ranks issue the same sequence): epoch = counter + 1; every block
-// stores its share of the local values into data[epoch & 1], fences and takes a ticket; the LAST block of the grid
+// stores its share of the local values into slot [epoch & 1][my rank] of EVERY rank's buffer (P2P stores: push, not
+// pull — a peer that is saturating its HBM would serve remote loads tens of microseconds late, measured at N = 8),
+// fences (system scope) and takes a ticket; the LAST block of the grid
 // issues one system-scope fence (cumulative over the other blocks' stores, which it observed through the ticket), stores
 // `epoch` into flags[my rank] of every peer (st.release.sys over NVLink) and advances the counter — device side, so
 // the launch can sit in a CUDA graph. It never waits.
 // complete (a tiny kernel at the point of use): waits until flags[q] reached the current epoch for every peer q
-// (ld.acquire.sys on local memory), then reads every rank's data (ld.relaxed.sys — never from a stale L1 line) and adds
-// them in rank order: the sums are identical on all ranks and run to run. Between the two halves the NVLink latency and
-// the skew between the ranks hide behind whatever the stream runs (at most one publish outstanding per communicator).
+// (ld.acquire.sys on local memory), then reads the world slots of its OWN buffer (ld.relaxed.sys — never from a stale L1
+// line; no traffic to the peers at all) and adds them in rank order: the sums are identical on all ranks and run to
+// run. Between the two halves the NVLink latency and the skew between the ranks hide behind whatever the stream runs (at most one publish outstanding per communicator).
 // Double-buffered data: a rank can be at most one publish ahead of a peer, because its complete(e+1) needs the peer's
 // flag e+1, which the peer only sets after its own complete(e) has been issued. Nothing that waits holds up a
 // publish, so the exchange cannot deadlock; a dead peer trips the watchdog (~4 s) into a trap instead of a hang.
@@ -31,10 +33,10 @@ constexpr size_t CTR_BYTES = 256, FLAG_BYTES = 256, HDR_BYTES = CTR_BYTES + FLAG
 struct View {
     int world, rank;
     unsigned char *base[MAX_WORLD];
-    size_t cap;             // floats per parity
+    size_t cap;             // floats per (parity, source rank) slot
 };
 
-inline size_t bytes_for(size_t n_floats) { return HDR_BYTES + 2 * ebfi::round_up(n_floats, (size_t)64) * sizeof(float); }
+inline size_t bytes_for(size_t n_floats) { return HDR_BYTES + 2 * MAX_WORLD * ebfi::round_up(n_floats, (size_t)64) * sizeof(float); }
 
 // host: validate and convert the C struct; world == 1 is allowed (no peers: the exchange degenerates to a copy)
 int make_view(const ebfi_dp_comm *c, size_t n_floats, View &v);
@@ -45,9 +47,15 @@ int allreduce_sum(cudaStream_t st, const View &v, float *a, size_t na, float *b,
 #ifdef __CUDACC__
 __device__ __forceinline__ unsigned *ctr(const View &v) { return reinterpret_cast<unsigned *>(v.base[v.rank]); }
 __device__ __forceinline__ unsigned *flags(const View &v, int q) { return reinterpret_cast<unsigned *>(v.base[q] + CTR_BYTES); }
-__device__ __forceinline__ float *data(const View &v, int q, unsigned parity)
+// slot of source rank `src` inside rank `owner`'s buffer
+__device__ __forceinline__ float *data(const View &v, int owner, unsigned parity, int src)
 {
-    return reinterpret_cast<float *>(v.base[q] + HDR_BYTES) + (size_t)parity * v.cap;
+    return reinterpret_cast<float *>(v.base[owner] + HDR_BYTES) + ((size_t)parity * MAX_WORLD + src) * v.cap;
+}
+// hand value x of element e to every rank (the local copy included)
+__device__ __forceinline__ void push(const View &v, unsigned epoch, size_t e, float x)
+{
+    for (int t = 0; t < v.world; ++t) data(v, t, epoch & 1u, v.rank)[e] = x;
 }
 __device__ __forceinline__ unsigned epoch_of_launch(const View &v) { return *reinterpret_cast<volatile unsigned *>(ctr(v)) + 1u; }
 
@@ -68,14 +76,14 @@ __device__ __forceinline__ float ld_relaxed_sys(const float *p)
     return x;
 }
 
-// Called by ALL threads of EVERY block of the publishing grid after their stores into data(v, rank, epoch & 1): the last
+// Called by ALL threads of EVERY block of the publishing grid after their push() calls: the last
 // block to arrive hands the whole epoch to the peers and advances the counter. blockDim.x >= world.
 __device__ __forceinline__ void publish(const View &v, unsigned epoch)
 {
     __shared__ int last;
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();                                          // this block's data stores before its ticket
+        __threadfence_system();                                   // this block's (peer) data stores before its ticket
         unsigned *c = ctr(v);
         const unsigned nblk = gridDim.x * gridDim.y * gridDim.z;
         last = atomicAdd(c + 1, 1u) == nblk - 1;
@@ -114,7 +122,7 @@ __device__ __forceinline__ void wait_peers(const View &v, unsigned epoch)
 __device__ __forceinline__ float gather_sum(const View &v, unsigned epoch, size_t e)
 {
     float a = 0.f;
-    for (int q = 0; q < v.world; ++q) a += ld_relaxed_sys(data(v, q, epoch & 1u) + e);
+    for (int q = 0; q < v.world; ++q) a += ld_relaxed_sys(data(v, v.rank, epoch & 1u, q) + e);
     return a;
 }
 

@@ -287,8 +287,9 @@ int ebfi_frame_to_dcp(void *stream, const float *frames, float *dark, float *scr
  * grad_bias over the ranks (dcn_v2_cuda.cu:203-208 produces them per rank; the reference never reduces them,
  * train_ours.py:250-272 runs every backward under no_sync). Instead of a separate NCCL call the reduction is done by
  * the kernel that produces the gradients: every rank maps one symmetric allocation of each peer (torch symmetric
- * memory, cudaIpc, ... — the host's plumbing), the kernel publishes its local sums there, exchanges per-block flags
- * and adds the peers' values in rank order (identical bits on every rank and run to run). See csrc/dp_comm.cuh.
+ * memory, cudaIpc, ... — the host's plumbing), the kernel pushes its local sums into every peer's allocation and raises
+ * a flag there; the completing kernel adds the values it received in rank order (identical bits on every rank and run
+ * to run) from local memory only. See csrc/dp_comm.cuh.
  *
  * peer_base[q]: this process's mapping of rank q's allocation (peer_base[rank] = the local one), 256-byte aligned,
  * `bytes` >= ebfi_dp_comm_bytes(n) each, zero-filled ONCE before the first call (and a host barrier after the fill).
