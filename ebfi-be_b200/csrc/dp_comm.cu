@@ -25,7 +25,7 @@ int make_view(const ebfi_dp_comm *c, size_t n_floats, View &v)
 
 namespace {
 
-// a | b (logically concatenated) -> this rank's symmetric buffer, handed to the peers
+// a | b (logically concatenated) -> slot [rank] of every rank's symmetric buffer
 __global__ void __launch_bounds__(256) dp_publish_kernel(View v, const float *a, size_t na, const float *b, size_t nb)
 {
     const unsigned epoch = epoch_of_launch(v);

@@ -292,7 +292,8 @@ int ebfi_frame_to_dcp(void *stream, const float *frames, float *dark, float *scr
  * to run) from local memory only. See csrc/dp_comm.cuh.
  *
  * peer_base[q]: this process's mapping of rank q's allocation (peer_base[rank] = the local one), 256-byte aligned,
- * `bytes` >= ebfi_dp_comm_bytes(n) each, zero-filled ONCE before the first call (and a host barrier after the fill).
+ * `bytes` >= ebfi_dp_comm_bytes(n) each and THE SAME VALUE ON EVERY RANK (the slot layout derives from it), zero-filled
+ * ONCE before the first call (and a host barrier after the fill).
  * Every rank must issue the same sequence of calls on the communicator. world <= 8; world == 1 is a plain copy. */
 typedef struct ebfi_dp_comm {
     int world, rank;
@@ -307,7 +308,7 @@ size_t ebfi_dp_comm_bytes(size_t n_floats);
 int ebfi_dp_allreduce_sum(void *stream, const ebfi_dp_comm *comm, float *a, size_t na, float *b, size_t nb);
 
 /* The same exchange in two halves, so that the NVLink latency and the skew between the ranks hide behind the work in
- * between: publish copies the local values into the symmetric buffer and signals the peers (does not wait);
+ * between: publish stores the local values into every peer's symmetric buffer and signals the peers (does not wait);
  * complete waits for every peer's values of the LAST publish and writes the rank-ordered sums into a / b (same sizes).
  * At most one publish may be outstanding per communicator. */
 int ebfi_dp_publish(void *stream, const ebfi_dp_comm *comm, const float *a, size_t na, const float *b, size_t nb);
